@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the LCAONet hot path on B200 (BASELINE.json metric: molecules/s forward+backward on
+QM9-shape synthetic batches) — see DESIGN.md §Measurement for every definition used here.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one training step over one batch of 1024 synthetic QM9-shaped molecules per GPU
+(index build + forward + backward of the energy MSE loss + gradient all-reduce for N > 1 + fused
+Adam update).  `value` times it with the batch already resident in HBM; `e2e` times the same step
+through the public API starting from pinned HOST tensors (H2D copy of the batch and D2H read of the
+loss inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_KW = dict(cutoff=5.0, cutoff_net="polynomial")  # BASELINE.json configs[1]: default model, hydrogen rbf, poly cutoff 5.0
+WORKLOAD = "QM9-shape synthetic, {m} molecules/GPU (~18 atoms, cutoff 5.0), default LCAONet 128/128/128 x3, energy MSE training step"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_step_time(n_mol: int, reps: int, threads: int | None = None):
+    """fwd+bwd of the oracle (CPU port of the reference) on `n_mol` QM9-shape molecules; best of reps."""
+    from lcaonet_b200 import LCAONet
+    from lcaonet_b200.synth import qm9_like_batch
+    from oracle import lcao_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = dict(emb_size=128, emb_size_coeff=128, emb_size_conv=128, out_size=1, n_interaction=3, n_per_orb=1, cutoff=6.0,
+               rbf_type="hydrogen", cutoff_net="envelope", max_z=36, min_orb=None, max_orb=None, elec_to_node=True,
+               add_valence=False, extend_orb=False, is_extensive=True, regress_forces=False, direct_forces=True)
+    cfg.update(MODEL_KW)
+    torch.manual_seed(0)
+    sd = LCAONet(**MODEL_KW).state_dict()
+    p = O.cast_params(sd, torch.float32, requires_grad=True)
+    g = qm9_like_batch(n_mol, seed=0, cutoff=5.0)
+    y = g["y"]
+    times = []
+    for _ in range(reps + 1):  # first one is the warm-up
+        for v in p.values():
+            if v.grad is not None:
+                v.grad = None
+        t0 = time.perf_counter()
+        out = O.forward(p, cfg, g, training=True)
+        torch.nn.functional.mse_loss(out, y).backward()
+        times.append(time.perf_counter() - t0)
+    return min(times[1:]), times
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU algorithm (oracle port; the reference tree itself is
+    Python and does not travel to the GPU box) timed on the host cores, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_mol = 32  # BASELINE.json configs[0]: the reference's CPU-runnable case; a bounded sample of the workload
+    t0 = time.perf_counter()
+    steps = max(1, args.steps)
+    best, times = cpu_oracle_step_time(n_mol, reps=max(steps, 1) + max(args.warmup - 1, 0), threads=cores)
+    timed = times[-steps:]
+    dt = sum(timed) / len(timed)
+    val = n_mol / dt
+    line = {
+        "impl": "reference", "metric": "molecules/sec fwd+bwd (QM9-shape)", "value": val, "unit": "molecules/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(m=args.mol_per_gpu), "sample": f"{n_mol} molecules per step on host CPU"},
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_mol} QM9-shape molecules, fwd+bwd, mean of {steps} steps"},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, shp):
+    """Compulsory HBM bytes of one launch (FP32), per DESIGN.md §Kernels / SURVEY.md §8d."""
+    E, N, O, C, K, NL = shp["E"], shp["N"], shp["O"], shp["C"], shp["K"], shp["NL"]
+    if name == "lcao_threebody_fwd":  # read B (E,NL,C) + unit + CSR + xk rows; write tbw (E,C)
+        return E * (4 * NL * C + 12 + 8 + 4 * C) + N * (4 * C + 8)
+    if name == "lcao_threebody_bwd":  # read B, d_tbw, unit, CSR, xk; write dB (E,NL,C), q (E,C)
+        return E * (4 * NL * C + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+    if name == "lcao_coeff_contract_fwd":  # read cst' (E,O,C) + rb; write B
+        return E * (4 * O * C + 4 * O + 4 * NL * C)
+    if name == "lcao_coeff_contract_bwd":  # read dB + rb; write d_cst' (E,O,C)
+        return E * (4 * NL * C + 4 * O + 4 * O * C)
+    if name == "lcao_twobody_fwd":
+        return E * (4 * NL * C + 4 * C + 4 * C)
+    if name == "lcao_twobody_bwd":
+        return E * (4 * NL * C + 4 * C + 4 * C + 4 * NL * C + 4 * C)
+    return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from lcaonet_b200 import LCAONet, _lib, ops
+    from lcaonet_b200.dist import FlatGradBucket, broadcast_module
+    from lcaonet_b200.synth import graph_sizes, qm9_like_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly when the CUDA library is missing
+    ops.set_gemm_mode(args.gemm)
+
+    torch.manual_seed(0)
+    model = LCAONet(**MODEL_KW).to(dev).train()
+    model.side_effect_keys = not args.no_side_effect_keys
+    broadcast_module(model)
+    bucket = FlatGradBucket(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+    host = qm9_like_batch(args.mol_per_gpu, seed=1000 + rank, cutoff=5.0).pin_memory()
+    sizes = graph_sizes(host)
+    resident = host.to(dev)
+    y_dev = resident["y"]
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+
+    def step(batch, y):
+        bucket.zero()
+        out = model(batch)
+        loss = torch.nn.functional.mse_loss(out, y)
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- device-resident timing (value)
+    for _ in range(max(args.warmup, 3)):
+        step(GraphClone(resident), y_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_dev = timed(lambda: step(GraphClone(resident), y_dev), args.steps)
+    launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+
+    # ---- end-to-end timing (e2e): pinned host batch -> H2D -> step -> D2H loss
+    def e2e_step():
+        b = host.to(dev, non_blocking=True)
+        loss = step(b, b["y"])
+        return float(loss)  # D2H read of the step's result (synchronises)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel profile of one step (CUDA events around every C-ABI call on the launching stream)
+    prof = profile_step(ops, lambda: step(GraphClone(resident), y_dev), reps=3)
+    total_mols = args.mol_per_gpu * world
+    if rank == 0:
+        peak, peak_src = _peaks()
+        shp = dict(E=sizes["E"], N=sizes["N"], O=model.rbf.n_orb, C=model.emb_size_conv, K=model.emb_size_coeff,
+                   NL=model._n_l)
+        kernels = []
+        step_sum = sum(v["ms"] for v in prof.values())
+        for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            ent = {"call": name, "calls_per_step": v["calls"], "ms_per_step": round(v["ms"], 4),
+                   "share": round(v["ms"] / step_sum, 4)}
+            ab = algorithmic_bytes(name, shp)
+            if ab is not None:
+                gbs = ab / (v["ms"] / v["calls"] * 1e-3) / 1e9
+                ent.update(bytes_per_launch=ab, achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+            elif name.startswith("lcao_linear"):
+                ent.update(bytes_per_step=v["bytes"], achieved_gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                           tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2))
+                ent["frac"] = round(ent["achieved_gbs"] / peak, 4)
+            kernels.append(ent)
+        dom = next((k for k in kernels if "frac" in k), None)
+        roofline = None
+        if dom is not None:
+            per_launch = dom.get("bytes_per_launch", dom.get("bytes_per_step", 0) / max(dom["calls_per_step"], 1))
+            roofline = {"kernel": dom["call"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+                        "share_of_step": dom["share"]}
+        cpu = None
+        if world == 1 or True:
+            best, _ = cpu_oracle_step_time(32, reps=args.cpu_reps, threads=os.cpu_count())
+            cpu = {"value": 32 / best, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"32 QM9-shape molecules (BASELINE configs[0]), fwd+bwd, best of {args.cpu_reps}, oracle port of the reference"}
+        line = {
+            "metric": "molecules/sec fwd+bwd (QM9-shape)", "value": total_mols / (ms_dev * 1e-3), "unit": "molecules/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(m=args.mol_per_gpu), "N": sizes["N"], "E": sizes["E"], "T": sizes["T"],
+                       "gemm_mode": ops.get_gemm_mode(), "side_effect_keys": model.side_effect_keys,
+                       "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": total_mols / (ms_e2e * 1e-3), "unit": "molecules/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+class GraphClone(dict):
+    """Fresh shallow copy of the resident batch per step (forward writes side-effect keys into it)."""
+
+    def __init__(self, src):
+        super().__init__(src)
+
+    def get(self, k, default=None):
+        return super().get(k, default)
+
+
+def profile_step(ops, fn, reps=3):
+    """CUDA-event duration of every C-ABI call of one step, averaged over `reps` steps."""
+    import torch
+
+    records = []
+    orig = ops._call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *a)
+        e1.record()
+        meta = None
+        if name == "lcao_linear_fwd":
+            M, K, Nout = a[8], a[9], a[10]
+            meta = (4 * M * (K + Nout), 2 * M * K * Nout)
+        elif name == "lcao_linear_dgrad":
+            M, K, Nout = a[5], a[6], a[7]
+            meta = (4 * M * (K + Nout), 2 * M * K * Nout)
+        elif name == "lcao_linear_wgrad":
+            M, K, Nout = a[6], a[7], a[8]
+            meta = (4 * M * (K + Nout), 2 * M * K * Nout)
+        records.append((name, e0, e1, meta))
+
+    ops._call = timed_call
+    try:
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+    finally:
+        ops._call = orig
+    out = {}
+    for name, e0, e1, meta in records:
+        d = out.setdefault(name, {"ms": 0.0, "calls": 0, "bytes": 0, "flops": 0})
+        d["ms"] += e0.elapsed_time(e1) / reps
+        d["calls"] += 1
+        if meta:
+            d["bytes"] += meta[0] / reps
+            d["flops"] += meta[1] / reps
+    for d in out.values():
+        d["calls"] = max(d["calls"] // reps, 1)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mol-per-gpu", type=int, default=1024)
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--no-side-effect-keys", action="store_true")
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

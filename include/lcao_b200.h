@@ -1,0 +1,172 @@
+/*
+ * lcao_b200.h — C ABI of the B200-native LCAONet hot path (liblcao_b200.so, sm_100a).
+ *
+ * The reference (nmdl-mizo/lcaonet v0.0.3) is pure Python: it has no FFI.  The boundary a maintainer
+ * would bind is therefore the set of tensor operations its forward pass delegates to ATen /
+ * torch_scatter / torch_sparse; every entry point below names the reference lines it replaces.
+ * INTEGRATION.md shows the ctypes stub that binds them from the reference's own modules.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (LCAO_E_*); `lcao_last_error()` returns a
+ *     thread-local message.  Nothing throws, nothing allocates device memory, no global state
+ *     besides lazily-set kernel attributes: the CALLER owns every buffer (inputs, outputs, scratch).
+ *   - all pointers are device pointers unless marked "host"; all calls are asynchronous on
+ *     `stream` (a cudaStream_t passed as void*), re-entrant across streams.
+ *   - float = IEEE fp32, row-major, innermost dimension contiguous; `ld*` = row stride in elements.
+ *   - graph indices: the public edge list is int64 (2,E) like PyG's; every derived index is int32.
+ *   - "source" s = edge_index[0] (aggregation centre), "target" t = edge_index[1].
+ *   - in-CSR  : edges grouped by TARGET node, inside a node ordered by (source asc, edge id asc)
+ *     out-CSR : edges grouped by SOURCE node, inside a node ordered by edge id asc
+ */
+#ifndef LCAO_B200_H
+#define LCAO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCAO_OK 0
+#define LCAO_E_ARG (-1)      /* bad argument (null pointer, unsupported size) */
+#define LCAO_E_CUDA (-2)     /* CUDA runtime error, see lcao_last_error() */
+#define LCAO_E_UNSUPPORTED (-3)
+
+#define LCAO_MAX_UNIQUE_ORB 18
+#define LCAO_MAX_POLY 8
+#define LCAO_MAX_ORB 64
+
+enum { LCAO_CUT_POLYNOMIAL = 0, LCAO_CUT_ENVELOPE = 1, LCAO_CUT_COSINE = 2 };
+enum { LCAO_RBF_HYDROGEN = 0, LCAO_RBF_SPHERICAL_BESSEL = 1 };
+enum { LCAO_ACT_NONE = 0, LCAO_ACT_SILU = 1 };
+enum { LCAO_GEMM_FP32 = 0, LCAO_GEMM_TF32X3 = 1, LCAO_GEMM_TF32 = 2 };
+
+/* Radial-basis description (host struct, passed by value to the kernel).
+ * orbital o (0 <= o < n_unique*n_rep) uses unique entry o / n_rep  (reference: info.py:124-127). */
+typedef struct {
+  int32_t n_unique, n_rep, cutoff_kind, rbf_kind;
+  double rc, a0;
+  int32_t n[LCAO_MAX_UNIQUE_ORB], l[LCAO_MAX_UNIQUE_ORB], deg[LCAO_MAX_UNIQUE_ORB];
+  double norm[LCAO_MAX_UNIQUE_ORB];               /* s_nl, rbf.py:92-94 */
+  double poly[LCAO_MAX_UNIQUE_ORB][LCAO_MAX_POLY]; /* ascending coefficients of -(n+l)! L_{n-l-1}^{2l+1}, rbf.py:82-87 */
+} lcao_basis_spec;
+
+int lcao_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+int64_t lcao_launch_count(void);
+const char* lcao_last_error(void);
+
+/* ---- index construction -------------------------------------------------------------------- */
+/* Stable bucket sort: perm lists item ids grouped by key, inside a bucket ordered by (sec asc, id asc)
+ * (sec may be NULL).  ptr has nb+1 entries.  scratch: (nb + n) int32.  Replaces the argsort + CSR
+ * machinery of torch_sparse.SparseTensor (reference call site lcaonet.py:462) and the implicit
+ * sort inside torch_scatter-by-batch (lcaonet.py:293).  Bit-exact, deterministic. */
+int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,
+                     int32_t* perm, int32_t* scratch, void* stream);
+
+/* Everything the fused kernels need from edge_index (2,E), in one call:
+ *   src32/dst32 (E)            int32 copies of edge_index rows
+ *   in_ptr (N+1), in_edge (E)  in-CSR;   in_src (E) = src32[in_edge]
+ *   out_ptr (N+1), out_edge (E) out-CSR
+ *   tri_ptr (E+1)  exclusive scan of the triplet count per edge, tri_ptr[E] = T
+ *                  (T = sum_e indeg(s_e) - [s_e == t_e]; reference lcaonet.py:464-473)
+ * scratch: (2*N + 2*E + 8) int32. */
+int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,
+                           int32_t* in_ptr, int32_t* in_edge, int32_t* in_src, int32_t* out_ptr,
+                           int32_t* out_edge, int32_t* tri_ptr, int32_t* scratch, void* stream);
+
+/* Materialise the reference's triplet lists (lcaonet.py:468-485) and, if unit != NULL, the triplet
+ * cosines (lcaonet.py:431-435): for edge e, for e' in in(s_e) with e' != e:
+ *   tri_k = src[e'], e_ks = e', e_st = e, cos = unit[e].unit[e'].   T entries, int64 like the reference. */
+int lcao_triplets_fill(const int32_t* src32, const int32_t* in_ptr, const int32_t* in_edge,
+                       const int32_t* tri_ptr, int64_t E, int64_t* tri_k, int64_t* e_ks, int64_t* e_st,
+                       const float* unit, float* cos_out, void* stream);
+
+/* histogram of small integer keys (pair / species counts for the BatchNorm statistics) */
+int lcao_histogram(const int64_t* keys, int64_t n, int64_t nb, float* counts, void* stream);
+
+/* ---- geometry + radial basis (base.py:27-43, rbf.py:92-103,129-142, cutoff.py:32-67) --------- */
+/* dist (E), unit (E,3), rb (E,O), optional drb (E,O) = d rb / d r (for autograd forces). */
+int lcao_geom_basis_fwd(const float* pos, const float* shift, const float* lattice, const int64_t* batch,
+                        const int32_t* src32, const int32_t* dst32, int64_t E, const lcao_basis_spec* spec_host,
+                        float* dist, float* unit, float* rb, float* drb, void* stream);
+/* backward of the above w.r.t. positions: given d_dist (E, nullable), d_unit (E,3, nullable),
+ * d_rb (E,O, nullable; needs drb) accumulates dvec per edge and reduces it to d_pos (N,3) without
+ * atomics (out-CSR for -dvec at s, in-CSR for +dvec at t).  dvec_scratch: (E,3) float. */
+int lcao_geom_basis_bwd(const float* dist, const float* unit, const float* drb, const float* d_dist,
+                        const float* d_unit, const float* d_rb, int64_t E, int64_t N, int32_t O,
+                        const int32_t* in_ptr, const int32_t* in_edge, const int32_t* out_ptr,
+                        const int32_t* out_edge, float* dvec_scratch, float* d_pos, void* stream);
+
+/* ---- orbital contraction (the einsum "ed,edh->eh" sites lcaonet.py:180-183,200-203) ----------- */
+/* B[e,l,:]  = sum_{o: l(o)=l} rb[e,o] * (A[e,o,:] + m[e,o] V[e,o,:])        l = 0..NL-1
+ * B[e,NL,:] = sum_o rb[e,o] m[e,o] V[e,o,:]                                  (only if valence)
+ * with cst1 (E,O,Cp) = [A | V], Cp = C or 2C; lgrp (O) = l of each orbital; vmask (E,O) 0/1 floats. */
+int lcao_coeff_contract_fwd(const float* cst1, const float* rb, const float* vmask, const int32_t* lgrp,
+                            int64_t E, int32_t O, int32_t C, int32_t NL, int32_t valence, float* B, void* stream);
+/* d_cst1 (E,O,Cp) from dB (E,NG,C); d_rb (E,O) written if non-NULL. */
+int lcao_coeff_contract_bwd(const float* cst1, const float* rb, const float* vmask, const int32_t* lgrp,
+                            const float* dB, int64_t E, int32_t O, int32_t C, int32_t NL, int32_t valence,
+                            float* d_cst1, float* d_rb, void* stream);
+
+/* ---- three-body message passing (lcaonet.py:173-189, shbf.py:75-87) --------------------------- */
+/* tbw[e,:] = sum_{e' in in(s_e), e' != e} normalize( sum_l Y_l(unit[e].unit[e']) B[e',l,:] ) * sigmoid(xk[src[e'],:])
+ * B has NG groups per edge (row stride NG*C); xk (N,C) with row stride ldxk. */
+int lcao_threebody_fwd(const float* B, int32_t NG, const float* unit, const float* xk, int64_t ldxk,
+                       const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+                       const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
+                       int32_t NL, float* tbw, void* stream);
+/* backward: dB (E,NG,C) groups 0..NL-1 are OVERWRITTEN with the three-body contribution (group NL is
+ * zeroed when NG > NL); q (E,C) = per in-edge gradient of the sigmoid gate pre-activation
+ * (d_xk[k] = sum_{e' in out(k)} q[e']); d_unit (E,3) written if non-NULL (needs 2 passes' scratch:
+ * d_unit_st (E,3) partial for the s->t role). */
+int lcao_threebody_bwd(const float* B, int32_t NG, const float* unit, const float* xk, int64_t ldxk,
+                       const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+                       const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
+                       int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks, float* d_unit_st,
+                       void* stream);
+
+/* ---- two-body weight (lcaonet.py:192-204) ----------------------------------------------------- */
+/* p = (1+g[:, :C]) * PA + (1+g[:, C:]) * PV ;  lw = p / max(|p|, 1e-12)
+ * PA = sum_l B[e,l,:] - B[e,NL,:],  PV = B[e,NL,:] (valence) ;  PA = sum_l B[e,l,:] otherwise. */
+int lcao_twobody_fwd(const float* B, int32_t NG, const float* g, int64_t E, int32_t C, int32_t NL,
+                     int32_t valence, float* lw, void* stream);
+int lcao_twobody_bwd(const float* B, int32_t NG, const float* g, const float* d_lw, int64_t E, int32_t C,
+                     int32_t NL, int32_t valence, float* dB, float* d_g, void* stream);
+
+/* ---- edge <- node gathers and node <- edge segment sums (torch_scatter sites lcaonet.py:208,293,307;
+ *      ATen index sites lcaonet.py:209) --------------------------------------------------------- */
+/* out[e,:] = act(a[src[e],:] + b[dst[e],:] + bias) ; pre[e,:] (nullable) = value before act */
+int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, int64_t ldb, const float* bias,
+                       const int32_t* src32, const int32_t* dst32, int64_t E, int32_t C, int32_t act,
+                       float* out, float* pre, void* stream);
+/* out[r,:] = sum_{j in [ptr[r],ptr[r+1])} x[perm[j],:] * (y ? y[perm[j],:] : 1) * scale_r
+ * scale_r = 1 (mean=0) or 1/max(count,1) (mean=1).  Deterministic, no atomics. */
+int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int64_t ldy, const int32_t* ptr,
+                     const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo, void* stream);
+/* out[i,:] = table[idx[i],:] * (mul ? mul[i,:] : 1)   (idx int64 or int32 chosen by idx_is64) */
+int lcao_gather_rows(const float* table, int64_t ldt, const void* idx, int32_t idx_is64, const float* mul, int64_t ldm,
+                     int64_t n, int32_t W, float* out, int64_t ldo, void* stream);
+/* acc[key[i],:] += x[i,:]   (keys int64, few distinct values: pair / species tables; acc pre-zeroed) */
+int lcao_reduce_by_key(const float* x, int64_t ldx, const int32_t* kptr, const int32_t* kperm, int64_t nkeys,
+                       int64_t n, int32_t W, float* acc, void* stream);
+
+/* ---- dense layers (nn/base.py:11-81 = nn.Linear; sites listed in SURVEY.md §8 a-7) ------------- */
+/* Y = act(X W^T + bias); X (M,K) ldx, W (Nout,K) contiguous, Y (M,Nout) ldy; pre (nullable) gets X W^T + bias */
+int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy,
+                    float* pre, int64_t ldp, int64_t M, int32_t K, int32_t Nout, int32_t act, int32_t mode,
+                    void* stream);
+/* dX = dY W  (accumulate=1: dX += ...) */
+int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* W, float* dX, int64_t ldx, int64_t M, int32_t K,
+                      int32_t Nout, int32_t accumulate, int32_t mode, void* stream);
+/* dW (Nout,K) += dY^T X ; db (Nout) += column sums of dY (db nullable).  dW/db must be zeroed by the caller. */
+int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int64_t M,
+                      int32_t K, int32_t Nout, int32_t mode, void* stream);
+/* dH = dY * act'(H)  elementwise over (M,C) with row strides (in place allowed: dH == dY) */
+int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
+                 int32_t C, int32_t act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCAO_B200_H */

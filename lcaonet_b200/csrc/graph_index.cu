@@ -1,0 +1,223 @@
+// Index construction for the LCAO hot path: by-target / by-source CSR, triplet offsets and the
+// reference's triplet lists, all deterministic and bit-exact (integer work, HBM/latency bound).
+// Replaces torch_sparse.SparseTensor at lcaonet.py:462-477 (argsort + CSR select + boolean mask).
+#include "common.cuh"
+
+namespace {
+
+__global__ void k_hist64(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&cnt[keys[i]], 1);
+}
+
+__global__ void k_hist_f(const int64_t* __restrict__ keys, int64_t n, int64_t nb, float* __restrict__ cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    int64_t k = keys[i];
+    if (k >= 0 && k < nb) atomicAdd(&cnt[k], 1.0f);  // integer-valued float adds are exact below 2^24
+  }
+}
+
+// single-CTA exclusive scan; out has n+1 entries (out[n] = total).  in may alias out.
+__global__ void __launch_bounds__(1024) k_exscan(const int32_t* in, int64_t n, int32_t* out) {
+  __shared__ int32_t wsum[32];
+  __shared__ int32_t total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t carry = 0;
+  for (int64_t base = 0; base < n; base += 4096) {
+    int64_t idx = base + (int64_t)threadIdx.x * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
+    int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int32_t s = wsum[lane], inc = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      wsum[lane] = inc - s;
+      if (lane == 31) total = inc;
+    }
+    __syncthreads();
+    int32_t run = carry + wsum[w] + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (idx + j < n) out[idx + j] = run;
+      run += v[j];
+    }
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void k_fill64(const int64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ ptr,
+                         int32_t* __restrict__ cursor, int32_t* __restrict__ tmp) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    int64_t k = keys[i];
+    int32_t p = ptr[k] + atomicAdd(&cursor[k], 1);
+    tmp[p] = (int32_t)i;
+  }
+}
+
+// rank-sort inside each bucket by (sec, id): deterministic whatever order the atomics produced.
+// aux (nullable) receives sec[perm[j]] as int32.
+__global__ void k_rank64(const int64_t* __restrict__ keys, const int64_t* __restrict__ sec, int64_t n,
+                         const int32_t* __restrict__ ptr, const int32_t* __restrict__ tmp,
+                         int32_t* __restrict__ perm, int32_t* __restrict__ aux) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int32_t i = tmp[p];
+  const int64_t b = keys[i];
+  const int64_t si = sec ? sec[i] : 0;
+  const int32_t lo = ptr[b], hi = ptr[b + 1];
+  int32_t rank = 0;
+  for (int32_t q = lo; q < hi; ++q) {
+    const int32_t j = tmp[q];
+    const int64_t sj = sec ? sec[j] : 0;
+    rank += (sj < si) || (sj == si && j < i);
+  }
+  perm[lo + rank] = i;
+  if (aux) aux[lo + rank] = (int32_t)si;
+}
+
+__global__ void k_edge_prep(const int64_t* __restrict__ ei, int64_t E, int32_t* __restrict__ src32,
+                            int32_t* __restrict__ dst32) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  src32[e] = (int32_t)ei[e];
+  dst32[e] = (int32_t)ei[E + e];
+}
+
+__global__ void k_tri_count(const int32_t* __restrict__ src32, const int32_t* __restrict__ dst32,
+                            const int32_t* __restrict__ in_ptr, int64_t E, int32_t* __restrict__ cnt) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int32_t s = src32[e];
+  cnt[e] = in_ptr[s + 1] - in_ptr[s] - (dst32[e] == s ? 1 : 0);
+}
+
+// one warp per edge e: expand its triplets (e' in in(s_e), e' != e) in in-CSR order
+__global__ void k_triplets_fill(const int32_t* __restrict__ src32, const int32_t* __restrict__ in_ptr,
+                                const int32_t* __restrict__ in_edge, const int32_t* __restrict__ tri_ptr, int64_t E,
+                                int64_t* __restrict__ tri_k, int64_t* __restrict__ e_ks, int64_t* __restrict__ e_st,
+                                const float* __restrict__ unit, float* __restrict__ cos_out) {
+  const int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int32_t s = src32[e];
+  const int32_t lo = in_ptr[s], hi = in_ptr[s + 1];
+  const int64_t base = tri_ptr[e];
+  const bool has_self = (tri_ptr[e + 1] - tri_ptr[e]) != (hi - lo);
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (unit) { ux = unit[3 * e]; uy = unit[3 * e + 1]; uz = unit[3 * e + 2]; }
+  int32_t skipped = 0;  // number of dropped entries before the current 32-chunk (0 or 1)
+  for (int32_t j0 = lo; j0 < hi; j0 += 32) {
+    const int32_t j = j0 + lane;
+    int32_t ep = (j < hi) ? in_edge[j] : -1;
+    const bool drop = has_self && (ep == (int32_t)e);
+    const unsigned dm = __ballot_sync(0xffffffffu, drop);
+    const int32_t before = skipped + __popc(dm & ((1u << lane) - 1u));
+    if (j < hi && !drop) {
+      const int64_t o = base + (j - lo) - before;
+      tri_k[o] = src32[ep];
+      e_ks[o] = ep;
+      e_st[o] = e;
+      if (cos_out) cos_out[o] = ux * unit[3 * ep] + uy * unit[3 * ep + 1] + uz * unit[3 * ep + 2];
+    }
+    skipped += __popc(dm);
+  }
+}
+
+int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr, int32_t* perm,
+                     int32_t* aux, int32_t* scratch, cudaStream_t st) {
+  int32_t* cursor = scratch;     // nb
+  int32_t* tmp = scratch + nb;   // n
+  LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
+  if (n > 0) {
+    k_hist64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, cursor);
+    LCAO_LAUNCH_CHECK();
+  }
+  k_exscan<<<1, 1024, 0, st>>>(cursor, nb, ptr);
+  LCAO_LAUNCH_CHECK();
+  if (n > 0) {
+    LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
+    k_fill64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, ptr, cursor, tmp);
+    LCAO_LAUNCH_CHECK();
+    k_rank64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, sec, n, ptr, tmp, perm, aux);
+    LCAO_LAUNCH_CHECK();
+  }
+  return LCAO_OK;
+}
+
+}  // namespace
+
+extern "C" int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,
+                                int32_t* perm, int32_t* scratch, void* stream) {
+  LCAO_REQUIRE(n >= 0 && nb >= 0 && ptr && scratch && (n == 0 || (keys && perm)), "lcao_bucket_sort: bad arguments");
+  LCAO_REQUIRE(n < (1ll << 31) && nb < (1ll << 31), "lcao_bucket_sort: sizes must fit int32");
+  return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,
+                                      int32_t* in_ptr, int32_t* in_edge, int32_t* in_src, int32_t* out_ptr,
+                                      int32_t* out_edge, int32_t* tri_ptr, int32_t* scratch, void* stream) {
+  LCAO_REQUIRE(E >= 0 && N >= 0 && in_ptr && out_ptr && tri_ptr && scratch, "lcao_graph_index_build: null buffer");
+  LCAO_REQUIRE(E == 0 || (edge_index && src32 && dst32 && in_edge && in_src && out_edge),
+               "lcao_graph_index_build: null edge buffer");
+  LCAO_REQUIRE(E < (1ll << 31) && N < (1ll << 31), "lcao_graph_index_build: sizes must fit int32");
+  cudaStream_t st = (cudaStream_t)stream;
+  // in-CSR: key = target, secondary = source ; out-CSR: key = source, secondary none
+  int32_t* scr_in = scratch;               // N + E
+  int32_t* scr_out = scratch + N + E;      // N + E
+  int rc = bucket_sort_impl(edge_index + E, edge_index, E, N, in_ptr, in_edge, in_src, scr_in, st);
+  if (rc) return rc;
+  rc = bucket_sort_impl(edge_index, nullptr, E, N, out_ptr, out_edge, nullptr, scr_out, st);
+  if (rc) return rc;
+  if (E > 0) {
+    k_edge_prep<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(edge_index, E, src32, dst32);
+    LCAO_LAUNCH_CHECK();
+    int32_t* cnt = scr_out;  // E entries, free after the out sort
+    k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, cnt);
+    LCAO_LAUNCH_CHECK();
+    k_exscan<<<1, 1024, 0, st>>>(cnt, E, tri_ptr);
+    LCAO_LAUNCH_CHECK();
+  } else {
+    LCAO_CUDA(cudaMemsetAsync(tri_ptr, 0, sizeof(int32_t), st));
+  }
+  return LCAO_OK;
+}
+
+extern "C" int lcao_triplets_fill(const int32_t* src32, const int32_t* in_ptr, const int32_t* in_edge,
+                                  const int32_t* tri_ptr, int64_t E, int64_t* tri_k, int64_t* e_ks, int64_t* e_st,
+                                  const float* unit, float* cos_out, void* stream) {
+  if (E == 0) return LCAO_OK;
+  LCAO_REQUIRE(src32 && in_ptr && in_edge && tri_ptr && tri_k && e_ks && e_st, "lcao_triplets_fill: null buffer");
+  LCAO_REQUIRE(!cos_out || unit, "lcao_triplets_fill: cos_out needs unit");
+  k_triplets_fill<<<(unsigned)ceil_div64(E * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      src32, in_ptr, in_edge, tri_ptr, E, tri_k, e_ks, e_st, unit, cos_out);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_histogram(const int64_t* keys, int64_t n, int64_t nb, float* counts, void* stream) {
+  LCAO_REQUIRE(counts && nb > 0 && (n == 0 || keys), "lcao_histogram: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  LCAO_CUDA(cudaMemsetAsync(counts, 0, sizeof(float) * nb, st));
+  if (n > 0) {
+    k_hist_f<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, nb, counts);
+    LCAO_LAUNCH_CHECK();
+  }
+  return LCAO_OK;
+}

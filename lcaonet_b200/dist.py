@@ -1,0 +1,46 @@
+"""Data-parallel plumbing: one process per GPU, parameters replicated, ONE flat FP32 gradient bucket
+all-reduced per step over NCCL (NVLink 5 / NVSwitch).  The reference has no distributed code; molecule
+batches are independent, so the only exchange step of training is this gradient sum.
+BatchNorm statistics stay per replica, as they would under DDP with the reference."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket:
+    """Makes every parameter's .grad a view into one contiguous buffer so that the gradient exchange
+    is a single all-reduce with no packing copies."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / dist.get_world_size())
+
+
+def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
+    """Rank `src`'s parameters and buffers to every replica (one-time, at start)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
+def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [lo, hi) slice of `n_items` independent molecules owned by `rank`."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

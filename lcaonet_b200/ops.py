@@ -1,0 +1,450 @@
+"""torch.autograd Functions over the C ABI (include/lcao_b200.h).
+
+
+PyTorch is used for device memory, the current stream and autograd bookkeeping only: every
+edge-sized operation of the hot path (forward and backward) is a call into liblcao_b200.so.
+All functions require CUDA tensors and raise `LcaoError` otherwise — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import Tensor
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, call, ptr, require_cuda, stream_ptr
+
+# GEMM arithmetic mode for the dense layers: fp32 CUDA cores, 3xTF32 tcgen05 (fp32-equivalent), 1xTF32
+GEMM_MODES = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "tf32": _lib.GEMM_TF32}
+_gemm_mode = _lib.GEMM_FP32
+
+# launch counter: every C-ABI compute call increments it (bench.py reports it as gpu_launches)
+n_calls = 0
+
+
+def set_gemm_mode(mode: str) -> None:
+    global _gemm_mode
+    _gemm_mode = GEMM_MODES[mode]
+
+
+def get_gemm_mode() -> str:
+    return {v: k for k, v in GEMM_MODES.items()}[_gemm_mode]
+
+
+def _call(name, *args):
+    global n_calls
+    n_calls += 1
+    call(name, *args)
+
+
+def _rows(x: Tensor) -> Tensor:
+    """2-D view with unit inner stride (copy only if needed)."""
+    if x.dim() != 2:
+        x = x.reshape(-1, x.shape[-1])
+    if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    return x
+
+
+def _ld(x: Tensor) -> int:
+    return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# graph indices
+# ------------------------------------------------------------------------------------------------
+class GraphIndex:
+    """int32 CSR views of `edge_index` built on the GPU (bit-exact, deterministic):
+    in-CSR by target (ordered by source, then edge id), out-CSR by source, triplet offsets.
+    Replaces torch_sparse.SparseTensor in `LCAONet.get_triplets` (reference lcaonet.py:439-486)."""
+
+    def __init__(self, edge_index: Tensor, n_nodes: int):
+        require_cuda(edge_index)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must be an int64 tensor of shape (2, E)")
+        ei = edge_index.contiguous()
+        E, N, dev = ei.shape[1], int(n_nodes), ei.device
+        self.E, self.N, self.edge_index = E, N, ei
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.src32, self.dst32 = torch.empty(E, **i32), torch.empty(E, **i32)
+        self.in_ptr, self.out_ptr = torch.empty(N + 1, **i32), torch.empty(N + 1, **i32)
+        self.in_edge, self.in_src, self.out_edge = torch.empty(E, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
+        self.tri_ptr = torch.empty(E + 1, **i32)
+        scratch = torch.empty(2 * N + 2 * E + 8, **i32)
+        _call("lcao_graph_index_build", ptr(ei), E, N, ptr(self.src32), ptr(self.dst32), ptr(self.in_ptr),
+              ptr(self.in_edge), ptr(self.in_src), ptr(self.out_ptr), ptr(self.out_edge), ptr(self.tri_ptr),
+              ptr(scratch), stream_ptr())
+
+    def num_triplets(self) -> int:
+        return int(self.tri_ptr[-1].item())  # host sync: T is data dependent
+
+    def triplets(self, unit: Tensor | None = None):
+        """(tri_idx_k, edge_idx_ks, edge_idx_st[, cos]) int64 lists in the reference's order."""
+        T, dev = self.num_triplets(), self.src32.device
+        k, e_ks, e_st = (torch.empty(T, dtype=torch.int64, device=dev) for _ in range(3))
+        cos = torch.empty(T, dtype=torch.float32, device=dev) if unit is not None else None
+        _call("lcao_triplets_fill", ptr(self.src32), ptr(self.in_ptr), ptr(self.in_edge), ptr(self.tri_ptr), self.E,
+              ptr(k), ptr(e_ks), ptr(e_st), ptr(unit), ptr(cos), stream_ptr())
+        return (k, e_ks, e_st) if unit is None else (k, e_ks, e_st, cos)
+
+
+def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None):
+    """(ptr int32 (nb+1), perm int32 (n)): items grouped by key, stable in (sec, id)."""
+    require_cuda(keys)
+    keys = keys.contiguous()
+    n, dev = keys.numel(), keys.device
+    p = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(n_buckets + n + 1, dtype=torch.int32, device=dev)
+    _call("lcao_bucket_sort", ptr(keys), ptr(sec.contiguous() if sec is not None else None), n, n_buckets, ptr(p),
+          ptr(perm), ptr(scratch), stream_ptr())
+    return p, perm
+
+
+def histogram(keys: Tensor, n_buckets: int) -> Tensor:
+    require_cuda(keys)
+    out = torch.empty(n_buckets, dtype=torch.float32, device=keys.device)
+    _call("lcao_histogram", ptr(keys.contiguous()), keys.numel(), n_buckets, ptr(out), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry + radial basis
+# ------------------------------------------------------------------------------------------------
+class _GeomBasis(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, shift, lattice, batch, gi: GraphIndex, spec, n_orb: int):
+        require_cuda(pos, shift, lattice)
+        pos_c, shift_c, lat_c = pos.contiguous().float(), shift.contiguous().float(), lattice.contiguous().float()
+        E, dev = gi.E, pos.device
+        dist = torch.empty(E, device=dev)
+        unit = torch.empty(E, 3, device=dev)
+        rb = torch.empty(E, n_orb, device=dev)
+        need_grad = ctx.needs_input_grad[0]
+        drb = torch.empty(E, n_orb, device=dev) if need_grad else None
+        _call("lcao_geom_basis_fwd", ptr(pos_c), ptr(shift_c), ptr(lat_c), ptr(batch), ptr(gi.src32), ptr(gi.dst32), E,
+              ctypes.byref(spec), ptr(dist), ptr(unit), ptr(rb), ptr(drb), stream_ptr())
+        ctx.gi, ctx.n_orb = gi, n_orb
+        ctx.save_for_backward(dist, unit, drb)
+        return dist, unit, rb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_dist, d_unit, d_rb):
+        dist, unit, drb = ctx.saved_tensors
+        gi = ctx.gi
+        if drb is None:
+            return (None,) * 7
+        dev = dist.device
+        dvec = torch.empty(gi.E, 3, device=dev)
+        d_pos = torch.empty(gi.N, 3, device=dev)
+        c = lambda t: t.contiguous() if t is not None else None  # noqa: E731
+        d_dist, d_unit, d_rb = c(d_dist), c(d_unit), c(d_rb)
+        _call("lcao_geom_basis_bwd", ptr(dist), ptr(unit), ptr(drb), ptr(d_dist), ptr(d_unit), ptr(d_rb), gi.E, gi.N,
+              ctx.n_orb, ptr(gi.in_ptr), ptr(gi.in_edge), ptr(gi.out_ptr), ptr(gi.out_edge), ptr(dvec), ptr(d_pos),
+              stream_ptr())
+        return d_pos, None, None, None, None, None, None
+
+
+def geom_basis(pos, shift, lattice, batch, gi, spec, n_orb):
+    return _GeomBasis.apply(pos, shift, lattice, batch, gi, spec, n_orb)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int):
+        require_cuda(x, weight)
+        shape = x.shape
+        x2 = _rows(x)
+        w = weight.contiguous()
+        M, K, Nout = x2.shape[0], x2.shape[1], w.shape[0]
+        y = torch.empty(M, Nout, device=x.device)
+        need_pre = act != ACT_NONE and any(ctx.needs_input_grad)
+        pre = torch.empty(M, Nout, device=x.device) if need_pre else None
+        _call("lcao_linear_fwd", ptr(x2), _ld(x2), ptr(w), ptr(bias), ptr(y), Nout, ptr(pre), Nout, M, K, Nout, act,
+              _gemm_mode, stream_ptr())
+        ctx.act, ctx.shape, ctx.has_bias = act, shape, bias is not None
+        ctx.save_for_backward(x2, w, pre)
+        return y.reshape(*shape[:-1], Nout)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w, pre = ctx.saved_tensors
+        M, K, Nout = x2.shape[0], x2.shape[1], w.shape[0]
+        dy2 = _rows(dy)
+        st = stream_ptr()
+        if ctx.act != ACT_NONE:
+            dh = torch.empty(M, Nout, device=dy.device)
+            _call("lcao_act_bwd", ptr(dy2), _ld(dy2), ptr(pre), Nout, ptr(dh), Nout, M, Nout, ctx.act, st)
+            dy2 = dh
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device)
+            _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), ptr(w), ptr(dx), K, M, K, Nout, 0, _gemm_mode, st)
+            dx = dx.reshape(ctx.shape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros(Nout, K, device=dy.device)
+            db = torch.zeros(Nout, device=dy.device) if ctx.has_bias else None
+            _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), ptr(x2), _ld(x2), ptr(dw), ptr(db), M, K, Nout, _gemm_mode, st)
+        return dx, dw, db, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Tensor | None = None, silu: bool = False) -> Tensor:
+    """act(x W^T + b) — nn.Linear semantics (reference nn/base.py:72-81) with an optional fused SiLU.
+    Requires the feature sizes to be multiples of 4 only for the vector paths; any size works."""
+    return _Linear.apply(x, weight, bias, ACT_SILU if silu else ACT_NONE)
+
+
+# ------------------------------------------------------------------------------------------------
+# orbital contraction, three-body, two-body
+# ------------------------------------------------------------------------------------------------
+class _CoeffContract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cst1, rb, vmask, lgrp, NL: int, C: int):
+        require_cuda(cst1, rb)
+        cst1 = cst1.contiguous()
+        E, O, Cp = cst1.shape
+        valence = 1 if vmask is not None else 0
+        assert Cp == C * (1 + valence)
+        NG = NL + valence
+        B = torch.empty(E, NG, C, device=cst1.device)
+        _call("lcao_coeff_contract_fwd", ptr(cst1), ptr(rb), ptr(vmask), ptr(lgrp), E, O, C, NL, valence, ptr(B),
+              stream_ptr())
+        ctx.dims = (E, O, C, NL, valence)
+        ctx.save_for_backward(cst1, rb, vmask, lgrp)
+        return B
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dB):
+        cst1, rb, vmask, lgrp = ctx.saved_tensors
+        E, O, C, NL, valence = ctx.dims
+        dB = dB.contiguous()
+        d_cst1 = torch.empty_like(cst1)
+        d_rb = torch.empty_like(rb) if ctx.needs_input_grad[1] else None
+        _call("lcao_coeff_contract_bwd", ptr(cst1), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB), E, O, C, NL, valence,
+              ptr(d_cst1), ptr(d_rb), stream_ptr())
+        return d_cst1, d_rb, None, None, None, None
+
+
+def coeff_contract(cst1, rb, vmask, lgrp, NL, C):
+    """B[e,l,:] = sum_{o in l} rb[e,o] (A[e,o,:] + m V[e,o,:]) (+ valence slot) — the orbital sums of
+    lcaonet.py:180-183 and :200-203, grouped by angular momentum so both consumers share them."""
+    return _CoeffContract.apply(cst1, rb.contiguous(), vmask, lgrp, NL, C)
+
+
+class _ThreeBody(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, B, unit, xk, gi: GraphIndex, NL: int):
+        require_cuda(B, unit, xk)
+        E, NG, C = B.shape
+        assert xk.stride(1) == 1
+        tbw = torch.empty(E, C, device=B.device)
+        _call("lcao_threebody_fwd", ptr(B), NG, ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr), ptr(gi.in_edge),
+              ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(tbw), stream_ptr())
+        ctx.gi, ctx.NL = gi, NL
+        ctx.save_for_backward(B, unit, xk)
+        return tbw
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_tbw):
+        B, unit, xk = ctx.saved_tensors
+        gi, NL = ctx.gi, ctx.NL
+        E, NG, C = B.shape
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("gradients w.r.t. edge directions (autograd forces through the three-body "
+                                      "term) are not implemented yet")
+        d_tbw = d_tbw.contiguous()
+        dB = torch.empty_like(B)
+        q = torch.empty(E, C, device=B.device)
+        st = stream_ptr()
+        _call("lcao_threebody_bwd", ptr(B), NG, ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr), ptr(gi.in_edge),
+              ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(d_tbw), ptr(dB), ptr(q), None,
+              None, st)
+        d_xk = torch.empty(gi.N, C, device=B.device)
+        _call("lcao_segment_sum", ptr(q), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, C, 0, ptr(d_xk), C, st)
+        return dB, None, d_xk, None, None
+
+
+def threebody(B, unit, xk, gi, NL):
+    """Fused gather / angular basis / normalise / gate / triplet->edge sum (lcaonet.py:173-189)."""
+    return _ThreeBody.apply(B, unit, xk, gi, NL)
+
+
+class _TwoBody(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, B, g, NL: int, valence: int):
+        require_cuda(B, g)
+        E, NG, C = B.shape
+        g = g.contiguous()
+        lw = torch.empty(E, C, device=B.device)
+        _call("lcao_twobody_fwd", ptr(B), NG, ptr(g), E, C, NL, valence, ptr(lw), stream_ptr())
+        ctx.dims = (NL, valence)
+        ctx.save_for_backward(B, g)
+        return lw
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_lw):
+        B, g = ctx.saved_tensors
+        NL, valence = ctx.dims
+        E, NG, C = B.shape
+        dB, dg = torch.empty_like(B), torch.empty_like(g)
+        _call("lcao_twobody_bwd", ptr(B), NG, ptr(g), ptr(d_lw.contiguous()), E, C, NL, valence, ptr(dB), ptr(dg),
+              stream_ptr())
+        return dB, dg, None, None
+
+
+def twobody(B, g, NL, valence):
+    """lw = normalize((1+g_A) P_A + (1+g_V) P_V) with P = sum_l B_l (lcaonet.py:192-204)."""
+    return _TwoBody.apply(B, g, NL, valence)
+
+
+# ------------------------------------------------------------------------------------------------
+# gathers / segment sums
+# ------------------------------------------------------------------------------------------------
+class _EdgePair(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, bias, gi: GraphIndex, act: int):
+        require_cuda(a, b)
+        assert a.stride(1) == 1 and b.stride(1) == 1
+        C = a.shape[1]
+        out = torch.empty(gi.E, C, device=a.device)
+        need_pre = act != ACT_NONE and any(ctx.needs_input_grad)
+        pre = torch.empty(gi.E, C, device=a.device) if need_pre else None
+        _call("lcao_edge_pair_fwd", ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(bias), ptr(gi.src32), ptr(gi.dst32),
+              gi.E, C, act, ptr(out), ptr(pre), stream_ptr())
+        ctx.gi, ctx.act, ctx.has_bias = gi, act, bias is not None
+        ctx.save_for_backward(pre)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        (pre,) = ctx.saved_tensors
+        gi = ctx.gi
+        d_out = d_out.contiguous()
+        E, C = d_out.shape
+        st = stream_ptr()
+        if ctx.act != ACT_NONE:
+            dh = torch.empty_like(d_out)
+            _call("lcao_act_bwd", ptr(d_out), C, ptr(pre), C, ptr(dh), C, E, C, ctx.act, st)
+            d_out = dh
+        da = torch.empty(gi.N, C, device=d_out.device)
+        db = torch.empty(gi.N, C, device=d_out.device)
+        _call("lcao_segment_sum", ptr(d_out), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, C, 0, ptr(da), C, st)
+        _call("lcao_segment_sum", ptr(d_out), C, None, 0, ptr(gi.in_ptr), ptr(gi.in_edge), gi.N, C, 0, ptr(db), C, st)
+        dbias = da.sum(0) if ctx.has_bias else None
+        return da, db, dbias, None, None
+
+
+def edge_pair(a, b, bias, gi, silu: bool):
+    """act(a[s_e] + b[t_e] + bias): `W [x_s ; x_t] + b` with W split per node (lcaonet.py:209, :304)."""
+    return _EdgePair.apply(a, b, bias, gi, ACT_SILU if silu else ACT_NONE)
+
+
+class _MulSegSum(torch.autograd.Function):
+    """agg[s,:] = sum_{e in out(s)} x[e,:] * y[e,:]   (torch_scatter site lcaonet.py:207-214)."""
+
+    @staticmethod
+    def forward(ctx, x, y, gi: GraphIndex):
+        require_cuda(x, y)
+        x, y = x.contiguous(), y.contiguous()
+        C = x.shape[1]
+        out = torch.empty(gi.N, C, device=x.device)
+        _call("lcao_segment_sum", ptr(x), C, ptr(y), C, ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, C, 0, ptr(out), C,
+              stream_ptr())
+        ctx.gi = gi
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        x, y = ctx.saved_tensors
+        gi = ctx.gi
+        d_out = d_out.contiguous()
+        E, C = x.shape
+        st = stream_ptr()
+        dx, dy = torch.empty_like(x), torch.empty_like(y)
+        _call("lcao_gather_rows", ptr(d_out), C, ptr(gi.src32), 0, ptr(y), C, E, C, ptr(dx), C, st)
+        _call("lcao_gather_rows", ptr(d_out), C, ptr(gi.src32), 0, ptr(x), C, E, C, ptr(dy), C, st)
+        return dx, dy, None
+
+
+def mul_segment_sum(x, y, gi):
+    return _MulSegSum.apply(x, y, gi)
+
+
+class _SegmentReduce(torch.autograd.Function):
+    """out[r] = sum (or mean) of x over the items of segment r; items listed by (ptr, perm), and
+    `seg_of_item` (int64 or int32, n) maps items back to segments for the backward gather."""
+
+    @staticmethod
+    def forward(ctx, x, seg_ptr, seg_perm, seg_of_item, mean: bool):
+        require_cuda(x)
+        x2 = _rows(x)
+        R, C = seg_ptr.numel() - 1, x2.shape[1]
+        out = torch.empty(R, C, device=x.device)
+        _call("lcao_segment_sum", ptr(x2), _ld(x2), None, 0, ptr(seg_ptr), ptr(seg_perm), R, C, 1 if mean else 0,
+              ptr(out), C, stream_ptr())
+        ctx.mean, ctx.n = mean, x2.shape[0]
+        ctx.save_for_backward(seg_ptr, seg_of_item)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        seg_ptr, seg_of_item = ctx.saved_tensors
+        d_out = d_out.contiguous()
+        if ctx.mean:
+            cnt = (seg_ptr[1:] - seg_ptr[:-1]).clamp(min=1).to(d_out.dtype)
+            d_out = d_out / cnt.unsqueeze(-1)
+        C = d_out.shape[1]
+        dx = torch.empty(ctx.n, C, device=d_out.device)
+        _call("lcao_gather_rows", ptr(d_out), C, ptr(seg_of_item), 1 if seg_of_item.dtype == torch.int64 else 0, None,
+              0, ctx.n, C, ptr(dx), C, stream_ptr())
+        return dx, None, None, None, None
+
+
+def segment_reduce(x, seg_ptr, seg_perm, seg_of_item, mean=False):
+    return _SegmentReduce.apply(x, seg_ptr, seg_perm, seg_of_item, mean)
+
+
+class _GatherRows(torch.autograd.Function):
+    """out[i,:] = table[idx[i],:]; backward is a keyed reduction over the (ptr, perm) grouping of idx."""
+
+    @staticmethod
+    def forward(ctx, table, idx, key_ptr, key_perm):
+        require_cuda(table, idx)
+        t2 = table.reshape(table.shape[0], -1)
+        assert t2.stride(1) == 1
+        n, W = idx.numel(), t2.shape[1]
+        out = torch.empty(n, W, device=table.device)
+        _call("lcao_gather_rows", ptr(t2), t2.stride(0), ptr(idx), 1 if idx.dtype == torch.int64 else 0, None, 0, n, W,
+              ptr(out), W, stream_ptr())
+        ctx.tshape = table.shape
+        ctx.save_for_backward(key_ptr, key_perm)
+        return out.reshape(n, *table.shape[1:])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        key_ptr, key_perm = ctx.saved_tensors
+        d2 = d_out.reshape(d_out.shape[0], -1).contiguous()
+        n, W = d2.shape
+        nkeys = ctx.tshape[0]
+        acc = torch.zeros(nkeys, W, device=d_out.device)
+        _call("lcao_reduce_by_key", ptr(d2), W, ptr(key_ptr), ptr(key_perm), nkeys, n, W, ptr(acc), stream_ptr())
+        return acc.reshape(ctx.tshape), None, None, None
+
+
+def gather_rows(table, idx, key_ptr, key_perm):
+    return _GatherRows.apply(table, idx, key_ptr, key_perm)

@@ -39,7 +39,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 def run_case(name, kwargs, graph, training=True):
     res = {"kwargs": kwargs, "training": training,
-           "graph": {k: v for k, v in graph.items()}}
+           "graph": {k: v.detach().clone() for k, v in graph.items()}}
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         torch.manual_seed(0)
         model = RefLCAONet(**kwargs)
@@ -47,7 +47,7 @@ def run_case(name, kwargs, graph, training=True):
             res["state_dict"] = {k: v.clone() for k, v in model.state_dict().items()}
         model = model.to(dtype)
         model.train(training)
-        g = Data(**{k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in graph.items() if k != "y"})
+        g = Data(**{k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in graph.items() if k != "y"})
         out = model(g)
         if isinstance(out, tuple):
             energy, forces = out

@@ -1,0 +1,269 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI,
+against (a) the committed golden vectors of the unmodified reference, (b) the float64 oracle on seeded
+inputs, (c) the per-kernel CPU restatement in tests/cpu_abi.py, and (d) size-independent properties
+at the BASELINE.json batch size.  Integer outputs must be bit-exact; floating point tolerances are
+stated at each assert (FP32 arithmetic, 1e-5 relative on energies per BASELINE.json:north_star)."""
+import pytest
+import torch
+
+from lcaonet_b200 import LCAONet, ops
+from lcaonet_b200.synth import GraphBatch, crystal_like_batch, graph_sizes, qm9_like_batch, reference_fixture_graph
+from oracle import lcao_oracle as O
+from tests import cpu_abi
+from tests._util import full_cfg, graph_as, load_golden, rel_l2, same_triplets_up_to_duplicate_order
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN_CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
+                "fixture_cosine_minmaxorb_atomref"]
+
+
+# ---------------------------------------------------------------------------- index construction
+@pytest.mark.parametrize("maker", [reference_fixture_graph, lambda: qm9_like_batch(16, 2), lambda: crystal_like_batch(2, 1),
+                                   lambda: qm9_like_batch(1024, 0)])
+def test_triplets_bit_exact_vs_oracle(maker):
+    g = maker()
+    ei, n = g["edge_index"], g["z"].shape[0]
+    gi = ops.GraphIndex(ei.to(DEV), n)
+    k, e_ks, e_st = gi.triplets()
+    rk, reks, rest = O.triplets(ei, n)
+    assert gi.num_triplets() == graph_sizes(g)["T"] == rk.numel()
+    assert torch.equal(k.cpu(), rk) and torch.equal(e_ks.cpu(), reks) and torch.equal(e_st.cpu(), rest)
+
+
+def test_triplets_edge_cases():
+    # unsorted sources, self loops, duplicate pairs, isolated nodes, empty graph
+    ei = torch.tensor([[3, 0, 0, 2, 0, 3, 3, 2], [0, 0, 3, 3, 3, 3, 2, 0]])
+    gi = ops.GraphIndex(ei.to(DEV), 6)
+    got = tuple(t.cpu() for t in gi.triplets())
+    ref = O.triplets(ei, 6)
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    gi0 = ops.GraphIndex(torch.zeros(2, 0, dtype=torch.long, device=DEV), 5)
+    assert gi0.num_triplets() == 0 and all(t.numel() == 0 for t in gi0.triplets())
+
+
+def test_golden_triplets_fixture():
+    gold = load_golden("fixture_small")
+    gi = ops.GraphIndex(gold["graph"]["edge_index"].to(DEV), 3)
+    k, e_ks, e_st = gi.triplets()
+    t = gold["triplets"]
+    assert k.tolist() == t["idx_k_3b"].tolist() and e_ks.tolist() == t["edge_idx_ks_3b"].tolist()
+    assert e_st.tolist() == t["edge_idx_st_3b"].tolist()
+
+
+def test_bucket_sort_is_stable_and_exact():
+    torch.manual_seed(0)
+    keys = torch.randint(0, 37, (5000,))
+    sec = torch.randint(0, 11, (5000,))
+    p, perm = ops.bucket_sort(keys.to(DEV), 37, sec.to(DEV))
+    order = torch.argsort(sec, stable=True)
+    order = order[torch.argsort(keys[order], stable=True)]
+    assert torch.equal(perm.cpu().long(), order)
+    assert torch.equal(p.cpu().long()[1:], torch.bincount(keys, minlength=37).cumsum(0))
+
+
+# ---------------------------------------------------------------------------- basis
+@pytest.mark.parametrize("cfgk", [dict(max_z=36, cutoff=5.0, cutoff_net="polynomial"), dict(max_z=36, n_per_orb=2, cutoff=6.0),
+                                  dict(max_z=84, max_orb="6d", cutoff=3.0, cutoff_net="cosine"),
+                                  dict(max_z=12, cutoff=2.0, rbf_type="sphericalbessel")])
+def test_radial_basis_vs_oracle(cfgk):
+    model = LCAONet(emb_size=16, emb_size_coeff=16, emb_size_conv=16, **cfgk)
+    r = torch.linspace(0.05, 7.0, 1500)
+    rb = model.rbf(r.to(DEV)).cpu().double()
+    nl = O.orbital_quantum_numbers(cfgk["max_z"], cfgk.get("max_orb"), cfgk.get("n_per_orb", 1))
+    ref = O.radial_basis(r.double(), nl, cfgk["cutoff"], cfgk.get("cutoff_net", "envelope"), cfgk.get("rbf_type", "hydrogen"))
+    scale = ref.abs().max(0).values.clamp(min=1e-30)
+    assert float(((rb - ref).abs() / scale).max()) < 2e-6  # fp32 rounding of an fp64 evaluation
+    assert torch.all(rb[r > cfgk["cutoff"]] == 0)
+
+
+# ---------------------------------------------------------------------------- per-kernel vs CPU restatement
+def _both(fn, monkeypatch, *cpu_args):
+    """run fn(*args) on the GPU through the real library and on the CPU through the emulator."""
+    gpu_args = [a.to(DEV) if torch.is_tensor(a) else a for a in cpu_args]
+    for a, b in zip(cpu_args, gpu_args):
+        if torch.is_tensor(a) and a.requires_grad:
+            b.requires_grad_(True)
+    out_g = fn(*gpu_args)
+    with monkeypatch.context() as m:
+        cpu_abi.install(m)
+        out_c = fn(*cpu_args)
+    return out_g, out_c, gpu_args
+
+
+@pytest.mark.parametrize("M,K,N,silu,bias", [(1000, 128, 128, True, False), (777, 256, 128, True, True), (64, 128, 256, False, True),
+                                             (333, 64, 1, False, False), (5, 20, 12, True, True), (40000, 128, 128, True, False)])
+def test_linear_fwd_bwd(M, K, N, silu, bias, monkeypatch):
+    torch.manual_seed(M)
+    x = torch.randn(M, K, requires_grad=True)
+    w = (torch.randn(N, K) / K**0.5).requires_grad_(True)
+    b = torch.randn(N, requires_grad=True) if bias else None
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double() if bias else None)
+    ref = torch.nn.functional.silu(ref) if silu else ref
+    gx, gw = torch.autograd.grad((ref**2).sum(), [x, w])
+    xg, wg = x.detach().to(DEV).requires_grad_(True), w.detach().to(DEV).requires_grad_(True)
+    bg = b.detach().to(DEV).requires_grad_(True) if bias else None
+    y = ops.linear(xg, wg, bg, silu)
+    assert rel_l2(y, ref) < 2e-6
+    (y**2).sum().backward()
+    assert rel_l2(xg.grad, gx) < 5e-6 and rel_l2(wg.grad, gw) < 5e-6
+
+
+def _edge_problem(seed=0, n_mol=6, C=32, NL=3, valence=0, crystal=False):
+    g = crystal_like_batch(1, seed, margin=0.05) if crystal else qm9_like_batch(n_mol, seed, margin=0.05)
+    torch.manual_seed(seed)
+    E, N = g["edge_index"].shape[1], g["z"].shape[0]
+    NG = NL + valence
+    B = torch.randn(E, NG, C)
+    unit = torch.nn.functional.normalize(torch.randn(E, 3), dim=1)
+    xk = torch.randn(N, 2 * C)
+    return g, B, unit, xk
+
+
+@pytest.mark.parametrize("C,NL,valence,crystal", [(32, 3, 0, False), (128, 3, 0, False), (128, 3, 1, True), (64, 4, 0, True),
+                                                  (12, 2, 1, False), (256, 1, 0, False)])
+def test_threebody_fwd_bwd_vs_restatement(C, NL, valence, crystal, monkeypatch):
+    g, B, unit, xk = _edge_problem(C=C, NL=NL, valence=valence, crystal=crystal)
+    ei, N = g["edge_index"], g["z"].shape[0]
+
+    def fn(ei, B, unit, xk):
+        B = B.clone().requires_grad_(True)
+        xk = xk.clone().requires_grad_(True)
+        gi = ops.GraphIndex(ei, N)
+        tbw = ops.threebody(B, unit, xk[:, C:], gi, NL)
+        (tbw * torch.linspace(-1, 1, C, device=tbw.device)).sum().backward()
+        return tbw.detach(), B.grad, xk.grad
+
+    (t_g, dB_g, dx_g), (t_c, dB_c, dx_c), _ = _both(fn, monkeypatch, ei, B, unit, xk)
+    assert rel_l2(t_g, t_c) < 2e-6 and rel_l2(dB_g, dB_c) < 1e-5 and rel_l2(dx_g, dx_c) < 1e-5
+
+
+@pytest.mark.parametrize("C,NL,valence", [(128, 3, 0), (128, 3, 1), (32, 4, 1), (256, 2, 0)])
+def test_twobody_and_contract_vs_restatement(C, NL, valence, monkeypatch):
+    torch.manual_seed(1)
+    E, O = 3000, 8
+    Cp = C * (1 + valence)
+    cst1 = torch.randn(E, O, Cp)
+    rb = torch.randn(E, O)
+    rb[::17] = 0.0  # edges beyond the cutoff: zero rows must normalise to zero without NaN
+    vmask = (torch.rand(E, O) > 0.5).float() if valence else None
+    lgrp = torch.randint(0, NL, (O,), dtype=torch.int32)
+    lgrp[0] = NL - 1
+    g = torch.randn(E, Cp)
+
+    def fn(cst1, rb, vmask, lgrp, g):
+        cst1 = cst1.clone().requires_grad_(True)
+        rb = rb.clone().requires_grad_(True)
+        g = g.clone().requires_grad_(True)
+        B = ops.coeff_contract(cst1, rb, vmask, lgrp, NL, C)
+        lw = ops.twobody(B, g, NL, valence)
+        (lw * torch.linspace(-1, 2, C, device=lw.device) + 0.01 * B.sum(1)).sum().backward()
+        return B.detach(), lw.detach(), cst1.grad, rb.grad, g.grad
+
+    out_g, out_c, _ = _both(fn, monkeypatch, cst1, rb, vmask, lgrp, g)
+    for a, b, tol in zip(out_g, out_c, (2e-6, 2e-6, 2e-5, 2e-5, 2e-5)):
+        assert torch.isfinite(a).all() and rel_l2(a, b) < tol
+
+
+def test_edge_gathers_and_segment_sums_vs_restatement(monkeypatch):
+    g = qm9_like_batch(8, 3)
+    ei, N, C = g["edge_index"], g["z"].shape[0], 64
+    torch.manual_seed(2)
+    u, x, y, bias = torch.randn(N, 2 * C), torch.randn(ei.shape[1], C), torch.randn(ei.shape[1], C), torch.randn(C)
+
+    def fn(ei, u, x, y, bias, batch):
+        u, x, y = (t.clone().requires_grad_(True) for t in (u, x, y))
+        bias = bias.clone().requires_grad_(True)
+        gi = ops.GraphIndex(ei, N)
+        a = ops.edge_pair(u[:, :C], u[:, C:], bias, gi, silu=True)
+        agg = ops.mul_segment_sum(x * a, y, gi)
+        seg = (*ops.bucket_sort(batch, 8), batch)
+        pooled = ops.segment_reduce(agg, *seg, mean=True)
+        (pooled**2).sum().backward()
+        return a.detach(), agg.detach(), pooled.detach(), u.grad, x.grad, y.grad, bias.grad
+
+    out_g, out_c, _ = _both(fn, monkeypatch, ei, u, x, y, bias, g["batch"])
+    for a, b in zip(out_g, out_c):
+        assert rel_l2(a, b) < 1e-5
+
+
+# ---------------------------------------------------------------------------- end to end vs the reference
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_model_matches_reference_golden(name):
+    gold = load_golden(name)
+    model = LCAONet(**gold["kwargs"])
+    model.load_state_dict(gold["state_dict"], strict=True)
+    model = model.to(DEV).train(gold["training"])
+    g = GraphBatch(gold["graph"]).to(DEV)
+    out = model(g)
+    if isinstance(out, tuple):
+        energy, forces = out
+        assert rel_l2(forces, gold["forces_f64"]) < 1e-5
+        loss = (energy**2).mean() + (forces**2).mean()
+    else:
+        energy, loss = out, (out**2).mean()
+    # reference FP32's own distance to FP64 on these graphs is 1e-7..1e-6 (printed by make_golden.py)
+    assert rel_l2(energy, gold["energy_f64"]) < 1e-5
+    trip = gold["triplets"]
+    assert same_triplets_up_to_duplicate_order(
+        (g["idx_k_3b"], g["edge_idx_ks_3b"], g["edge_idx_st_3b"]),
+        (trip["idx_k_3b"], trip["edge_idx_ks_3b"], trip["edge_idx_st_3b"]))
+    assert torch.allclose(g["edge_dist"].cpu().double(), gold["edge_dist_f64"], rtol=1e-6, atol=1e-6)
+    loss.backward()
+    worst, worst_ref = 0.0, 0.0
+    for n, p in model.named_parameters():
+        ref = gold["grads_f64"][n]
+        if ref is None or float(ref.norm()) == 0.0:
+            continue
+        worst = max(worst, rel_l2(p.grad, ref))
+        worst_ref = max(worst_ref, gold["grads_f32_rel_to_f64"][n])
+    # per-tensor gradient rel-L2 vs the FP64 reference; the FP32 reference itself sits at `worst_ref`
+    assert worst < max(5e-5, 3 * worst_ref), (worst, worst_ref)
+    if gold["training"]:
+        sd = model.state_dict()
+        for k, v in gold["bn_after_f64"].items():
+            assert torch.allclose(sd[k].cpu().double(), v, rtol=1e-4, atol=1e-5), k
+
+
+def test_node_features_match_oracle_layer_by_layer():
+    kwargs = dict(cutoff=5.0, cutoff_net="polynomial")
+    torch.manual_seed(3)
+    model = LCAONet(**kwargs)
+    g = qm9_like_batch(12, seed=9, margin=0.05)
+    p = O.cast_params(model.state_dict(), torch.float64)
+    trace = {}
+    O.forward(p, full_cfg(kwargs), graph_as(g, torch.float64), training=True, trace=trace)
+    model = model.to(DEV).train()
+    feats = []
+    hooks = [layer.register_forward_hook(lambda m, i, o: feats.append(o.detach())) for layer in model.int_layers]
+    model(g.to(DEV))
+    for h in hooks:
+        h.remove()
+    for i, f in enumerate(feats):
+        assert rel_l2(f, trace[f"x{i + 1}"]) < 1e-5, i
+
+
+# ---------------------------------------------------------------------------- full-size properties
+def test_full_size_batch_properties():
+    """BASELINE.json config 2 shape (1024 QM9-like molecules): determinism, per-molecule additivity
+    (energies of a batch == energies of its halves, eval mode) and finite gradients."""
+    torch.manual_seed(0)
+    model = LCAONet(cutoff=5.0, cutoff_net="polynomial").to(DEV).eval()
+    model.side_effect_keys = False
+    g = qm9_like_batch(1024, seed=0)
+    with torch.no_grad():
+        e1 = model(g.to(DEV))
+        e2 = model(g.to(DEV))
+        assert torch.equal(e1, e2)  # no atomics on the forward path: bitwise reproducible
+        z, b = g["z"], g["batch"]
+        half = int((b < 512).sum())
+        s, t = g["edge_index"]
+        m = s < half
+        lo = GraphBatch(z=z[:half], pos=g["pos"][:half], edge_index=g["edge_index"][:, m], edge_shift=g["edge_shift"][m],
+                        lattice=g["lattice"][:512], batch=b[:half])
+        e_lo = model(lo.to(DEV))
+    assert rel_l2(e_lo, e1[:512]) < 1e-6
+    model.train()
+    out = model(g.to(DEV))
+    (out**2).mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
