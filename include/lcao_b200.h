@@ -57,12 +57,14 @@ int64_t lcao_launch_count(void);
 const char* lcao_last_error(void);
 
 /* ---- index construction -------------------------------------------------------------------- */
-/* Stable bucket sort: perm lists item ids grouped by key, inside a bucket ordered by (sec asc, id asc)
- * (sec may be NULL).  ptr has nb+1 entries.  scratch: (nb + n) int32.  Replaces the argsort + CSR
+/* Bucket sort: perm lists item ids grouped by key; ptr has nb+1 entries; scratch: (nb + n) int32.
+ * stable=1: inside a bucket items are ordered by (sec asc, id asc) (sec may be NULL) — deterministic,
+ *           cost sum_b |b|^2, meant for small buckets (edges per node, atoms per graph).
+ * stable=0: grouping only (order inside a bucket unspecified) — for few huge buckets (species / pair keys).  Replaces the argsort + CSR
  * machinery of torch_sparse.SparseTensor (reference call site lcaonet.py:462) and the implicit
  * sort inside torch_scatter-by-batch (lcaonet.py:293).  Bit-exact, deterministic. */
 int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,
-                     int32_t* perm, int32_t* scratch, void* stream);
+                     int32_t* perm, int32_t* scratch, int32_t stable, void* stream);
 
 /* Everything the fused kernels need from edge_index (2,E), in one call:
  *   src32/dst32 (E)            int32 copies of edge_index rows

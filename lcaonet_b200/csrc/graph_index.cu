@@ -5,9 +5,21 @@
 
 namespace {
 
+// warp-aggregated: lanes holding the same key elect a leader that issues one atomic for the group
+// (few hot keys — species / pair tables — would otherwise serialise on a handful of addresses)
+__device__ __forceinline__ int32_t grouped_atomic_add(int32_t* cnt, int64_t key, bool valid) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? key : (int64_t)-1 - lane);
+  const int leader = __ffs(peers) - 1;
+  int32_t base = 0;
+  if (valid && (int)lane == leader) base = atomicAdd(&cnt[key], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __global__ void k_hist64(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ cnt) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&cnt[keys[i]], 1);
+  grouped_atomic_add(cnt, i < n ? keys[i] : 0, i < n);
 }
 
 __global__ void k_hist_f(const int64_t* __restrict__ keys, int64_t n, int64_t nb, float* __restrict__ cnt) {
@@ -64,11 +76,10 @@ __global__ void __launch_bounds__(1024) k_exscan(const int32_t* in, int64_t n, i
 __global__ void k_fill64(const int64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ ptr,
                          int32_t* __restrict__ cursor, int32_t* __restrict__ tmp) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) {
-    int64_t k = keys[i];
-    int32_t p = ptr[k] + atomicAdd(&cursor[k], 1);
-    tmp[p] = (int32_t)i;
-  }
+  const bool valid = i < n;
+  const int64_t k = valid ? keys[i] : 0;
+  const int32_t off = grouped_atomic_add(cursor, k, valid);
+  if (valid) tmp[ptr[k] + off] = (int32_t)i;
 }
 
 // rank-sort inside each bucket by (sec, id): deterministic whatever order the atomics produced.
@@ -141,7 +152,7 @@ __global__ void k_triplets_fill(const int32_t* __restrict__ src32, const int32_t
 }
 
 int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr, int32_t* perm,
-                     int32_t* aux, int32_t* scratch, cudaStream_t st) {
+                     int32_t* aux, int32_t* scratch, bool stable, cudaStream_t st) {
   int32_t* cursor = scratch;     // nb
   int32_t* tmp = scratch + nb;   // n
   LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
@@ -153,10 +164,12 @@ int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t
   LCAO_LAUNCH_CHECK();
   if (n > 0) {
     LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
-    k_fill64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, ptr, cursor, tmp);
+    k_fill64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, ptr, cursor, stable ? tmp : perm);
     LCAO_LAUNCH_CHECK();
-    k_rank64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, sec, n, ptr, tmp, perm, aux);
-    LCAO_LAUNCH_CHECK();
+    if (stable) {
+      k_rank64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, sec, n, ptr, tmp, perm, aux);
+      LCAO_LAUNCH_CHECK();
+    }
   }
   return LCAO_OK;
 }
@@ -164,10 +177,10 @@ int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t
 }  // namespace
 
 extern "C" int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,
-                                int32_t* perm, int32_t* scratch, void* stream) {
+                                int32_t* perm, int32_t* scratch, int32_t stable, void* stream) {
   LCAO_REQUIRE(n >= 0 && nb >= 0 && ptr && scratch && (n == 0 || (keys && perm)), "lcao_bucket_sort: bad arguments");
   LCAO_REQUIRE(n < (1ll << 31) && nb < (1ll << 31), "lcao_bucket_sort: sizes must fit int32");
-  return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, (cudaStream_t)stream);
+  return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, stable != 0, (cudaStream_t)stream);
 }
 
 extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,
@@ -181,9 +194,9 @@ extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int6
   // in-CSR: key = target, secondary = source ; out-CSR: key = source, secondary none
   int32_t* scr_in = scratch;               // N + E
   int32_t* scr_out = scratch + N + E;      // N + E
-  int rc = bucket_sort_impl(edge_index + E, edge_index, E, N, in_ptr, in_edge, in_src, scr_in, st);
+  int rc = bucket_sort_impl(edge_index + E, edge_index, E, N, in_ptr, in_edge, in_src, scr_in, true, st);
   if (rc) return rc;
-  rc = bucket_sort_impl(edge_index, nullptr, E, N, out_ptr, out_edge, nullptr, scr_out, st);
+  rc = bucket_sort_impl(edge_index, nullptr, E, N, out_ptr, out_edge, nullptr, scr_out, true, st);
   if (rc) return rc;
   if (E > 0) {
     k_edge_prep<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(edge_index, E, src32, dst32);

@@ -193,7 +193,11 @@ class LCAOEmbedding(nn.Module):
         # node embedding: species table -> BN with species counts -> gather
         xtab = _mlp(self.node_embed.f_enc, enc_in.contiguous())
         xtab = _weighted_batch_norm(self.node_embed.bn, xtab, ops.histogram(z, Zd), self.training)
-        x = xtab[z]
+        need_bwd = torch.is_grad_enabled() and xtab.requires_grad
+        if H % 4 == 0:
+            x = ops.gather_rows(xtab.contiguous(), z, *(ops.bucket_sort(z, Zd, stable=False) if need_bwd else (None, None)))
+        else:
+            x = xtab[z]
         # coefficient embedding: pair table (z_s, z_t) -> BN with pair counts -> row gather
         wz = self.coeff_embed.f_z[0].weight  # (K, 2K) acting on [z_s ; z_t]
         za = ops.linear(coeff_z.contiguous(), wz[:, :K].contiguous())
@@ -204,7 +208,7 @@ class LCAOEmbedding(nn.Module):
         ctab = _weighted_batch_norm(self.coeff_embed.bn, pre.reshape(Zd * Zd, O * K), ops.histogram(pair, Zd * Zd),
                                     self.training)
         if torch.is_grad_enabled() and ctab.requires_grad:
-            kptr, kperm = ops.bucket_sort(pair, Zd * Zd)
+            kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
         else:
             kptr = kperm = None
         cst = ops.gather_rows(ctab, pair, kptr, kperm).reshape(-1, O, K)

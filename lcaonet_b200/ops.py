@@ -90,8 +90,9 @@ class GraphIndex:
         return (k, e_ks, e_st) if unit is None else (k, e_ks, e_st, cos)
 
 
-def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None):
-    """(ptr int32 (nb+1), perm int32 (n)): items grouped by key, stable in (sec, id)."""
+def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None, stable: bool = True):
+    """(ptr int32 (nb+1), perm int32 (n)): items grouped by key; stable=True orders each bucket by
+    (sec, id) (small buckets only), stable=False just groups (few huge buckets)."""
     require_cuda(keys)
     keys = keys.contiguous()
     n, dev = keys.numel(), keys.device
@@ -99,7 +100,7 @@ def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None):
     perm = torch.empty(n, dtype=torch.int32, device=dev)
     scratch = torch.empty(n_buckets + n + 1, dtype=torch.int32, device=dev)
     _call("lcao_bucket_sort", ptr(keys), ptr(sec.contiguous() if sec is not None else None), n, n_buckets, ptr(p),
-          ptr(perm), ptr(scratch), stream_ptr())
+          ptr(perm), ptr(scratch), 1 if stable else 0, stream_ptr())
     return p, perm
 
 

@@ -50,7 +50,7 @@ def _bucket_sort(keys, sec, nb):
     return ptr.to(I32), order.to(I32)
 
 
-def lcao_bucket_sort(keys, sec, n, nb, ptr, perm, scratch, stream):
+def lcao_bucket_sort(keys, sec, n, nb, ptr, perm, scratch, stable, stream):
     k = view(keys, n, dtype=I64)
     s = view(sec, n, dtype=I64)
     p, o = _bucket_sort(k if n else torch.empty(0, dtype=I64), s, nb)
