@@ -158,12 +158,15 @@ int lcao_reduce_by_key(const float* x, int64_t ldx, const int32_t* kptr, const i
 int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy,
                     float* pre, int64_t ldp, int64_t M, int32_t K, int32_t Nout, int32_t act, int32_t mode,
                     void* stream);
-/* dX = dY W  (accumulate=1: dX += ...) */
-int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* W, float* dX, int64_t ldx, int64_t M, int32_t K,
-                      int32_t Nout, int32_t accumulate, int32_t mode, void* stream);
-/* dW (Nout,K) += dY^T X ; db (Nout) += column sums of dY (db nullable).  dW/db must be zeroed by the caller. */
-int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int64_t M,
-                      int32_t K, int32_t Nout, int32_t mode, void* stream);
+/* dX = (dY * act'(H)) W   (accumulate=1: dX += ...).  H (M,Nout) = the layer's pre-activation, or NULL /
+ * act = NONE for a plain dY.  The tcgen05 path fuses the act' factor into its operand prologue; the
+ * CUDA-core path needs `scratch` (M*Nout floats, may be NULL when act == NONE). */
+int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W, float* dX,
+                      int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t accumulate, int32_t mode, float* scratch,
+                      void* stream);
+/* dW (Nout,K) += (dY * act'(H))^T X ; db (Nout) += its column sums (db nullable).  dW/db zeroed by the caller. */
+int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
+                      float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode, float* scratch, void* stream);
 /* dH = dY * act'(H)  elementwise over (M,C) with row strides (in place allowed: dH == dY) */
 int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
                  int32_t C, int32_t act, void* stream);

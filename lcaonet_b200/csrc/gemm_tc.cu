@@ -1,0 +1,556 @@
+// tcgen05 (5th-gen tensor core) GEMMs for the dense layers of the LCAO hot path, sm_100a only.
+//
+// Arithmetic: kind::tf32 MMAs with FP32 accumulation in TMEM.  In LCAO_GEMM_TF32X3 mode every FP32
+// operand x is split into hi = x with the 13 low mantissa bits cleared (exactly a TF32 number) and
+// lo = x - hi (cleared the same way), and each product is issued as hi*hi + lo*hi + hi*lo
+// (3 MMAs, error ~2^-21 per product: FP32-equivalent, which the 1e-5 parity bar needs); LCAO_GEMM_TF32
+// issues hi*hi only.
+//
+// Operands never go through TMA: "transform" warps stream the FP32 rows from HBM with coalesced 128-bit
+// loads, apply the fused prologue (identity, or dY * SiLU'(H) for the backward passes), split hi/lo in
+// registers and write both halves straight into the UMMA canonical NO-SWIZZLE shared-memory layouts
+// (K-major for the row-streaming kernel, MN-major for the weight-gradient kernel).  The leading/stride
+// byte offsets are padded by 16 B so those 128-bit shared stores are bank-conflict free.
+//
+// Warp roles (288 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31 -> registers -> HBM),
+// warps 4-7 transform/producer, warp 8 MMA issuer (one elected lane) + TMEM allocator.
+// Pipelines: smem stages full/empty (producer <-> MMA), TMEM accumulator full/empty (MMA <-> epilogue),
+// persistent loop over 128-row blocks (grid = #SMs).  All mbarrier waits are bounded (trap on timeout)
+// so a protocol bug aborts the kernel instead of hanging the GPU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kThreadsTC = (kEpiWarps + kProdWarps + 1) * 32;  // 288
+constexpr int kBlockM = 128;                                   // rows per tile (UMMA M)
+constexpr int kChunkK = 32;                                    // contraction elements per smem stage
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+  hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+  lo = make_float4(tf32_hi(x.x - hi.x), tf32_hi(x.y - hi.y), tf32_hi(x.z - hi.z), tf32_hi(x.w - hi.w));
+}
+__device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
+  return make_float4(g.x * silu_gradf(h.x), g.y * silu_gradf(h.y), g.z * silu_gradf(h.z), g.w * silu_gradf(h.w));
+}
+
+// =================================================================================================
+// Kernel 1: row-streaming GEMM   Y[M, Nb] = epi( pro(A)[M, Kc] * Bop[Kc, Nb] )
+//   forward : A = X, Bop(n, k) = W[n*ldw + k]            (b_trans = 0, W is (Nb, Kc) row-major)
+//   dgrad   : A = dY (* SiLU'(H)), Bop(n, k) = W[k*ldw + n] (b_trans = 1, W is (Kc, Nb) row-major)
+// A and B tiles live in smem as K-major no-swizzle core matrices: element (row, k) at
+//   (k/4)*LBO + row*16 + (k%4)*4   with LBO = rows*16 + 16 (padded), SBO = 128 (8 rows x 16 B)
+// =================================================================================================
+struct RowsArgs {
+  const float* A; int64_t lda;
+  const float* H; int64_t ldh;     // prologue: A *= SiLU'(H) when H != nullptr
+  const float* W; int64_t ldw;
+  const float* bias;
+  float* Y; int64_t ldy;
+  float* pre; int64_t ldp;
+  int64_t M; int Kc; int Nb;
+  int b_trans, act, accumulate, x3, stages;
+};
+
+__global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lboA = kBlockM * 16 + 16, lboB = g.Nb * 16 + 16;
+  const uint32_t halfB = (g.Kc / 4) * lboB;          // bytes of one of {W_hi, W_lo}
+  const uint32_t halfA = (kChunkK / 4) * lboA;        // bytes of one of {A_hi, A_lo} per stage
+  uint8_t* sB = smem_raw;
+  uint8_t* sA = sB + 2 * halfB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)g.stages * 2 * halfA);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + g.stages;
+  uint64_t* tfull = bars + 2 * g.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int64_t nblocks = (g.M + kBlockM - 1) / kBlockM;
+  const int nchunk = g.Kc / kChunkK;
+  const uint32_t tmem_cols = (2 * g.Nb <= 32) ? 32 : (2 * g.Nb <= 64) ? 64 : (2 * g.Nb <= 128) ? 128 : (2 * g.Nb <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full[s], kProdWarps * 32);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+
+  // ---- resident B operand (the layer's weight), split hi/lo once per CTA, by all threads
+  for (int idx = threadIdx.x; idx < g.Nb * (g.Kc / 4); idx += kThreadsTC) {
+    if (!g.b_trans) {
+      const int n = idx / (g.Kc / 4), kg = idx - n * (g.Kc / 4);
+      float4 hi, lo;
+      split4(ldg4(g.W + (int64_t)n * g.ldw + kg * 4), hi, lo);
+      *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
+      *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
+    } else {
+      // W is (Kc, Nb): thread takes contraction group kg (4 rows of W) and one output column n
+      const int kg = idx / g.Nb, n = idx - kg * g.Nb;
+      const float4 w = make_float4(__ldg(g.W + (int64_t)(kg * 4 + 0) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 1) * g.ldw + n),
+                                   __ldg(g.W + (int64_t)(kg * 4 + 2) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 3) * g.ldw + n));
+      float4 hi, lo;
+      split4(w, hi, lo);
+      *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
+      *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // ============================== producer / transform warps ==============================
+    const int t = threadIdx.x - kEpiWarps * 32;  // 0..127
+    const int kg = t & 7, r0 = t >> 3;           // 8 k-groups x 16 row phases
+    uint32_t it = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
+      const int64_t m0 = mb * kBlockM;
+      for (int kc = 0; kc < nchunk; ++kc, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = m0 + r0 + 16 * i;
+          v[i] = (m < g.M) ? ldg4(g.A + m * g.lda + kc * kChunkK + kg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (g.H) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + r0 + 16 * i;
+            if (m < g.M) v[i] = silu_grad4(v[i], ldg4(g.H + m * g.ldh + kc * kChunkK + kg * 4));
+          }
+        }
+        uint8_t* st = sA + (size_t)s * 2 * halfA;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 hi, lo;
+          split4(v[i], hi, lo);
+          const uint32_t off = kg * lboA + (r0 + 16 * i) * 16;
+          *reinterpret_cast<float4*>(st + off) = hi;
+          if (g.x3) *reinterpret_cast<float4*>(st + halfA + off) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, g.Nb, 0, 0);
+      const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+      uint32_t it = 0, tile = 0;
+      for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
+        const int acc = tile & 1;
+        mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * g.Nb;
+        for (int kc = 0; kc < nchunk; ++kc, ++it) {
+          const int s = it % g.stages;
+          mbar_wait(&full[s], (it / g.stages) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = aBase + s * 2 * halfA, a_lo = a_hi + halfA;
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 8; ++kk) {
+            const uint32_t b_hi = bBase + (kc * (kChunkK / 4) + kk * 2) * lboB, b_lo = b_hi + halfB;
+            const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi, lboB, 128);
+            umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
+            if (g.x3) {
+              umma_tf32(d, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, 1);
+              umma_tf32(d, dAh, make_desc(b_lo, lboB, 128), idesc, 1);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps ==============================
+    uint32_t tile = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
+      const int acc = tile & 1;
+      mbar_wait(&tfull[acc], (tile >> 1) & 1);
+      tc_fence_after();
+      const int64_t m = mb * kBlockM + warp * 32 + lane;
+      for (int c0 = 0; c0 < g.Nb; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * g.Nb + c0, v);
+        if (m < g.M) {
+          const int nc = min(32, g.Nb - c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < nc) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (g.bias) {
+                const float4 b = ldg4(g.bias + c0 + j);
+                o = make_float4(o.x + b.x, o.y + b.y, o.z + b.z, o.w + b.w);
+              }
+              if (g.accumulate) {
+                const float4 p = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
+                o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+              }
+              if (g.pre) st4(g.pre + m * g.ldp + c0 + j, o);
+              if (g.act == LCAO_ACT_SILU) o = make_float4(siluf(o.x), siluf(o.y), siluf(o.z), siluf(o.w));
+              st4(g.Y + m * g.ldy + c0 + j, o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =================================================================================================
+// Kernel 2: weight gradient   dW[128, Kx] += sum_m pro(dY)[m, 0:128]^T X[m, 0:Kx] ,  db += colsum(pro(dY))
+// Both operands stream; contraction runs over the rows m.  Tiles are stored MN-major no-swizzle:
+// element (mn, kk) at (mn/4)*SBO + (mn%4)*4 + (kk%8)*16 + (kk/8)*LBO with SBO = 144 (padded),
+// LBO = (#mn/4)*144.  One TMEM accumulator per CTA, flushed with red.global.add at the end.
+// =================================================================================================
+struct WgradArgs {
+  const float* dY; int64_t ldy;
+  const float* H; int64_t ldh;
+  const float* X; int64_t ldx;
+  float* dW; int64_t ldw;
+  float* db;
+  int64_t M; int Kx; int x3, stages;
+};
+
+__global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kSbo = 144;
+  const uint32_t lboA = 32 * kSbo, lboB = (g.Kx / 4) * kSbo;         // bytes per 8-row k-block
+  const uint32_t halfA = (kChunkK / 8) * lboA, halfB = (kChunkK / 8) * lboB;
+  const uint32_t stage_bytes = 2 * halfA + 2 * halfB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)g.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + g.stages;
+  uint64_t* tfull = bars + 2 * g.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const uint32_t tmem_cols = g.Kx <= 32 ? 32 : g.Kx <= 64 ? 64 : g.Kx <= 128 ? 128 : 256;
+
+  // contiguous row range of this CTA, in units of 32 rows
+  const int64_t nchunks = (g.M + kChunkK - 1) / kChunkK;
+  const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c_beg = min(nchunks, (int64_t)blockIdx.x * per), c_end = min(nchunks, c_beg + per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full[s], kProdWarps * 32);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (c_beg >= c_end) {  // nothing to do (more CTAs than row chunks)
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // ============================== producer / transform warps ==============================
+    const int t = threadIdx.x - kEpiWarps * 32;  // 0..127
+    const int grp = t & 31, r0 = t >> 5;         // float4 column group, row phase (4 phases x 8 rows)
+    const int ngB = g.Kx / 4;                    // column groups of X
+    float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t it = 0;
+    for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+      const int s = it % g.stages;
+      mbar_wait(&empty[s], ((it / g.stages) & 1) ^ 1);
+      uint8_t* st = smem_raw + (size_t)s * stage_bytes;
+      const int64_t m0 = c * kChunkK;
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + r0 + 4 * i;
+        a[i] = (m < g.M) ? ldg4(g.dY + m * g.ldy + grp * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (g.H) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = m0 + r0 + 4 * i;
+          if (m < g.M) a[i] = silu_grad4(a[i], ldg4(g.H + m * g.ldh + grp * 4));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 4 * i;  // row inside the 32-row chunk = contraction index kk
+        float4 hi, lo;
+        split4(a[i], hi, lo);
+        colsum = make_float4(colsum.x + a[i].x, colsum.y + a[i].y, colsum.z + a[i].z, colsum.w + a[i].w);
+        const uint32_t off = grp * kSbo + (r & 7) * 16 + (r >> 3) * lboA;
+        *reinterpret_cast<float4*>(st + off) = hi;
+        if (g.x3) *reinterpret_cast<float4*>(st + halfA + off) = lo;
+      }
+      for (int gb = grp; gb < ngB; gb += 32) {
+        float4 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = m0 + r0 + 4 * i;
+          b[i] = (m < g.M) ? ldg4(g.X + m * g.ldx + gb * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 4 * i;
+          float4 hi, lo;
+          split4(b[i], hi, lo);
+          const uint32_t off = 2 * halfA + gb * kSbo + (r & 7) * 16 + (r >> 3) * lboB;
+          *reinterpret_cast<float4*>(st + off) = hi;
+          if (g.x3) *reinterpret_cast<float4*>(st + halfB + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+    if (g.db) {
+      atomicAdd(g.db + grp * 4 + 0, colsum.x);
+      atomicAdd(g.db + grp * 4 + 1, colsum.y);
+      atomicAdd(g.db + grp * 4 + 2, colsum.z);
+      atomicAdd(g.db + grp * 4 + 3, colsum.w);
+    }
+  } else if (warp == 8) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, g.Kx, 1, 1);
+      const uint32_t base = smem_u32(smem_raw);
+      uint32_t it = 0;
+      for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+        const int s = it % g.stages;
+        mbar_wait(&full[s], (it / g.stages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + halfA, b_hi = a_hi + 2 * halfA, b_lo = b_hi + halfB;
+#pragma unroll
+        for (int kk = 0; kk < kChunkK / 8; ++kk) {
+          const uint64_t dAh = make_desc(a_hi + kk * lboA, lboA, kSbo), dBh = make_desc(b_hi + kk * lboB, lboB, kSbo);
+          umma_tf32(tmem_base, dAh, dBh, idesc, (it | kk) != 0);
+          if (g.x3) {
+            umma_tf32(tmem_base, make_desc(a_lo + kk * lboA, lboA, kSbo), dBh, idesc, 1);
+            umma_tf32(tmem_base, dAh, make_desc(b_lo + kk * lboB, lboB, kSbo), idesc, 1);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps: dW[n, :] += acc[n, :] ==============================
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int n = warp * 32 + lane;
+    for (int c0 = 0; c0 < g.Kx; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      const int nc = min(32, g.Kx - c0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nc) atomicAdd(g.dW + (int64_t)n * g.ldw + c0 + j, v[j]);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// ---- eligibility + launchers (called from linear.cu) -------------------------------------------
+// rows kernel: contraction Kc % 32 == 0, output columns Nb % 16 == 0 and <= 128 per launch, weights resident.
+static size_t rows_smem(int Kc, int Nb, int stages) {
+  const size_t halfB = (size_t)(Kc / 4) * (Nb * 16 + 16);
+  const size_t halfA = (size_t)(kChunkK / 4) * (kBlockM * 16 + 16);
+  return 2 * halfB + (size_t)stages * 2 * halfA + 256;
+}
+
+bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y) {
+  return M >= 512 && Kc % 32 == 0 && Kc >= 32 && Nb % 16 == 0 && Nb >= 16 && Nb <= 128 && lda % 4 == 0 && ldy % 4 == 0 &&
+         al16(A) && al16(Y) && rows_smem(Kc, Nb, 2) <= kMaxSmem;
+}
+
+int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const float* W, int64_t ldw, int b_trans,
+                 const float* bias, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
+                 int accumulate, int x3, cudaStream_t st) {
+  RowsArgs g{};
+  g.A = A; g.lda = lda; g.H = H; g.ldh = ldh; g.W = W; g.ldw = ldw; g.bias = bias; g.Y = Y; g.ldy = ldy;
+  g.pre = pre; g.ldp = ldp; g.M = M; g.Kc = Kc; g.Nb = Nb; g.b_trans = b_trans; g.act = act; g.accumulate = accumulate;
+  g.x3 = x3;
+  int stages = 4;
+  while (stages > 2 && rows_smem(Kc, Nb, stages) > kMaxSmem) --stages;
+  g.stages = stages;
+  const size_t smem = rows_smem(Kc, Nb, stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    attr_set = true;
+  }
+  const int64_t nblocks = (M + kBlockM - 1) / kBlockM;
+  const unsigned grid = (unsigned)(nblocks < num_sms() ? nblocks : num_sms());
+  k_tc_rows<<<grid, kThreadsTC, smem, st>>>(g);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+static size_t wgrad_smem(int Kx, int stages) {
+  const size_t halfA = (size_t)(kChunkK / 8) * 32 * 144, halfB = (size_t)(kChunkK / 8) * (Kx / 4) * 144;
+  return (size_t)stages * (2 * halfA + 2 * halfB) + 256;
+}
+
+bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X) {
+  return M >= 512 && Kx % 16 == 0 && Kx >= 16 && Kx <= 256 && ldy % 4 == 0 && ldx % 4 == 0 && al16(dY) && al16(X) &&
+         wgrad_smem(Kx, 2) <= kMaxSmem;
+}
+
+// dW (128 rows of the weight gradient, row stride ldw) += pro(dY[:, 0:128])^T X[:, 0:Kx]
+int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, const float* X, int64_t ldx, float* dW,
+                  int64_t ldw, float* db, int64_t M, int Kx, int x3, cudaStream_t st) {
+  WgradArgs g{};
+  g.dY = dY; g.ldy = ldy; g.H = H; g.ldh = ldh; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db;
+  g.M = M; g.Kx = Kx; g.x3 = x3;
+  int stages = 4;
+  while (stages > 2 && wgrad_smem(Kx, stages) > kMaxSmem) --stages;
+  g.stages = stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCAO_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    attr_set = true;
+  }
+  const int64_t nchunks = (M + kChunkK - 1) / kChunkK;
+  const unsigned grid = (unsigned)(nchunks < num_sms() ? nchunks : num_sms());
+  k_tc_wgrad<<<grid, kThreadsTC, wgrad_smem(Kx, stages), st>>>(g);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}

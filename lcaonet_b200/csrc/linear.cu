@@ -1,4 +1,6 @@
-// C-ABI dispatch for the dense layers (nn/base.py:11-81; call sites SURVEY.md §8 a-7).
+// C-ABI dispatch for the dense layers (nn/base.py:11-81; call sites SURVEY.md §8 a-7):
+// tcgen05 3xTF32 / TF32 kernels (gemm_tc.cu) for the large row-streaming layers, FP32 CUDA-core
+// kernels (gemm_simt.cu) for exact-fp32 mode and for small or unaligned shapes.
 #include "common.cuh"
 
 int lcao_simt_linear_fwd(const float*, int64_t, const float*, const float*, float*, int64_t, float*, int64_t, int64_t,
@@ -7,6 +9,16 @@ int lcao_simt_linear_dgrad(const float*, int64_t, const float*, float*, int64_t,
                            cudaStream_t);
 int lcao_simt_linear_wgrad(const float*, int64_t, const float*, int64_t, float*, float*, int64_t, int32_t, int32_t,
                            cudaStream_t);
+bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y);
+int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const float* W, int64_t ldw, int b_trans,
+                 const float* bias, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
+                 int accumulate, int x3, cudaStream_t st);
+bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
+int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, const float* X, int64_t ldx, float* dW,
+                  int64_t ldw, float* db, int64_t M, int Kx, int x3, cudaStream_t st);
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
 
 extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy,
                                float* pre, int64_t ldp, int64_t M, int32_t K, int32_t Nout, int32_t act, int32_t mode,
@@ -14,22 +26,77 @@ extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, cons
   if (M == 0 || Nout == 0) return LCAO_OK;
   LCAO_REQUIRE(X && W && Y && K > 0, "lcao_linear_fwd: null buffer");
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_fwd: unsupported activation %d", act);
-  (void)mode;
-  return lcao_simt_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = mode != LCAO_GEMM_FP32 && Nout % 16 == 0 && K <= 128 && al16(W) && (!bias || al16(bias)) &&
+                  (!pre || (al16(pre) && ldp % 4 == 0)) && lcao_tc_rows_ok(M, K, imin(Nout, 128), ldx, ldy, X, Y);
+  if (!tc) return lcao_simt_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, st);
+  for (int n0 = 0; n0 < Nout; n0 += 128) {
+    const int nb = imin(128, Nout - n0);
+    int rc = lcao_tc_rows(X, ldx, nullptr, 0, W + (int64_t)n0 * K, K, 0, bias ? bias + n0 : nullptr, Y + n0, ldy,
+                          pre ? pre + n0 : nullptr, ldp, M, K, nb, act, 0, mode == LCAO_GEMM_TF32X3, st);
+    if (rc) return rc;
+  }
+  return LCAO_OK;
 }
 
-extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* W, float* dX, int64_t ldx, int64_t M,
-                                 int32_t K, int32_t Nout, int32_t accumulate, int32_t mode, void* stream) {
+// run the un-fused SiLU' pass into the caller's scratch (CUDA-core path only)
+static int act_bwd_to_scratch(const float*& dY, int64_t& ldy, const float* H, int64_t ldh, int32_t act, int64_t M,
+                              int32_t Nout, float* scratch, void* stream, const char* who) {
+  if (act == LCAO_ACT_NONE || !H) return LCAO_OK;
+  LCAO_REQUIRE(scratch, "%s: the CUDA-core path needs an (M, Nout) scratch buffer for dY * act'(H)", who);
+  int rc = lcao_act_bwd(dY, ldy, H, ldh, scratch, Nout, M, Nout, act, stream);
+  if (rc) return rc;
+  dY = scratch;
+  ldy = Nout;
+  return LCAO_OK;
+}
+
+extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
+                                 float* dX, int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t accumulate,
+                                 int32_t mode, float* scratch, void* stream) {
   if (M == 0 || K == 0) return LCAO_OK;
   LCAO_REQUIRE(dY && W && dX && Nout > 0, "lcao_linear_dgrad: null buffer");
-  (void)mode;
-  return lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, accumulate, (cudaStream_t)stream);
+  LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_dgrad: unsupported activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fuse = act != LCAO_ACT_NONE && H;
+  const bool tc = mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) && (!fuse || (al16(H) && ldh % 4 == 0)) &&
+                  lcao_tc_rows_ok(M, imin(Nout, 128), imin(K, 128), ldy, ldx, dY, dX);
+  if (!tc) {
+    int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_dgrad");
+    if (rc) return rc;
+    return lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, accumulate, st);
+  }
+  for (int n0 = 0; n0 < K; n0 += 128) {          // output columns
+    const int nb = imin(128, K - n0);
+    for (int c0 = 0; c0 < Nout; c0 += 128) {     // contraction chunks
+      const int kc = imin(128, Nout - c0);
+      int rc = lcao_tc_rows(dY + c0, ldy, fuse ? H + c0 : nullptr, ldh, W + (int64_t)c0 * K + n0, K, 1, nullptr, dX + n0,
+                            ldx, nullptr, 0, M, kc, nb, LCAO_ACT_NONE, accumulate || c0 > 0, mode == LCAO_GEMM_TF32X3, st);
+      if (rc) return rc;
+    }
+  }
+  return LCAO_OK;
 }
 
-extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db,
-                                 int64_t M, int32_t K, int32_t Nout, int32_t mode, void* stream) {
+extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X,
+                                 int64_t ldx, float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode,
+                                 float* scratch, void* stream) {
   if (M == 0 || K == 0 || Nout == 0) return LCAO_OK;
   LCAO_REQUIRE(dY && X && dW, "lcao_linear_wgrad: null buffer");
-  (void)mode;
-  return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, (cudaStream_t)stream);
+  LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_wgrad: unsupported activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fuse = act != LCAO_ACT_NONE && H;
+  const bool tc = mode != LCAO_GEMM_FP32 && Nout % 128 == 0 && (!fuse || (al16(H) && ldh % 4 == 0)) &&
+                  lcao_tc_wgrad_ok(M, K, ldy, ldx, dY, X);
+  if (!tc) {
+    int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_wgrad");
+    if (rc) return rc;
+    return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
+  }
+  for (int n0 = 0; n0 < Nout; n0 += 128) {
+    int rc = lcao_tc_wgrad(dY + n0, ldy, fuse ? H + n0 : nullptr, ldh, X, ldx, dW + (int64_t)n0 * K, K,
+                           db ? db + n0 : nullptr, M, K, mode == LCAO_GEMM_TF32X3, st);
+    if (rc) return rc;
+  }
+  return LCAO_OK;
 }

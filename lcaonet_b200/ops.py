@@ -180,19 +180,20 @@ class _Linear(torch.autograd.Function):
         M, K, Nout = x2.shape[0], x2.shape[1], w.shape[0]
         dy2 = _rows(dy)
         st = stream_ptr()
-        if ctx.act != ACT_NONE:
-            dh = torch.empty(M, Nout, device=dy.device)
-            _call("lcao_act_bwd", ptr(dy2), _ld(dy2), ptr(pre), Nout, ptr(dh), Nout, M, Nout, ctx.act, st)
-            dy2 = dh
+        # dY * SiLU'(pre) is fused into the tcgen05 operand prologue; only the CUDA-core path uses scratch
+        fused_tc = _gemm_mode != _lib.GEMM_FP32 and M >= 512
+        scratch = torch.empty(M, Nout, device=dy.device) if (ctx.act != ACT_NONE and not fused_tc) else None
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device)
-            _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), ptr(w), ptr(dx), K, M, K, Nout, 0, _gemm_mode, st)
+            _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(w), ptr(dx), K, M, K, Nout, 0,
+                  _gemm_mode, ptr(scratch), st)
             dx = dx.reshape(ctx.shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros(Nout, K, device=dy.device)
             db = torch.zeros(Nout, device=dy.device) if ctx.has_bias else None
-            _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), ptr(x2), _ld(x2), ptr(dw), ptr(db), M, K, Nout, _gemm_mode, st)
+            _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(x2), _ld(x2), ptr(dw), ptr(db), M,
+                  K, Nout, _gemm_mode, ptr(scratch), st)
         return dx, dw, db, None
 
 

@@ -378,14 +378,23 @@ def lcao_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, mode, st
     view(Y, M, Nout, ld=ldy).copy_(_act(v, act))
 
 
-def lcao_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, accumulate, mode, stream):
-    v = view(dY, M, Nout, ld=ldy) @ view(W, Nout, K)
+def _dy_eff(dY, ldy, H, ldh, act, M, Nout):
+    d = view(dY, M, Nout, ld=ldy)
+    if act == 1 and H:
+        h = view(H, M, Nout, ld=ldh)
+        s = torch.sigmoid(h)
+        d = d * (s * (1 + h * (1 - s)))
+    return d
+
+
+def lcao_linear_dgrad(dY, ldy, H, ldh, act, W, dX, ldx, M, K, Nout, accumulate, mode, scratch, stream):
+    v = _dy_eff(dY, ldy, H, ldh, act, M, Nout) @ view(W, Nout, K)
     o = view(dX, M, K, ld=ldx)
     o.copy_(o + v if accumulate else v)
 
 
-def lcao_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, mode, stream):
-    d = view(dY, M, Nout, ld=ldy)
+def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, scratch, stream):
+    d = _dy_eff(dY, ldy, H, ldh, act, M, Nout)
     view(dW, Nout, K).add_(d.t() @ view(X, M, K, ld=ldx))
     if db:
         view(db, Nout).add_(d.sum(0))

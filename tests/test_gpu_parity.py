@@ -267,3 +267,52 @@ def test_full_size_batch_properties():
     out = model(g.to(DEV))
     (out**2).mean().backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+# ---------------------------------------------------------------------------- tcgen05 GEMMs
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 3e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("M,K,N,silu,bias", [(5000, 128, 128, True, False), (4173, 128, 256, True, True), (3000, 64, 128, False, True),
+                                             (2000, 32, 16, True, False), (1500, 128, 48, False, False), (600, 96, 128, True, True),
+                                             (300000, 128, 128, True, False)])
+def test_linear_tensor_core_modes(mode, tol, M, K, N, silu, bias):
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K**0.5
+    b = torch.randn(N, device=DEV) if bias else None
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True) if bias else None
+    ref = torch.nn.functional.linear(xd, wd, bd)
+    ref = torch.nn.functional.silu(ref) if silu else ref
+    probe = torch.randn(M, N, device=DEV, dtype=torch.float64)
+    grads = torch.autograd.grad((ref * probe).sum(), [xd, wd] + ([bd] if bias else []))
+    ops.set_gemm_mode(mode)
+    try:
+        xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        bg = b.clone().requires_grad_(True) if bias else None
+        y = ops.linear(xg, wg, bg, silu)
+        (y * probe.float()).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("fp32")
+    assert rel_l2(y, ref) < tol
+    assert rel_l2(xg.grad, grads[0]) < 2 * tol and rel_l2(wg.grad, grads[1]) < 2 * tol
+    if bias:
+        assert rel_l2(bg.grad, grads[2]) < 2 * tol
+
+
+def test_model_golden_with_tf32x3_gemms():
+    gold = load_golden("qm9_default")
+    model = LCAONet(**gold["kwargs"])
+    model.load_state_dict(gold["state_dict"], strict=True)
+    model = model.to(DEV).train()
+    ops.set_gemm_mode("tf32x3")
+    try:
+        out = model(GraphBatch(gold["graph"]).to(DEV))
+        (out**2).mean().backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("fp32")
+    assert rel_l2(out, gold["energy_f64"]) < 1e-5
+    worst = max(rel_l2(p.grad, gold["grads_f64"][n]) for n, p in model.named_parameters()
+                if gold["grads_f64"][n] is not None and float(gold["grads_f64"][n].norm()) > 0)
+    assert worst < 5e-5, worst
