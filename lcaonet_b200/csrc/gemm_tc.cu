@@ -8,9 +8,9 @@
 //
 // Operands never go through TMA: "transform" warps stream the FP32 rows from HBM with coalesced 128-bit
 // loads, apply the fused prologue (identity, or dY * SiLU'(H) for the backward passes), split hi/lo in
-// registers and write both halves straight into the UMMA canonical NO-SWIZZLE shared-memory layouts
-// (K-major for the row-streaming kernel, MN-major for the weight-gradient kernel).  The leading/stride
-// byte offsets are padded by 16 B so those 128-bit shared stores are bank-conflict free.
+// registers and write both halves straight into the UMMA canonical NO-SWIZZLE K-major shared-memory
+// layout (the weight-gradient kernel transposes 4x4 blocks in registers on the way).  The leading byte
+// offset is padded by 16 B so those 128-bit shared stores are bank-conflict free.
 //
 // Warp roles (288 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31 -> registers -> HBM),
 // warps 4-7 transform/producer, warp 8 MMA issuer (one elected lane) + TMEM allocator.
@@ -311,9 +311,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
 
 // =================================================================================================
 // Kernel 2: weight gradient   dW[128, Kx] += sum_m pro(dY)[m, 0:128]^T X[m, 0:Kx] ,  db += colsum(pro(dY))
-// Both operands stream; contraction runs over the rows m.  Tiles are stored MN-major no-swizzle:
-// element (mn, kk) at (mn/4)*SBO + (mn%4)*4 + (kk%8)*16 + (kk/8)*LBO with SBO = 144 (padded),
-// LBO = (#mn/4)*144.  One TMEM accumulator per CTA, flushed with red.global.add at the end.
+// Both operands stream; the contraction runs over the rows m, so the row-major HBM tiles have to be
+// TRANSPOSED into the K-major layout of kernel 1: element (col, m) at (m/4)*LBO + col*16 + (m%4)*4.
+// Each transform thread owns 4x4 blocks (4 consecutive rows x 4 consecutive columns): four 128-bit
+// loads, a register transpose, four 128-bit shared stores; lanes of a quarter-warp differ in the row
+// group, so the padded LBO keeps the stores conflict free.  One TMEM accumulator per CTA (its row
+// range is contiguous), flushed with red.global.add at the end.
 // =================================================================================================
 struct WgradArgs {
   const float* dY; int64_t ldy;
@@ -324,12 +327,24 @@ struct WgradArgs {
   int64_t M; int Kx; int x3, stages;
 };
 
+__device__ __forceinline__ void store_transposed(uint8_t* base, uint32_t half, bool x3, const float4 (&r)[4]) {
+  // r[i] = row i, 4 consecutive columns;  column j becomes one 16-byte K-vector (rows 0..3)
+  const float4 c[4] = {make_float4(r[0].x, r[1].x, r[2].x, r[3].x), make_float4(r[0].y, r[1].y, r[2].y, r[3].y),
+                       make_float4(r[0].z, r[1].z, r[2].z, r[3].z), make_float4(r[0].w, r[1].w, r[2].w, r[3].w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 hi, lo;
+    split4(c[j], hi, lo);
+    *reinterpret_cast<float4*>(base + j * 16) = hi;
+    if (x3) *reinterpret_cast<float4*>(base + half + j * 16) = lo;
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t kSbo = 144;
-  const uint32_t lboA = 32 * kSbo, lboB = (g.Kx / 4) * kSbo;         // bytes per 8-row k-block
-  const uint32_t halfA = (kChunkK / 8) * lboA, halfB = (kChunkK / 8) * lboB;
+  const uint32_t lboA = 128 * 16 + 16, lboB = g.Kx * 16 + 16;
+  const uint32_t halfA = (kChunkK / 4) * lboA, halfB = (kChunkK / 4) * lboB;
   const uint32_t stage_bytes = 2 * halfA + 2 * halfB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)g.stages * stage_bytes);
   uint64_t* full = bars;
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (c_beg >= c_end) {  // nothing to do (more CTAs than row chunks)
+  if (c_beg >= c_end) {  // more CTAs than row chunks: nothing to do
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
     return;
@@ -365,68 +380,61 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
   if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
     // ============================== producer / transform warps ==============================
     const int t = threadIdx.x - kEpiWarps * 32;  // 0..127
-    const int grp = t & 31, r0 = t >> 5;         // float4 column group, row phase (4 phases x 8 rows)
-    const int ngB = g.Kx / 4;                    // column groups of X
-    float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kg = t & 7, g0 = t >> 3;           // row group (4 rows) x first column group
+    const int ngB = g.Kx / 4;
+    float4 colsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     uint32_t it = 0;
     for (int64_t c = c_beg; c < c_end; ++c, ++it) {
       const int s = it % g.stages;
       mbar_wait(&empty[s], ((it / g.stages) & 1) ^ 1);
       uint8_t* st = smem_raw + (size_t)s * stage_bytes;
-      const int64_t m0 = c * kChunkK;
-      float4 a[8];
+      const int64_t m0 = c * kChunkK + kg * 4;
+      // ---- A operand: pro(dY) columns 0..127 (32 column groups, 2 per thread)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = m0 + r0 + 4 * i;
-        a[i] = (m < g.M) ? ldg4(g.dY + m * g.ldy + grp * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (g.H) {
+      for (int i = 0; i < 2; ++i) {
+        const int ng = g0 + 16 * i;
+        float4 r[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t m = m0 + r0 + 4 * i;
-          if (m < g.M) a[i] = silu_grad4(a[i], ldg4(g.H + m * g.ldh + grp * 4));
+        for (int q = 0; q < 4; ++q) {
+          const int64_t m = m0 + q;
+          r[q] = (m < g.M) ? ldg4(g.dY + m * g.ldy + ng * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
+        if (g.H) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 4 * i;  // row inside the 32-row chunk = contraction index kk
-        float4 hi, lo;
-        split4(a[i], hi, lo);
-        colsum = make_float4(colsum.x + a[i].x, colsum.y + a[i].y, colsum.z + a[i].z, colsum.w + a[i].w);
-        const uint32_t off = grp * kSbo + (r & 7) * 16 + (r >> 3) * lboA;
-        *reinterpret_cast<float4*>(st + off) = hi;
-        if (g.x3) *reinterpret_cast<float4*>(st + halfA + off) = lo;
-      }
-      for (int gb = grp; gb < ngB; gb += 32) {
-        float4 b[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t m = m0 + r0 + 4 * i;
-          b[i] = (m < g.M) ? ldg4(g.X + m * g.ldx + gb * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 4; ++q) {
+            const int64_t m = m0 + q;
+            if (m < g.M) r[q] = silu_grad4(r[q], ldg4(g.H + m * g.ldh + ng * 4));
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 4 * i;
-          float4 hi, lo;
-          split4(b[i], hi, lo);
-          const uint32_t off = 2 * halfA + gb * kSbo + (r & 7) * 16 + (r >> 3) * lboB;
-          *reinterpret_cast<float4*>(st + off) = hi;
-          if (g.x3) *reinterpret_cast<float4*>(st + halfB + off) = lo;
+        for (int q = 0; q < 4; ++q)
+          colsum[i] = make_float4(colsum[i].x + r[q].x, colsum[i].y + r[q].y, colsum[i].z + r[q].z, colsum[i].w + r[q].w);
+        store_transposed(st + kg * lboA + ng * 64, halfA, g.x3, r);
+      }
+      // ---- B operand: X columns 0..Kx-1
+      for (int ng = g0; ng < ngB; ng += 16) {
+        float4 r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t m = m0 + q;
+          r[q] = (m < g.M) ? ldg4(g.X + m * g.ldx + ng * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        store_transposed(st + 2 * halfA + kg * lboB + ng * 64, halfB, g.x3, r);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
     if (g.db) {
-      atomicAdd(g.db + grp * 4 + 0, colsum.x);
-      atomicAdd(g.db + grp * 4 + 1, colsum.y);
-      atomicAdd(g.db + grp * 4 + 2, colsum.z);
-      atomicAdd(g.db + grp * 4 + 3, colsum.w);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float* d = g.db + (g0 + 16 * i) * 4;
+        atomicAdd(d + 0, colsum[i].x); atomicAdd(d + 1, colsum[i].y); atomicAdd(d + 2, colsum[i].z); atomicAdd(d + 3, colsum[i].w);
+      }
     }
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBlockM, g.Kx, 1, 1);
+      const uint32_t idesc = make_idesc(kBlockM, g.Kx, 0, 0);
       const uint32_t base = smem_u32(smem_raw);
       uint32_t it = 0;
       for (int64_t c = c_beg; c < c_end; ++c, ++it) {
@@ -436,11 +444,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
         const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + halfA, b_hi = a_hi + 2 * halfA, b_lo = b_hi + halfB;
 #pragma unroll
         for (int kk = 0; kk < kChunkK / 8; ++kk) {
-          const uint64_t dAh = make_desc(a_hi + kk * lboA, lboA, kSbo), dBh = make_desc(b_hi + kk * lboB, lboB, kSbo);
+          const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi + kk * 2 * lboB, lboB, 128);
           umma_tf32(tmem_base, dAh, dBh, idesc, (it | kk) != 0);
           if (g.x3) {
-            umma_tf32(tmem_base, make_desc(a_lo + kk * lboA, lboA, kSbo), dBh, idesc, 1);
-            umma_tf32(tmem_base, dAh, make_desc(b_lo + kk * lboB, lboB, kSbo), idesc, 1);
+            umma_tf32(tmem_base, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, 1);
+            umma_tf32(tmem_base, dAh, make_desc(b_lo + kk * 2 * lboB, lboB, 128), idesc, 1);
           }
         }
         umma_commit(&empty[s]);
@@ -525,7 +533,7 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const
 }
 
 static size_t wgrad_smem(int Kx, int stages) {
-  const size_t halfA = (size_t)(kChunkK / 8) * 32 * 144, halfB = (size_t)(kChunkK / 8) * (Kx / 4) * 144;
+  const size_t halfA = (size_t)(kChunkK / 4) * (128 * 16 + 16), halfB = (size_t)(kChunkK / 4) * (Kx * 16 + 16);
   return (size_t)stages * (2 * halfA + 2 * halfB) + 256;
 }
 
