@@ -167,6 +167,11 @@ int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh,
 /* dW (Nout,K) += (dY * act'(H))^T X ; db (Nout) += its column sums (db nullable).  dW/db zeroed by the caller. */
 int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
                       float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode, float* scratch, void* stream);
+/* number of floats of `scratch` the two calls above need for these arguments (0 when the act' factor is fused
+ * into the tcgen05 prologue).  Pass X = NULL / dX = NULL for the call that will not be made. */
+int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
+                                const float* X, int64_t ldx, const float* dX, int64_t lddx, int64_t M, int32_t K,
+                                int32_t Nout, int32_t mode);
 /* dH = dY * act'(H)  elementwise over (M,C) with row strides (in place allowed: dH == dY) */
 int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
                  int32_t C, int32_t act, void* stream);

@@ -70,6 +70,8 @@ def load():
     lib.lcao_version.restype = C.c_int
     lib.lcao_last_error.restype = C.c_char_p
     lib.lcao_launch_count.restype = C.c_int64
+    lib.lcao_linear_bwd_scratch.restype = C.c_int64
+    lib.lcao_linear_bwd_scratch.argtypes = [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -51,6 +51,28 @@ static int act_bwd_to_scratch(const float*& dY, int64_t& ldy, const float* H, in
   return LCAO_OK;
 }
 
+static bool dgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W, const float* dX,
+                     int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t mode) {
+  const bool fuse = act != LCAO_ACT_NONE && H;
+  return mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) && (!fuse || (al16(H) && ldh % 4 == 0)) &&
+         lcao_tc_rows_ok(M, imin(Nout, 128), imin(K, 128), ldy, ldx, dY, dX);
+}
+static bool wgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
+                     int64_t M, int32_t K, int32_t Nout, int32_t mode) {
+  const bool fuse = act != LCAO_ACT_NONE && H;
+  return mode != LCAO_GEMM_FP32 && Nout % 128 == 0 && (!fuse || (al16(H) && ldh % 4 == 0)) &&
+         lcao_tc_wgrad_ok(M, K, ldy, ldx, dY, X);
+}
+
+extern "C" int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act,
+                                           const float* W, const float* X, int64_t ldx, const float* dX, int64_t lddx,
+                                           int64_t M, int32_t K, int32_t Nout, int32_t mode) {
+  if (act == LCAO_ACT_NONE || !H) return 0;
+  const bool d_ok = !dX || dgrad_tc(dY, ldy, H, ldh, act, W, dX, lddx, M, K, Nout, mode);
+  const bool w_ok = !X || wgrad_tc(dY, ldy, H, ldh, act, X, ldx, M, K, Nout, mode);
+  return (d_ok && w_ok) ? 0 : M * (int64_t)Nout;
+}
+
 extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
                                  float* dX, int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t accumulate,
                                  int32_t mode, float* scratch, void* stream) {
@@ -59,8 +81,7 @@ extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_dgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   const bool fuse = act != LCAO_ACT_NONE && H;
-  const bool tc = mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) && (!fuse || (al16(H) && ldh % 4 == 0)) &&
-                  lcao_tc_rows_ok(M, imin(Nout, 128), imin(K, 128), ldy, ldx, dY, dX);
+  const bool tc = dgrad_tc(dY, ldy, H, ldh, act, W, dX, ldx, M, K, Nout, mode);
   if (!tc) {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_dgrad");
     if (rc) return rc;
@@ -86,8 +107,7 @@ extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_wgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   const bool fuse = act != LCAO_ACT_NONE && H;
-  const bool tc = mode != LCAO_GEMM_FP32 && Nout % 128 == 0 && (!fuse || (al16(H) && ldh % 4 == 0)) &&
-                  lcao_tc_wgrad_ok(M, K, ldy, ldx, dY, X);
+  const bool tc = wgrad_tc(dY, ldy, H, ldh, act, X, ldx, M, K, Nout, mode);
   if (!tc) {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_wgrad");
     if (rc) return rc;

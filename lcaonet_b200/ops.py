@@ -180,16 +180,22 @@ class _Linear(torch.autograd.Function):
         M, K, Nout = x2.shape[0], x2.shape[1], w.shape[0]
         dy2 = _rows(dy)
         st = stream_ptr()
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dx = torch.empty(M, K, device=dy.device) if need_dx else None
         # dY * SiLU'(pre) is fused into the tcgen05 operand prologue; only the CUDA-core path uses scratch
-        fused_tc = _gemm_mode != _lib.GEMM_FP32 and M >= 512
-        scratch = torch.empty(M, Nout, device=dy.device) if (ctx.act != ACT_NONE and not fused_tc) else None
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(M, K, device=dy.device)
+        n_scratch = 0
+        if ctx.act != ACT_NONE:
+            n_scratch = _lib.load().lcao_linear_bwd_scratch(ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(w),
+                                                            ptr(x2) if need_dw else None, _ld(x2), ptr(dx), K, M, K, Nout,
+                                                            _gemm_mode)
+        scratch = torch.empty(n_scratch, device=dy.device) if n_scratch else None
+        dw = db = None
+        if need_dx:
             _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(w), ptr(dx), K, M, K, Nout, 0,
                   _gemm_mode, ptr(scratch), st)
             dx = dx.reshape(ctx.shape)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if need_dw:
             dw = torch.zeros(Nout, K, device=dy.device)
             db = torch.zeros(Nout, device=dy.device) if ctx.has_bias else None
             _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(x2), _ld(x2), ptr(dw), ptr(db), M,

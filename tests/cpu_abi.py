@@ -412,6 +412,14 @@ def lcao_act_bwd(dY, ldy, H, ldh, dH, ldd, M, Cc, act, stream):
 _TABLE = {k: v for k, v in list(globals().items()) if k.startswith("lcao_")}
 
 
+class _FakeLib:
+    """stands in for the CDLL in the few places ops.py calls the library object directly"""
+
+    @staticmethod
+    def lcao_linear_bwd_scratch(*a):
+        return 0
+
+
 def install(monkeypatch):
     """Route lcaonet_b200's C-ABI calls to this emulator and lift the CUDA-only guards (pytest only)."""
     from lcaonet_b200 import _lib, ops
@@ -420,6 +428,7 @@ def install(monkeypatch):
         _TABLE[name](*args)
 
     monkeypatch.setattr(_lib, "call", fake_call)
+    monkeypatch.setattr(_lib, "load", lambda: _FakeLib)
     monkeypatch.setattr(ops, "call", fake_call)
     monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
     monkeypatch.setattr(ops, "require_cuda", lambda *a: None)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_python_signatures_cover_the_header():
-    declared = set(_declared()) - {"lcao_version", "lcao_last_error", "lcao_launch_count"}
+    declared = set(_declared()) - {"lcao_version", "lcao_last_error", "lcao_launch_count", "lcao_linear_bwd_scratch"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     text = open(os.path.join(ROOT, "include", "lcao_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
