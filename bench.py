@@ -324,10 +324,10 @@ def profile_step(ops, fn, reps=3):
             M, K, Nout = a[8], a[9], a[10]
             meta = (4 * M * (K + Nout), 2 * M * K * Nout)
         elif name == "lcao_linear_dgrad":
-            M, K, Nout = a[5], a[6], a[7]
+            M, K, Nout = a[8], a[9], a[10]
             meta = (4 * M * (K + Nout), 2 * M * K * Nout)
         elif name == "lcao_linear_wgrad":
-            M, K, Nout = a[6], a[7], a[8]
+            M, K, Nout = a[9], a[10], a[11]
             meta = (4 * M * (K + Nout), 2 * M * K * Nout)
         records.append((name, e0, e1, meta))
 

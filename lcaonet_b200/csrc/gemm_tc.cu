@@ -156,7 +156,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
 
   const int64_t nblocks = (g.M + kBlockM - 1) / kBlockM;
   const int nchunk = g.Kc / kChunkK;
-  const uint32_t tmem_cols = (2 * g.Nb <= 32) ? 32 : (2 * g.Nb <= 64) ? 64 : (2 * g.Nb <= 128) ? 128 : (2 * g.Nb <= 256) ? 256 : 512;
+  // TMEM: 2 accumulator buffers; in x3 mode each buffer holds TWO accumulators: hi*hi and the small
+  // lo*hi + hi*lo corrections.  The tensor core truncates (RZ) on every accumulate, so keeping the
+  // dominant chain at K/8 steps and the corrections (2^-10 of the magnitude) apart cuts the bias 3x.
+  const uint32_t acc_cols = g.x3 ? 2 * g.Nb : g.Nb;
+  const uint32_t need_cols = 2 * acc_cols;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.stages; ++s) {
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
         const int acc = tile & 1;
         mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * g.Nb;
+        const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Nb;
         for (int kc = 0; kc < nchunk; ++kc, ++it) {
           const int s = it % g.stages;
           mbar_wait(&full[s], (it / g.stages) & 1);
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
             const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi, lboB, 128);
             umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
             if (g.x3) {
-              umma_tf32(d, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, 1);
-              umma_tf32(d, dAh, make_desc(b_lo, lboB, 128), idesc, 1);
+              umma_tf32(dc, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, (kc | kk) != 0);
+              umma_tf32(dc, dAh, make_desc(b_lo, lboB, 128), idesc, 1);
             }
           }
           umma_commit(&empty[s]);
@@ -275,7 +280,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
       const int64_t m = mb * kBlockM + warp * 32 + lane;
       for (int c0 = 0; c0 < g.Nb; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * g.Nb + c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
+        if (g.x3) {
+          float w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + g.Nb + c0, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
         if (m < g.M) {
           const int nc = min(32, g.Nb - c0);
 #pragma unroll
@@ -349,9 +360,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)g.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + g.stages;
-  uint64_t* tfull = bars + 2 * g.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
-  const uint32_t tmem_cols = g.Kx <= 32 ? 32 : g.Kx <= 64 ? 64 : g.Kx <= 128 ? 128 : 256;
+  uint64_t* tfull = bars + 2 * g.stages;   // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // The tensor core truncates on every accumulate: a TMEM chain is kept to kFlush chunks (256 rows) and then
+  // drained into round-to-nearest FP32 registers of the epilogue warps (double-buffered accumulators, and in
+  // x3 mode separate accumulators for hi*hi and for the small correction products).
+  constexpr int kFlush = 8;
+  const uint32_t acc_cols = g.x3 ? 2 * g.Kx : g.Kx;
+  const uint32_t need_cols = 2 * acc_cols;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
 
   // contiguous row range of this CTA, in units of 32 rows
   const int64_t nchunks = (g.M + kChunkK - 1) / kChunkK;
@@ -363,7 +381,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
       mbar_init(&full[s], kProdWarps * 32);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps * 32);
+    }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
@@ -436,40 +457,67 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBlockM, g.Kx, 0, 0);
       const uint32_t base = smem_u32(smem_raw);
-      uint32_t it = 0;
-      for (int64_t c = c_beg; c < c_end; ++c, ++it) {
-        const int s = it % g.stages;
-        mbar_wait(&full[s], (it / g.stages) & 1);
+      uint32_t it = 0, fl = 0;
+      for (int64_t c = c_beg; c < c_end; ++fl) {
+        const int acc = fl & 1;
+        mbar_wait(&tempty[acc], ((fl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + halfA, b_hi = a_hi + 2 * halfA, b_lo = b_hi + halfB;
+        const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Kx;
+        const int64_t c_stop = min(c_end, c + kFlush);
+        for (int first = 1; c < c_stop; ++c, ++it) {
+          const int s = it % g.stages;
+          mbar_wait(&full[s], (it / g.stages) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + halfA, b_hi = a_hi + 2 * halfA, b_lo = b_hi + halfB;
 #pragma unroll
-        for (int kk = 0; kk < kChunkK / 8; ++kk) {
-          const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi + kk * 2 * lboB, lboB, 128);
-          umma_tf32(tmem_base, dAh, dBh, idesc, (it | kk) != 0);
-          if (g.x3) {
-            umma_tf32(tmem_base, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, 1);
-            umma_tf32(tmem_base, dAh, make_desc(b_lo + kk * 2 * lboB, lboB, 128), idesc, 1);
+          for (int kk = 0; kk < kChunkK / 8; ++kk) {
+            const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi + kk * 2 * lboB, lboB, 128);
+            umma_tf32(d, dAh, dBh, idesc, !first);
+            if (g.x3) {
+              umma_tf32(dc, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, !first);
+              umma_tf32(dc, dAh, make_desc(b_lo + kk * 2 * lboB, lboB, 128), idesc, 1);
+            }
+            first = 0;
           }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&tfull[acc]);
       }
-      umma_commit(tfull);
     }
     __syncwarp();
   } else {
-    // ============================== epilogue warps: dW[n, :] += acc[n, :] ==============================
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-    const int n = warp * 32 + lane;
-    for (int c0 = 0; c0 < g.Kx; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-      const int nc = min(32, g.Kx - c0);
+    // ============================== epilogue warps: drain TMEM chains into registers, then dW += ==============
+    constexpr int kMaxCols = 128;
+    float sum[kMaxCols];
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nc) atomicAdd(g.dW + (int64_t)n * g.ldw + c0 + j, v[j]);
+    for (int j = 0; j < kMaxCols; ++j) sum[j] = 0.f;
+    const int64_t n_flush = (c_end - c_beg + kFlush - 1) / kFlush;
+    for (int64_t fl = 0; fl < n_flush; ++fl) {
+      const int acc = fl & 1;
+      mbar_wait(&tfull[acc], (fl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols;
+#pragma unroll
+      for (int c0 = 0; c0 < kMaxCols; c0 += 32) {
+        if (c0 < g.Kx) {
+          float v[32];
+          tmem_ld32(t0 + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
+          if (g.x3) {
+            tmem_ld32(t0 + g.Kx + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
     }
-    tc_fence_before();
+    const int n = warp * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < kMaxCols; ++j)
+      if (j < g.Kx) atomicAdd(g.dW + (int64_t)n * g.ldw + j, sum[j]);
   }
   tc_fence_before();
   __syncthreads();
@@ -538,7 +586,7 @@ static size_t wgrad_smem(int Kx, int stages) {
 }
 
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X) {
-  return M >= 512 && Kx % 16 == 0 && Kx >= 16 && Kx <= 256 && ldy % 4 == 0 && ldx % 4 == 0 && al16(dY) && al16(X) &&
+  return M >= 512 && Kx % 32 == 0 && Kx >= 32 && Kx <= 128 && ldy % 4 == 0 && ldx % 4 == 0 && al16(dY) && al16(X) &&
          wgrad_smem(Kx, 2) <= kMaxSmem;
 }
 

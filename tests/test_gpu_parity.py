@@ -295,9 +295,11 @@ def test_linear_tensor_core_modes(mode, tol, M, K, N, silu, bias):
     finally:
         ops.set_gemm_mode("fp32")
     assert rel_l2(y, ref) < tol
-    assert rel_l2(xg.grad, grads[0]) < 2 * tol and rel_l2(wg.grad, grads[1]) < 2 * tol
+    # the weight gradient sums M terms in FP32: allow the sqrt(M) * eps growth any FP32 reduction shows
+    tol_w = max(2 * tol, 2e-8 * M**0.5)
+    assert rel_l2(xg.grad, grads[0]) < 2 * tol and rel_l2(wg.grad, grads[1]) < tol_w
     if bias:
-        assert rel_l2(bg.grad, grads[2]) < 2 * tol
+        assert rel_l2(bg.grad, grads[2]) < tol_w
 
 
 def test_model_golden_with_tf32x3_gemms():
