@@ -122,36 +122,55 @@ __device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
 }
 
 // =================================================================================================
-// Kernel 1: row-streaming GEMM   Y[M, Nb] = epi( pro(A)[M, Kc] * Bop[Kc, Nb] )
-//   forward : A = X, Bop(n, k) = W[n*ldw + k]            (b_trans = 0, W is (Nb, Kc) row-major)
-//   dgrad   : A = dY (* SiLU'(H)), Bop(n, k) = W[k*ldw + n] (b_trans = 1, W is (Kc, Nb) row-major)
+// Kernel 1: row-streaming GEMM   Y[M, Nb] = epi( A[M, Kc] * Bop[Kc, Nb] )
+//   forward : Bop(n, k) = W[n*ldw + k]  (b_trans = 0, W is (Nb, Kc) row-major)
+//   dgrad   : Bop(n, k) = W[k*ldw + n]  (b_trans = 1, W is (Kc, Nb) row-major)
 // A and B tiles live in smem as K-major no-swizzle core matrices: element (row, k) at
 //   (k/4)*LBO + row*16 + (k%4)*4   with LBO = rows*16 + 16 (padded), SBO = 128 (8 rows x 16 B)
+//
+// Warp roles (320 threads): 0-3 epilogue, 4-7 hi/lo split (smem -> smem), 8 MMA issuer, 9 loader.
+// The loader warp streams A with 16-byte cp.async copies that land DIRECTLY in the K-major layout, up to
+// R-1 stages (16.5 KB each) ahead of the consumer, so ~50 KB per SM are always in flight; completion is
+// signalled with cp.async.mbarrier.arrive.  The split warps then rewrite the stage in place as `hi` and
+// produce `lo` in a short ring (L = 2), fence to the async proxy and hand the stage to the MMA warp.
 // =================================================================================================
 struct RowsArgs {
   const float* A; int64_t lda;
-  const float* H; int64_t ldh;     // prologue: A *= SiLU'(H) when H != nullptr
   const float* W; int64_t ldw;
   const float* bias;
+  const float* G; int64_t ldg;     // epilogue: out *= SiLU'(G) (dgrad chained into the previous layer's pre-activation)
   float* Y; int64_t ldy;
   float* pre; int64_t ldp;
   int64_t M; int Kc; int Nb;
-  int b_trans, act, accumulate, x3, stages;
+  int b_trans, act, accumulate, x3, stages, lo_stages;
 };
 
-__global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
+constexpr int kRowsThreads = 320;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lboA = kBlockM * 16 + 16, lboB = g.Nb * 16 + 16;
   const uint32_t halfB = (g.Kc / 4) * lboB;          // bytes of one of {W_hi, W_lo}
-  const uint32_t halfA = (kChunkK / 4) * lboA;        // bytes of one of {A_hi, A_lo} per stage
+  const uint32_t halfA = (kChunkK / 4) * lboA;        // bytes of one A stage (hi or lo)
+  const int R = g.stages, L = g.lo_stages;
   uint8_t* sB = smem_raw;
-  uint8_t* sA = sB + 2 * halfB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)g.stages * 2 * halfA);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + g.stages;
-  uint64_t* tfull = bars + 2 * g.stages;
-  uint64_t* tempty = tfull + 2;
+  uint8_t* sHi = sB + 2 * halfB;
+  uint8_t* sLo = sHi + (size_t)R * halfA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)L * halfA);
+  uint64_t* raw_full = bars;            // [R] loader (cp.async completion) -> split warps
+  uint64_t* full = raw_full + R;        // [R] split warps -> MMA
+  uint64_t* hi_empty = full + R;        // [R] MMA -> loader
+  uint64_t* lo_empty = hi_empty + R;    // [L] MMA -> split warps
+  uint64_t* tfull = lo_empty + L;       // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;         // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int64_t nblocks = (g.M + kBlockM - 1) / kBlockM;
@@ -164,10 +183,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
   const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&full[s], kProdWarps * 32);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&raw_full[s], 32);
+      mbar_init(&full[s], 4 * 32);
+      mbar_init(&hi_empty[s], 1);
     }
+    for (int s = 0; s < L; ++s) mbar_init(&lo_empty[s], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], kEpiWarps * 32);
@@ -177,23 +198,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
 
   // ---- resident B operand (the layer's weight), split hi/lo once per CTA, by all threads
-  for (int idx = threadIdx.x; idx < g.Nb * (g.Kc / 4); idx += kThreadsTC) {
+  for (int idx = threadIdx.x; idx < g.Nb * (g.Kc / 4); idx += kRowsThreads) {
+    float4 w;
+    int n, kg;
     if (!g.b_trans) {
-      const int n = idx / (g.Kc / 4), kg = idx - n * (g.Kc / 4);
-      float4 hi, lo;
-      split4(ldg4(g.W + (int64_t)n * g.ldw + kg * 4), hi, lo);
-      *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
-      *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
-    } else {
-      // W is (Kc, Nb): thread takes contraction group kg (4 rows of W) and one output column n
-      const int kg = idx / g.Nb, n = idx - kg * g.Nb;
-      const float4 w = make_float4(__ldg(g.W + (int64_t)(kg * 4 + 0) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 1) * g.ldw + n),
-                                   __ldg(g.W + (int64_t)(kg * 4 + 2) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 3) * g.ldw + n));
-      float4 hi, lo;
-      split4(w, hi, lo);
-      *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
-      *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
+      n = idx / (g.Kc / 4); kg = idx - n * (g.Kc / 4);
+      w = ldg4(g.W + (int64_t)n * g.ldw + kg * 4);
+    } else {  // W is (Kc, Nb): contraction group kg = 4 rows of W, one output column n
+      kg = idx / g.Nb; n = idx - kg * g.Nb;
+      w = make_float4(__ldg(g.W + (int64_t)(kg * 4 + 0) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 1) * g.ldw + n),
+                      __ldg(g.W + (int64_t)(kg * 4 + 2) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 3) * g.ldw + n));
     }
+    float4 hi, lo;
+    split4(w, hi, lo);
+    *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
+    *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -201,38 +220,48 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
-    // ============================== producer / transform warps ==============================
-    const int t = threadIdx.x - kEpiWarps * 32;  // 0..127
-    const int kg = t & 7, r0 = t >> 3;           // 8 k-groups x 16 row phases
+  if (warp == 9) {
+    // ============================== loader warp: cp.async straight into the K-major layout ==========
     uint32_t it = 0;
+    const uint32_t hi_base = smem_u32(sHi);
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
       const int64_t m0 = mb * kBlockM;
       for (int kc = 0; kc < nchunk; ++kc, ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (it / g.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t m = m0 + r0 + 16 * i;
-          v[i] = (m < g.M) ? ldg4(g.A + m * g.lda + kc * kChunkK + kg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int s = it % R;
+        mbar_wait(&hi_empty[s], ((it / R) & 1) ^ 1);
+        const uint32_t dst0 = hi_base + s * halfA;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const int p = lane + 32 * j;            // 1024 16-byte pieces: 128 rows x 8 k-groups
+          const int row = p >> 3, kg = p & 7;
+          const int64_t m = m0 + row;
+          const bool ok = m < g.M;
+          cp_async16(dst0 + kg * lboA + row * 16, g.A + (ok ? m : 0) * g.lda + kc * kChunkK + kg * 4, ok ? 16u : 0u);
         }
-        if (g.H) {
+        cp_async_arrive(&raw_full[s]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================== split warps: hi in place, lo into the short ring =================
+    const int t = threadIdx.x - 128;              // 0..127
+    uint32_t it = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
+      for (int kc = 0; kc < nchunk; ++kc, ++it) {
+        const int s = it % R, l = it % L;
+        mbar_wait(&raw_full[s], (it / R) & 1);
+        if (g.x3) {
+          mbar_wait(&lo_empty[l], ((it / L) & 1) ^ 1);
+          uint8_t* ph = sHi + (size_t)s * halfA;
+          uint8_t* pl = sLo + (size_t)l * halfA;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int64_t m = m0 + r0 + 16 * i;
-            if (m < g.M) v[i] = silu_grad4(v[i], ldg4(g.H + m * g.ldh + kc * kChunkK + kg * 4));
+            const int p = t + 128 * i;
+            const uint32_t off = (p & 7) * lboA + (p >> 3) * 16;
+            float4 hi, lo;
+            split4(*reinterpret_cast<const float4*>(ph + off), hi, lo);
+            *reinterpret_cast<float4*>(ph + off) = hi;
+            *reinterpret_cast<float4*>(pl + off) = lo;
           }
-        }
-        uint8_t* st = sA + (size_t)s * 2 * halfA;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 hi, lo;
-          split4(v[i], hi, lo);
-          const uint32_t off = kg * lboA + (r0 + 16 * i) * 16;
-          *reinterpret_cast<float4*>(st + off) = hi;
-          if (g.x3) *reinterpret_cast<float4*>(st + halfA + off) = lo;
         }
         fence_proxy_async();
         mbar_arrive(&full[s]);
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBlockM, g.Nb, 0, 0);
-      const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+      const uint32_t hiBase = smem_u32(sHi), loBase = smem_u32(sLo), bBase = smem_u32(sB);
       uint32_t it = 0, tile = 0;
       for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
         const int acc = tile & 1;
@@ -250,10 +279,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
         tc_fence_after();
         const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Nb;
         for (int kc = 0; kc < nchunk; ++kc, ++it) {
-          const int s = it % g.stages;
-          mbar_wait(&full[s], (it / g.stages) & 1);
+          const int s = it % R, l = it % L;
+          mbar_wait(&full[s], (it / R) & 1);
           tc_fence_after();
-          const uint32_t a_hi = aBase + s * 2 * halfA, a_lo = a_hi + halfA;
+          const uint32_t a_hi = hiBase + s * halfA, a_lo = loBase + l * halfA;
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 8; ++kk) {
             const uint32_t b_hi = bBase + (kc * (kChunkK / 4) + kk * 2) * lboB, b_lo = b_hi + halfB;
@@ -264,7 +293,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
               umma_tf32(dc, dAh, make_desc(b_lo, lboB, 128), idesc, 1);
             }
           }
-          umma_commit(&empty[s]);
+          umma_commit(&hi_empty[s]);
+          if (g.x3) umma_commit(&lo_empty[l]);
         }
         umma_commit(&tfull[acc]);
       }
@@ -303,6 +333,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_rows(const RowsArgs g) {
               }
               if (g.pre) st4(g.pre + m * g.ldp + c0 + j, o);
               if (g.act == LCAO_ACT_SILU) o = make_float4(siluf(o.x), siluf(o.y), siluf(o.z), siluf(o.w));
+              if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + c0 + j));
               st4(g.Y + m * g.ldy + c0 + j, o);
             }
           }
@@ -546,28 +577,30 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 // ---- eligibility + launchers (called from linear.cu) -------------------------------------------
 // rows kernel: contraction Kc % 32 == 0, output columns Nb % 16 == 0 and <= 128 per launch, weights resident.
-static size_t rows_smem(int Kc, int Nb, int stages) {
+static size_t rows_smem(int Kc, int Nb, int stages, int lo_stages) {
   const size_t halfB = (size_t)(Kc / 4) * (Nb * 16 + 16);
   const size_t halfA = (size_t)(kChunkK / 4) * (kBlockM * 16 + 16);
-  return 2 * halfB + (size_t)stages * 2 * halfA + 256;
+  return 2 * halfB + (size_t)(stages + lo_stages) * halfA + 512;
 }
 
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y) {
   return M >= 512 && Kc % 32 == 0 && Kc >= 32 && Nb % 16 == 0 && Nb >= 16 && Nb <= 128 && lda % 4 == 0 && ldy % 4 == 0 &&
-         al16(A) && al16(Y) && rows_smem(Kc, Nb, 2) <= kMaxSmem;
+         al16(A) && al16(Y) && rows_smem(Kc, Nb, 2, 2) <= kMaxSmem;
 }
 
-int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const float* W, int64_t ldw, int b_trans,
-                 const float* bias, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
+int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b_trans, const float* bias, const float* G,
+                 int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
                  int accumulate, int x3, cudaStream_t st) {
   RowsArgs g{};
-  g.A = A; g.lda = lda; g.H = H; g.ldh = ldh; g.W = W; g.ldw = ldw; g.bias = bias; g.Y = Y; g.ldy = ldy;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.G = G; g.ldg = ldg; g.Y = Y; g.ldy = ldy;
   g.pre = pre; g.ldp = ldp; g.M = M; g.Kc = Kc; g.Nb = Nb; g.b_trans = b_trans; g.act = act; g.accumulate = accumulate;
   g.x3 = x3;
-  int stages = 4;
-  while (stages > 2 && rows_smem(Kc, Nb, stages) > kMaxSmem) --stages;
+  const int lo_stages = x3 ? 2 : 0;
+  int stages = 8;
+  while (stages > 2 && rows_smem(Kc, Nb, stages, lo_stages) > kMaxSmem) --stages;
   g.stages = stages;
-  const size_t smem = rows_smem(Kc, Nb, stages);
+  g.lo_stages = x3 ? lo_stages : 1;  // (modulo operand only; no buffer is touched in 1x mode)
+  const size_t smem = rows_smem(Kc, Nb, stages, lo_stages);
   static bool attr_set = false;
   if (!attr_set) {
     LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -575,7 +608,7 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const
   }
   const int64_t nblocks = (M + kBlockM - 1) / kBlockM;
   const unsigned grid = (unsigned)(nblocks < num_sms() ? nblocks : num_sms());
-  k_tc_rows<<<grid, kThreadsTC, smem, st>>>(g);
+  k_tc_rows<<<grid, kRowsThreads, smem, st>>>(g);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -10,8 +10,8 @@ int lcao_simt_linear_dgrad(const float*, int64_t, const float*, float*, int64_t,
 int lcao_simt_linear_wgrad(const float*, int64_t, const float*, int64_t, float*, float*, int64_t, int32_t, int32_t,
                            cudaStream_t);
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y);
-int lcao_tc_rows(const float* A, int64_t lda, const float* H, int64_t ldh, const float* W, int64_t ldw, int b_trans,
-                 const float* bias, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
+int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b_trans, const float* bias, const float* G,
+                 int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
                  int accumulate, int x3, cudaStream_t st);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, const float* X, int64_t ldx, float* dW,
@@ -32,7 +32,7 @@ extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, cons
   if (!tc) return lcao_simt_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, st);
   for (int n0 = 0; n0 < Nout; n0 += 128) {
     const int nb = imin(128, Nout - n0);
-    int rc = lcao_tc_rows(X, ldx, nullptr, 0, W + (int64_t)n0 * K, K, 0, bias ? bias + n0 : nullptr, Y + n0, ldy,
+    int rc = lcao_tc_rows(X, ldx, W + (int64_t)n0 * K, K, 0, bias ? bias + n0 : nullptr, nullptr, 0, Y + n0, ldy,
                           pre ? pre + n0 : nullptr, ldp, M, K, nb, act, 0, mode == LCAO_GEMM_TF32X3, st);
     if (rc) return rc;
   }
@@ -51,10 +51,9 @@ static int act_bwd_to_scratch(const float*& dY, int64_t& ldy, const float* H, in
   return LCAO_OK;
 }
 
-static bool dgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W, const float* dX,
-                     int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t mode) {
-  const bool fuse = act != LCAO_ACT_NONE && H;
-  return mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) && (!fuse || (al16(H) && ldh % 4 == 0)) &&
+static bool dgrad_tc(const float* dY, int64_t ldy, const float* W, const float* dX, int64_t ldx, int64_t M, int32_t K,
+                     int32_t Nout, int32_t mode) {
+  return mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) &&
          lcao_tc_rows_ok(M, imin(Nout, 128), imin(K, 128), ldy, ldx, dY, dX);
 }
 static bool wgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
@@ -67,10 +66,11 @@ static bool wgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, 
 extern "C" int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act,
                                            const float* W, const float* X, int64_t ldx, const float* dX, int64_t lddx,
                                            int64_t M, int32_t K, int32_t Nout, int32_t mode) {
+  (void)W; (void)lddx;
   if (act == LCAO_ACT_NONE || !H) return 0;
-  const bool d_ok = !dX || dgrad_tc(dY, ldy, H, ldh, act, W, dX, lddx, M, K, Nout, mode);
+  if (dX) return M * (int64_t)Nout;  // the row-streaming kernels take dY * act'(H) as a plain operand
   const bool w_ok = !X || wgrad_tc(dY, ldy, H, ldh, act, X, ldx, M, K, Nout, mode);
-  return (d_ok && w_ok) ? 0 : M * (int64_t)Nout;
+  return w_ok ? 0 : M * (int64_t)Nout;
 }
 
 extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
@@ -80,19 +80,18 @@ extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(dY && W && dX && Nout > 0, "lcao_linear_dgrad: null buffer");
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_dgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fuse = act != LCAO_ACT_NONE && H;
-  const bool tc = dgrad_tc(dY, ldy, H, ldh, act, W, dX, ldx, M, K, Nout, mode);
-  if (!tc) {
+  {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_dgrad");
     if (rc) return rc;
-    return lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, accumulate, st);
   }
+  if (!dgrad_tc(dY, ldy, W, dX, ldx, M, K, Nout, mode))
+    return lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, accumulate, st);
   for (int n0 = 0; n0 < K; n0 += 128) {          // output columns
     const int nb = imin(128, K - n0);
     for (int c0 = 0; c0 < Nout; c0 += 128) {     // contraction chunks
       const int kc = imin(128, Nout - c0);
-      int rc = lcao_tc_rows(dY + c0, ldy, fuse ? H + c0 : nullptr, ldh, W + (int64_t)c0 * K + n0, K, 1, nullptr, dX + n0,
-                            ldx, nullptr, 0, M, kc, nb, LCAO_ACT_NONE, accumulate || c0 > 0, mode == LCAO_GEMM_TF32X3, st);
+      int rc = lcao_tc_rows(dY + c0, ldy, W + (int64_t)c0 * K + n0, K, 1, nullptr, nullptr, 0, dX + n0, ldx, nullptr, 0, M,
+                            kc, nb, LCAO_ACT_NONE, accumulate || c0 > 0, mode == LCAO_GEMM_TF32X3, st);
       if (rc) return rc;
     }
   }

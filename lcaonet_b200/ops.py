@@ -182,24 +182,21 @@ class _Linear(torch.autograd.Function):
         st = stream_ptr()
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        dx = torch.empty(M, K, device=dy.device) if need_dx else None
-        # dY * SiLU'(pre) is fused into the tcgen05 operand prologue; only the CUDA-core path uses scratch
-        n_scratch = 0
-        if ctx.act != ACT_NONE:
-            n_scratch = _lib.load().lcao_linear_bwd_scratch(ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(w),
-                                                            ptr(x2) if need_dw else None, _ld(x2), ptr(dx), K, M, K, Nout,
-                                                            _gemm_mode)
-        scratch = torch.empty(n_scratch, device=dy.device) if n_scratch else None
-        dw = db = None
+        if ctx.act != ACT_NONE:  # dH = dY * act'(pre), shared by the data and the weight gradient
+            dh = torch.empty(M, Nout, device=dy.device)
+            _call("lcao_act_bwd", ptr(dy2), _ld(dy2), ptr(pre), Nout, ptr(dh), Nout, M, Nout, ctx.act, st)
+            dy2 = dh
+        dx = dw = db = None
         if need_dx:
-            _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(w), ptr(dx), K, M, K, Nout, 0,
-                  _gemm_mode, ptr(scratch), st)
+            dx = torch.empty(M, K, device=dy.device)
+            _call("lcao_linear_dgrad", ptr(dy2), _ld(dy2), None, 0, ACT_NONE, ptr(w), ptr(dx), K, M, K, Nout, 0,
+                  _gemm_mode, None, st)
             dx = dx.reshape(ctx.shape)
         if need_dw:
             dw = torch.zeros(Nout, K, device=dy.device)
             db = torch.zeros(Nout, device=dy.device) if ctx.has_bias else None
-            _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), ptr(pre), Nout, ctx.act, ptr(x2), _ld(x2), ptr(dw), ptr(db), M,
-                  K, Nout, _gemm_mode, ptr(scratch), st)
+            _call("lcao_linear_wgrad", ptr(dy2), _ld(dy2), None, 0, ACT_NONE, ptr(x2), _ld(x2), ptr(dw), ptr(db), M,
+                  K, Nout, _gemm_mode, None, st)
         return dx, dw, db, None
 
 

@@ -1,0 +1,85 @@
+"""Micro-benchmarks of single C-ABI kernels on the BASELINE configs[1] shapes (CUDA events, L2 flushed
+between repetitions by a 512 MB write).  Usage: python scripts/bench_kernels.py [gemm|edge|all]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lcaonet_b200 import ops  # noqa: E402
+from lcaonet_b200.synth import qm9_like_batch  # noqa: E402
+
+DEV = "cuda"
+FLUSH = None
+
+
+def timeit(fn, reps=5, warm=2):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(128 * 1024 * 1024, device=DEV)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm():
+    M, K, N = 2_022_384, 128, 128
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K**0.5
+    dy = torch.randn(M, N, device=DEV)
+    y, pre, dx = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV), torch.empty(M, K, device=DEV)
+    dw = torch.zeros(N, K, device=DEV)
+    P, st = ops.ptr, ops.stream_ptr
+    for mode in ("fp32", "tf32x3", "tf32"):
+        m = ops.GEMM_MODES[mode]
+        t_f = timeit(lambda: ops._call("lcao_linear_fwd", P(x), K, P(w), None, P(y), N, P(pre), N, M, K, N, 1, m, st()))
+        t_f0 = timeit(lambda: ops._call("lcao_linear_fwd", P(x), K, P(w), None, P(y), N, None, N, M, K, N, 0, m, st()))
+        t_d = timeit(lambda: ops._call("lcao_linear_dgrad", P(dy), N, None, 0, 0, P(w), P(dx), K, M, K, N, 0, m, None, st()))
+        t_w = timeit(lambda: ops._call("lcao_linear_wgrad", P(dy), N, None, 0, 0, P(x), K, P(dw), None, M, K, N, m, None, st()))
+        gb = lambda nbytes, ms: nbytes / ms / 1e6  # noqa: E731
+        fl = 2.0 * M * K * N
+        print(f"gemm {mode:7s} M={M} K={K} N={N}: fwd+silu+pre {t_f:.3f} ms ({gb(4*M*(K+2*N), t_f):.0f} GB/s, {fl/t_f/1e9:.0f} TF/s) | "
+              f"fwd plain {t_f0:.3f} ms ({gb(4*M*(K+N), t_f0):.0f} GB/s) | dgrad {t_d:.3f} ms ({gb(4*M*(K+N), t_d):.0f} GB/s) | "
+              f"wgrad {t_w:.3f} ms ({gb(4*M*(K+N), t_w):.0f} GB/s)", flush=True)
+
+
+def edge():
+    g = qm9_like_batch(1024, seed=1000).to(DEV)
+    N, E, C, NL, O = g["z"].shape[0], g["edge_index"].shape[1], 128, 3, 8
+    gi = ops.GraphIndex(g["edge_index"], N)
+    B = torch.randn(E, NL, C, device=DEV)
+    unit = torch.nn.functional.normalize(torch.randn(E, 3, device=DEV), dim=1)
+    xk = torch.randn(N, 2 * C, device=DEV)[:, C:]
+    tbw, dB, q = torch.empty(E, C, device=DEV), torch.empty(E, NL, C, device=DEV), torch.empty(E, C, device=DEV)
+    d_tbw = torch.randn(E, C, device=DEV)
+    P, st = ops.ptr, ops.stream_ptr
+    t_f = timeit(lambda: ops._call("lcao_threebody_fwd", P(B), NL, P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge),
+                                   P(gi.in_src), P(gi.out_ptr), P(gi.out_edge), N, E, C, NL, P(tbw), st()))
+    t_b = timeit(lambda: ops._call("lcao_threebody_bwd", P(B), NL, P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge),
+                                   P(gi.in_src), P(gi.out_ptr), P(gi.out_edge), N, E, C, NL, P(d_tbw), P(dB), P(q), None,
+                                   None, st()))
+    T = gi.num_triplets()
+    bf = E * (4 * NL * C + 12 + 8 + 4 * C) + N * (4 * C + 8)
+    bb = E * (4 * NL * C + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+    print(f"threebody N={N} E={E} T={T}: fwd {t_f:.3f} ms ({bf/t_f/1e6:.0f} GB/s, {T/t_f/1e6:.2f} Gtriplets/s) | "
+          f"bwd {t_b:.3f} ms ({bb/t_b/1e6:.0f} GB/s, {T/t_b/1e6:.2f} Gtriplets/s)", flush=True)
+    t_i = timeit(lambda: ops.GraphIndex(g["edge_index"], N))
+    print(f"graph index build: {t_i:.3f} ms", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("gemm", "all"):
+        gemm()
+    if what in ("edge", "all"):
+        edge()
