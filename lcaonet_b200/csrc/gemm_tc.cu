@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   uint8_t* sB = smem_raw;
   uint8_t* sHi = sB + 2 * halfB;
   uint8_t* sLo = sHi + (size_t)R * halfA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)L * halfA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)(g.x3 ? L : 0) * halfA);  // no lo ring in 1x mode
   uint64_t* raw_full = bars;            // [R] loader (cp.async completion) -> split warps
   uint64_t* full = raw_full + R;        // [R] split warps -> MMA
   uint64_t* hi_empty = full + R;        // [R] MMA -> loader
