@@ -146,6 +146,8 @@ struct RowsArgs {
 };
 
 constexpr int kRowsThreads = 320;
+constexpr int kEpiPitch = 144;                   // bytes per staged row (32 floats + 16 B pad: conflict-free)
+constexpr int kEpiWarpBytes = 32 * kEpiPitch;    // one warp stages its 32 rows x 32 columns
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   uint8_t* sB = smem_raw;
   uint8_t* sHi = sB + 2 * halfB;
   uint8_t* sLo = sHi + (size_t)R * halfA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)(g.x3 ? L : 0) * halfA);  // no lo ring in 1x mode
+  uint8_t* sEpi = sLo + (size_t)(g.x3 ? L : 0) * halfA;  // no lo ring in 1x mode
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * kEpiWarpBytes);
   uint64_t* raw_full = bars;            // [R] loader (cp.async completion) -> split warps
   uint64_t* full = raw_full + R;        // [R] split warps -> MMA
   uint64_t* hi_empty = full + R;        // [R] MMA -> loader
@@ -302,12 +305,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     __syncwarp();
   } else {
     // ============================== epilogue warps ==============================
+    // TMEM gives every thread one ROW (32 columns per load); storing that directly would touch 32
+    // different 128-byte lines per instruction.  Each warp therefore transposes its 32x32 chunk through
+    // a private padded smem tile so that every global store instruction writes 4 full 128-byte rows.
+    uint8_t* stg = sEpi + warp * kEpiWarpBytes;
+    const int rl = lane >> 3, cl = (lane & 7) * 4;   // read-back mapping: 4 rows x 8 float4 per instruction
     uint32_t tile = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
       const int acc = tile & 1;
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
-      const int64_t m = mb * kBlockM + warp * 32 + lane;
+      const int64_t mw = mb * kBlockM + warp * 32;
       for (int c0 = 0; c0 < g.Nb; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
@@ -317,24 +325,32 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
         }
-        if (m < g.M) {
-          const int nc = min(32, g.Nb - c0);
+        __syncwarp();  // previous chunk fully read back
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < nc) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int nc = min(32, g.Nb - c0);
+        if (cl < nc) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rl + 4 * i;
+            const int64_t m = mw + r;
+            if (m < g.M) {
+              float4 o = *reinterpret_cast<const float4*>(stg + r * kEpiPitch + cl * 4);
+              const int64_t col = c0 + cl;
               if (g.bias) {
-                const float4 b = ldg4(g.bias + c0 + j);
+                const float4 b = ldg4(g.bias + col);
                 o = make_float4(o.x + b.x, o.y + b.y, o.z + b.z, o.w + b.w);
               }
               if (g.accumulate) {
-                const float4 p = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
+                const float4 p = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + col);
                 o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
               }
-              if (g.pre) st4(g.pre + m * g.ldp + c0 + j, o);
+              if (g.pre) st4(g.pre + m * g.ldp + col, o);
               if (g.act == LCAO_ACT_SILU) o = make_float4(siluf(o.x), siluf(o.y), siluf(o.z), siluf(o.w));
-              if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + c0 + j));
-              st4(g.Y + m * g.ldy + c0 + j, o);
+              if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + col));
+              st4(g.Y + m * g.ldy + col, o);
             }
           }
         }
@@ -580,7 +596,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 static size_t rows_smem(int Kc, int Nb, int stages, int lo_stages) {
   const size_t halfB = (size_t)(Kc / 4) * (Nb * 16 + 16);
   const size_t halfA = (size_t)(kChunkK / 4) * (kBlockM * 16 + 16);
-  return 2 * halfB + (size_t)(stages + lo_stages) * halfA + 512;
+  return 2 * halfB + (size_t)(stages + lo_stages) * halfA + kEpiWarps * kEpiWarpBytes + 512;
 }
 
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y) {
