@@ -117,8 +117,16 @@ __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
   hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
   lo = make_float4(tf32_hi(x.x - hi.x), tf32_hi(x.y - hi.y), tf32_hi(x.z - hi.z), tf32_hi(x.w - hi.w));
 }
+// SFU-based sigmoid for the GEMM epilogues/prologues (ex2.approx + rcp.approx: ~3e-7 relative error for |x| < 10,
+// an order below the 3xTF32 product error), so that 4 epilogue warps keep up with the tensor core
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float silu_grad_fast(float x) {
+  const float sg = sigmoid_fast(x);
+  return sg * fmaf(x, 1.0f - sg, 1.0f);
+}
 __device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
-  return make_float4(g.x * silu_gradf(h.x), g.y * silu_gradf(h.y), g.z * silu_gradf(h.z), g.w * silu_gradf(h.w));
+  return make_float4(g.x * silu_grad_fast(h.x), g.y * silu_grad_fast(h.y), g.z * silu_grad_fast(h.z), g.w * silu_grad_fast(h.w));
 }
 
 // =================================================================================================
@@ -128,8 +136,8 @@ __device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
 // A and B tiles live in smem as K-major no-swizzle core matrices: element (row, k) at
 //   (k/4)*LBO + row*16 + (k%4)*4   with LBO = rows*16 + 16 (padded), SBO = 128 (8 rows x 16 B)
 //
-// Warp roles (320 threads): 0-3 epilogue, 4-7 hi/lo split (smem -> smem), 8 MMA issuer, 9 loader.
-// The loader warp streams A with 16-byte cp.async copies that land DIRECTLY in the K-major layout, up to
+// Warp roles (416 threads): 0-3 epilogue, 4-7 hi/lo split (smem -> smem), 8 MMA issuer, 9-12 loaders.
+// The loader warps stream A with 16-byte cp.async copies that land DIRECTLY in the K-major layout, up to
 // R-1 stages (16.5 KB each) ahead of the consumer, so ~50 KB per SM are always in flight; completion is
 // signalled with cp.async.mbarrier.arrive.  The split warps then rewrite the stage in place as `hi` and
 // produce `lo` in a short ring (L = 2), fence to the async proxy and hand the stage to the MMA warp.
@@ -145,7 +153,8 @@ struct RowsArgs {
   int b_trans, act, accumulate, x3, stages, lo_stages;
 };
 
-constexpr int kRowsThreads = 320;
+constexpr int kLoadWarps = 4;
+constexpr int kRowsThreads = (4 + 4 + 1 + kLoadWarps) * 32;  // 416
 constexpr int kEpiPitch = 144;                   // bytes per staged row (32 floats + 16 B pad: conflict-free)
 constexpr int kEpiWarpBytes = 32 * kEpiPitch;    // one warp stages its 32 rows x 32 columns
 
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
-      mbar_init(&raw_full[s], 32);
+      mbar_init(&raw_full[s], kLoadWarps * 32);
       mbar_init(&full[s], 4 * 32);
       mbar_init(&hi_empty[s], 1);
     }
@@ -223,23 +232,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
-    // ============================== loader warp: cp.async straight into the K-major layout ==========
+  if (warp >= 9) {
+    // ============================== loader warps: cp.async straight into the K-major layout ==========
+    // warp lw streams rows [32 lw, 32 lw + 32) of the tile: 8 copies per lane and stage, lane = (row % 4, k-group)
+    const int lw = warp - 9, row_in = lane >> 3, kg = lane & 7;
+    const uint32_t dst_lane = smem_u32(sHi) + kg * lboA + (32 * lw + row_in) * 16;
     uint32_t it = 0;
-    const uint32_t hi_base = smem_u32(sHi);
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
-      const int64_t m0 = mb * kBlockM;
+      const int64_t mrow = mb * kBlockM + 32 * lw + row_in;
       for (int kc = 0; kc < nchunk; ++kc, ++it) {
         const int s = it % R;
         mbar_wait(&hi_empty[s], ((it / R) & 1) ^ 1);
-        const uint32_t dst0 = hi_base + s * halfA;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-          const int p = lane + 32 * j;            // 1024 16-byte pieces: 128 rows x 8 k-groups
-          const int row = p >> 3, kg = p & 7;
-          const int64_t m = m0 + row;
-          const bool ok = m < g.M;
-          cp_async16(dst0 + kg * lboA + row * 16, g.A + (ok ? m : 0) * g.lda + kc * kChunkK + kg * 4, ok ? 16u : 0u);
+        const uint32_t dst = dst_lane + s * halfA;
+        const float* src = g.A + mrow * g.lda + kc * kChunkK + kg * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = mrow + 4 * j < g.M;
+          cp_async16(dst + j * 64, ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
         }
         cp_async_arrive(&raw_full[s]);
       }
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
                 o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
               }
               if (g.pre) st4(g.pre + m * g.ldp + col, o);
-              if (g.act == LCAO_ACT_SILU) o = make_float4(siluf(o.x), siluf(o.y), siluf(o.z), siluf(o.w));
+              if (g.act == LCAO_ACT_SILU) o = make_float4(silu_fast(o.x), silu_fast(o.y), silu_fast(o.z), silu_fast(o.w));
               if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + col));
               st4(g.Y + m * g.ldy + col, o);
             }
