@@ -105,6 +105,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)1 << 46;
   return d;
 }
+// SWIZZLE_128B K-major tile: rows of 128 bytes (32 tf32), 16-byte chunk c of row r stored at chunk (c ^ (r & 7));
+// 8-row groups are 1024 B apart (SBO), LBO is unused (=1), layout_type = 2, tile base 1024-byte aligned.
+// One MMA consumes K = 8 tf32 = 32 bytes: the start address advances by 32 B inside the swizzled row.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13),
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -133,14 +146,15 @@ __device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
 // Kernel 1: row-streaming GEMM   Y[M, Nb] = epi( A[M, Kc] * Bop[Kc, Nb] )
 //   forward : Bop(n, k) = W[n*ldw + k]  (b_trans = 0, W is (Nb, Kc) row-major)
 //   dgrad   : Bop(n, k) = W[k*ldw + n]  (b_trans = 1, W is (Kc, Nb) row-major)
-// A and B tiles live in smem as K-major no-swizzle core matrices: element (row, k) at
-//   (k/4)*LBO + row*16 + (k%4)*4   with LBO = rows*16 + 16 (padded), SBO = 128 (8 rows x 16 B)
+// A stages (128 rows x 32 k) and the resident weight (Kc/32 blocks of Nb rows x 32 k) are SWIZZLE_128B
+// K-major tiles (see make_desc_sw128).
 //
 // Warp roles (416 threads): 0-3 epilogue, 4-7 hi/lo split (smem -> smem), 8 MMA issuer, 9-12 loaders.
-// The loader warps stream A with 16-byte cp.async copies that land DIRECTLY in the K-major layout, up to
-// R-1 stages (16.5 KB each) ahead of the consumer, so ~50 KB per SM are always in flight; completion is
-// signalled with cp.async.mbarrier.arrive.  The split warps then rewrite the stage in place as `hi` and
-// produce `lo` in a short ring (L = 2), fence to the async proxy and hand the stage to the MMA warp.
+// The loader warps stream A with 16-byte cp.async copies, 8 lanes per 128-byte row so that every group
+// writes ONE full swizzled 128-byte line of the tile (conflict free), up to R-1 stages (16 KB each)
+// ahead of the consumer; completion is signalled with cp.async.mbarrier.arrive.  The split warps
+// rewrite the stage in place as `hi` and produce `lo` in a short ring (L = 2) — an elementwise pass that
+// is layout agnostic — fence to the async proxy and hand the stage to the MMA warp.
 // =================================================================================================
 struct RowsArgs {
   const float* A; int64_t lda;
@@ -157,6 +171,7 @@ constexpr int kLoadWarps = 4;
 constexpr int kRowsThreads = (4 + 4 + 1 + kLoadWarps) * 32;  // 416
 constexpr int kEpiPitch = 144;                   // bytes per staged row (32 floats + 16 B pad: conflict-free)
 constexpr int kEpiWarpBytes = 32 * kEpiPitch;    // one warp stages its 32 rows x 32 columns
+constexpr uint32_t kStageBytes = kBlockM * 128;  // 16 KB: 128 rows x 32 tf32
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -166,20 +181,19 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t lboA = kBlockM * 16 + 16, lboB = g.Nb * 16 + 16;
-  const uint32_t halfB = (g.Kc / 4) * lboB;          // bytes of one of {W_hi, W_lo}
-  const uint32_t halfA = (kChunkK / 4) * lboA;        // bytes of one A stage (hi or lo)
+  const uint32_t blockB = g.Nb * 128;                 // bytes of one 32-k column block of the weight
+  const uint32_t halfB = (g.Kc / kChunkK) * blockB;   // bytes of one of {W_hi, W_lo}
   const int R = g.stages, L = g.lo_stages;
   uint8_t* sB = smem_raw;
   uint8_t* sHi = sB + 2 * halfB;
-  uint8_t* sLo = sHi + (size_t)R * halfA;
-  uint8_t* sEpi = sLo + (size_t)(g.x3 ? L : 0) * halfA;  // no lo ring in 1x mode
+  uint8_t* sLo = sHi + (size_t)R * kStageBytes;
+  uint8_t* sEpi = sLo + (size_t)(g.x3 ? L : 0) * kStageBytes;  // no lo ring in 1x mode
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * kEpiWarpBytes);
-  uint64_t* raw_full = bars;            // [R] loader (cp.async completion) -> split warps
+  uint64_t* raw_full = bars;            // [R] loaders (cp.async completion) -> split warps
   uint64_t* full = raw_full + R;        // [R] split warps -> MMA
-  uint64_t* hi_empty = full + R;        // [R] MMA -> loader
+  uint64_t* hi_empty = full + R;        // [R] MMA -> loaders
   uint64_t* lo_empty = hi_empty + R;    // [L] MMA -> split warps
   uint64_t* tfull = lo_empty + L;       // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;         // [2] epilogue -> MMA
@@ -223,8 +237,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     }
     float4 hi, lo;
     split4(w, hi, lo);
-    *reinterpret_cast<float4*>(sB + kg * lboB + n * 16) = hi;
-    *reinterpret_cast<float4*>(sB + halfB + kg * lboB + n * 16) = lo;
+    const uint32_t off = (kg >> 3) * blockB + sw128_off(n, kg & 7);
+    *reinterpret_cast<float4*>(sB + off) = hi;
+    *reinterpret_cast<float4*>(sB + halfB + off) = lo;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -233,22 +248,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 9) {
-    // ============================== loader warps: cp.async straight into the K-major layout ==========
-    // warp lw streams rows [32 lw, 32 lw + 32) of the tile: 8 copies per lane and stage, lane = (row % 4, k-group)
-    const int lw = warp - 9, row_in = lane >> 3, kg = lane & 7;
-    const uint32_t dst_lane = smem_u32(sHi) + kg * lboA + (32 * lw + row_in) * 16;
+    // ============================== loader warps ==============================
+    // warp lw streams rows [32 lw, 32 lw + 32) of the tile: 8 copies per lane and stage; lanes 0-7 / 8-15 / ...
+    // cover one 128-byte row each (global) and write its 8 chunks into one swizzled 128-byte smem line
+    const int lw = warp - 9, row_in = lane >> 3, c = lane & 7;
+    const uint32_t hi_base = smem_u32(sHi);
     uint32_t it = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
       const int64_t mrow = mb * kBlockM + 32 * lw + row_in;
       for (int kc = 0; kc < nchunk; ++kc, ++it) {
         const int s = it % R;
         mbar_wait(&hi_empty[s], ((it / R) & 1) ^ 1);
-        const uint32_t dst = dst_lane + s * halfA;
-        const float* src = g.A + mrow * g.lda + kc * kChunkK + kg * 4;
+        const uint32_t dst = hi_base + s * kStageBytes;
+        const float* src = g.A + mrow * g.lda + kc * kChunkK + c * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool ok = mrow + 4 * j < g.M;
-          cp_async16(dst + j * 64, ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+          cp_async16(dst + sw128_off(32 * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
         }
         cp_async_arrive(&raw_full[s]);
       }
@@ -263,16 +279,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
         mbar_wait(&raw_full[s], (it / R) & 1);
         if (g.x3) {
           mbar_wait(&lo_empty[l], ((it / L) & 1) ^ 1);
-          uint8_t* ph = sHi + (size_t)s * halfA;
-          uint8_t* pl = sLo + (size_t)l * halfA;
+          uint8_t* ph = sHi + (size_t)s * kStageBytes + t * 16;
+          uint8_t* pl = sLo + (size_t)l * kStageBytes + t * 16;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int p = t + 128 * i;
-            const uint32_t off = (p & 7) * lboA + (p >> 3) * 16;
+          for (int i = 0; i < 8; ++i) {           // elementwise: any bijection of the 1024 chunks works
             float4 hi, lo;
-            split4(*reinterpret_cast<const float4*>(ph + off), hi, lo);
-            *reinterpret_cast<float4*>(ph + off) = hi;
-            *reinterpret_cast<float4*>(pl + off) = lo;
+            split4(*reinterpret_cast<const float4*>(ph + i * 2048), hi, lo);
+            *reinterpret_cast<float4*>(ph + i * 2048) = hi;
+            *reinterpret_cast<float4*>(pl + i * 2048) = lo;
           }
         }
         fence_proxy_async();
@@ -294,15 +308,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
           const int s = it % R, l = it % L;
           mbar_wait(&full[s], (it / R) & 1);
           tc_fence_after();
-          const uint32_t a_hi = hiBase + s * halfA, a_lo = loBase + l * halfA;
+          const uint32_t a_hi = hiBase + s * kStageBytes, a_lo = loBase + l * kStageBytes;
+          const uint32_t b_hi = bBase + kc * blockB, b_lo = b_hi + halfB;
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 8; ++kk) {
-            const uint32_t b_hi = bBase + (kc * (kChunkK / 4) + kk * 2) * lboB, b_lo = b_hi + halfB;
-            const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi, lboB, 128);
+            const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
             umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
             if (g.x3) {
-              umma_tf32(dc, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, (kc | kk) != 0);
-              umma_tf32(dc, dAh, make_desc(b_lo, lboB, 128), idesc, 1);
+              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, (kc | kk) != 0);
+              umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
             }
           }
           umma_commit(&hi_empty[s]);
@@ -603,9 +617,8 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 // ---- eligibility + launchers (called from linear.cu) -------------------------------------------
 // rows kernel: contraction Kc % 32 == 0, output columns Nb % 16 == 0 and <= 128 per launch, weights resident.
 static size_t rows_smem(int Kc, int Nb, int stages, int lo_stages) {
-  const size_t halfB = (size_t)(Kc / 4) * (Nb * 16 + 16);
-  const size_t halfA = (size_t)(kChunkK / 4) * (kBlockM * 16 + 16);
-  return 2 * halfB + (size_t)(stages + lo_stages) * halfA + kEpiWarps * kEpiWarpBytes + 512;
+  const size_t halfB = (size_t)(Kc / kChunkK) * Nb * 128;
+  return 2 * halfB + (size_t)(stages + lo_stages) * kStageBytes + kEpiWarps * kEpiWarpBytes + 512 + 1024;
 }
 
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y) {
