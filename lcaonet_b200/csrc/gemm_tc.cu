@@ -391,51 +391,40 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
 }
 
 // =================================================================================================
-// Kernel 2: weight gradient   dW[128, Kx] += sum_m pro(dY)[m, 0:128]^T X[m, 0:Kx] ,  db += colsum(pro(dY))
-// Both operands stream; the contraction runs over the rows m, so the row-major HBM tiles have to be
-// TRANSPOSED into the K-major layout of kernel 1: element (col, m) at (m/4)*LBO + col*16 + (m%4)*4.
-// Each transform thread owns 4x4 blocks (4 consecutive rows x 4 consecutive columns): four 128-bit
-// loads, a register transpose, four 128-bit shared stores; lanes of a quarter-warp differ in the row
-// group, so the padded LBO keeps the stores conflict free.  One TMEM accumulator per CTA (its row
-// range is contiguous), flushed with red.global.add at the end.
+// Kernel 2: weight gradient   dW[128, Kx] += sum_m dY[m, 0:128]^T X[m, 0:Kx] ,  db += colsum(dY)
+// Both operands stream and the contraction runs over the rows m, so the row-major HBM tiles have to be
+// TRANSPOSED into K-major operand tiles.  Pipeline (416 threads):
+//   loaders (warps 9-12): cp.async 32-row chunks of dY and X into a raw row-major ring (16-byte pieces
+//       XOR-swizzled by (row/4) so the transposing reads below are conflict free), 2-3 chunks ahead;
+//   transform (warps 4-7): 4x4 register transposes raw -> SWIZZLE_128B K-major {A,B} x {hi,lo} tiles;
+//   MMA (warp 8): short TMEM chains (8 chunks = 256 rows; the tensor core truncates on accumulate);
+//   epilogue (warps 0-3): drain each chain into round-to-nearest FP32 registers, red.global.add at the end.
 // =================================================================================================
 struct WgradArgs {
   const float* dY; int64_t ldy;
-  const float* H; int64_t ldh;
   const float* X; int64_t ldx;
   float* dW; int64_t ldw;
   float* db;
-  int64_t M; int Kx; int x3, stages;
+  int64_t M; int Kx; int x3, raw_stages, op_stages;
 };
 
-__device__ __forceinline__ void store_transposed(uint8_t* base, uint32_t half, bool x3, const float4 (&r)[4]) {
-  // r[i] = row i, 4 consecutive columns;  column j becomes one 16-byte K-vector (rows 0..3)
-  const float4 c[4] = {make_float4(r[0].x, r[1].x, r[2].x, r[3].x), make_float4(r[0].y, r[1].y, r[2].y, r[3].y),
-                       make_float4(r[0].z, r[1].z, r[2].z, r[3].z), make_float4(r[0].w, r[1].w, r[2].w, r[3].w)};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float4 hi, lo;
-    split4(c[j], hi, lo);
-    *reinterpret_cast<float4*>(base + j * 16) = hi;
-    if (x3) *reinterpret_cast<float4*>(base + half + j * 16) = lo;
-  }
-}
-
-__global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t lboA = 128 * 16 + 16, lboB = g.Kx * 16 + 16;
-  const uint32_t halfA = (kChunkK / 4) * lboA, halfB = (kChunkK / 4) * lboB;
-  const uint32_t stage_bytes = 2 * halfA + 2 * halfB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)g.stages * stage_bytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + g.stages;
-  uint64_t* tfull = bars + 2 * g.stages;   // [2]
-  uint64_t* tempty = tfull + 2;            // [2]
+  const uint32_t rawA = kChunkK * 512, rawB = kChunkK * g.Kx * 4;     // raw chunk bytes (dY: 128 cols, X: Kx cols)
+  const uint32_t opA = 128 * 128, opB = g.Kx * 128;                   // operand tile bytes (rows x 32 k)
+  const uint32_t op_stage = (g.x3 ? 2 : 1) * (opA + opB);
+  const int Rr = g.raw_stages, S = g.op_stages;
+  uint8_t* sOp = smem_raw;                                            // 1024-aligned tiles first
+  uint8_t* sRaw = sOp + (size_t)S * op_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + (size_t)Rr * (rawA + rawB));
+  uint64_t* raw_full = bars;             // [Rr] loaders -> transform
+  uint64_t* raw_empty = raw_full + Rr;   // [Rr] transform -> loaders
+  uint64_t* op_full = raw_empty + Rr;    // [S]  transform -> MMA
+  uint64_t* op_empty = op_full + S;      // [S]  MMA -> transform
+  uint64_t* tfull = op_empty + S;        // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  // The tensor core truncates on every accumulate: a TMEM chain is kept to kFlush chunks (256 rows) and then
-  // drained into round-to-nearest FP32 registers of the epilogue warps (double-buffered accumulators, and in
-  // x3 mode separate accumulators for hi*hi and for the small correction products).
   constexpr int kFlush = 8;
   const uint32_t acc_cols = g.x3 ? 2 * g.Kx : g.Kx;
   const uint32_t need_cols = 2 * acc_cols;
@@ -447,9 +436,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
   const int64_t c_beg = min(nchunks, (int64_t)blockIdx.x * per), c_end = min(nchunks, c_beg + per);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(&full[s], kProdWarps * 32);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < Rr; ++s) {
+      mbar_init(&raw_full[s], kLoadWarps * 32);
+      mbar_init(&raw_empty[s], 4 * 32);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&op_full[s], 4 * 32);
+      mbar_init(&op_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -468,52 +461,88 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
     return;
   }
 
-  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
-    // ============================== producer / transform warps ==============================
-    const int t = threadIdx.x - kEpiWarps * 32;  // 0..127
-    const int kg = t & 7, g0 = t >> 3;           // row group (4 rows) x first column group
+  if (warp >= 9) {
+    // ============================== loader warps ==============================
+    // raw tile: row r (0..31) at r*pitch, 16-byte piece q stored at piece (q ^ (r >> 2)); lanes 0-7 of an
+    // instruction copy 8 consecutive pieces of one row = one full 128-byte line on both sides.
+    const int lw = warp - 9, r_in = lane >> 3, pl = lane & 7;
+    const uint32_t raw_base = smem_u32(sRaw);
+    const int pgB = g.Kx / 32;  // 128-byte piece groups per X row
+    uint32_t it = 0;
+    for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+      const int s = it % Rr;
+      mbar_wait(&raw_empty[s], ((it / Rr) & 1) ^ 1);
+      const uint32_t dA = raw_base + s * (rawA + rawB), dB = dA + rawA;
+      const int64_t m0 = c * kChunkK;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // dY: 32 rows x 4 piece groups; this warp: rows 8 lw .. 8 lw + 7
+        const int r = 8 * lw + (j & 1) * 4 + r_in, pg = j >> 1;
+        const bool ok = m0 + r < g.M;
+        cp_async16(dA + r * 512 + (((pg * 8 + pl) ^ (r >> 2)) << 4), ok ? g.dY + (m0 + r) * g.ldy + (pg * 8 + pl) * 4 : g.dY,
+                   ok ? 16u : 0u);
+      }
+      for (int j = 0; j < 2 * pgB; ++j) {
+        const int r = 8 * lw + (j & 1) * 4 + r_in, pg = j >> 1;
+        const bool ok = m0 + r < g.M;
+        cp_async16(dB + r * (g.Kx * 4) + (((pg * 8 + pl) ^ (r >> 2)) << 4), ok ? g.X + (m0 + r) * g.ldx + (pg * 8 + pl) * 4 : g.X,
+                   ok ? 16u : 0u);
+      }
+      cp_async_arrive(&raw_full[s]);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================== transform warps ==============================
+    const int t = threadIdx.x - 128;             // 0..127
+    const int kg = t & 7, g0 = t >> 3;           // 4-row group of the chunk, first 4-column group
     const int ngB = g.Kx / 4;
     float4 colsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     uint32_t it = 0;
     for (int64_t c = c_beg; c < c_end; ++c, ++it) {
-      const int s = it % g.stages;
-      mbar_wait(&empty[s], ((it / g.stages) & 1) ^ 1);
-      uint8_t* st = smem_raw + (size_t)s * stage_bytes;
-      const int64_t m0 = c * kChunkK + kg * 4;
-      // ---- A operand: pro(dY) columns 0..127 (32 column groups, 2 per thread)
+      const int r = it % Rr, s = it % S;
+      mbar_wait(&raw_full[r], (it / Rr) & 1);
+      mbar_wait(&op_empty[s], ((it / S) & 1) ^ 1);
+      const uint8_t* rA = sRaw + (size_t)r * (rawA + rawB);
+      const uint8_t* rB = rA + rawA;
+      uint8_t* oA = sOp + (size_t)s * op_stage;
+      uint8_t* oB = oA + (g.x3 ? 2 : 1) * opA;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 2; ++i) {              // A operand rows = dY columns: 32 column groups, 2 per thread
         const int ng = g0 + 16 * i;
-        float4 r[4];
+        float4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t m = m0 + q;
-          r[q] = (m < g.M) ? ldg4(g.dY + m * g.ldy + ng * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (g.H) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int64_t m = m0 + q;
-            if (m < g.M) r[q] = silu_grad4(r[q], ldg4(g.H + m * g.ldh + ng * 4));
-          }
-        }
+        for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(rA + (4 * kg + q) * 512 + ((ng ^ kg) << 4));
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          colsum[i] = make_float4(colsum[i].x + r[q].x, colsum[i].y + r[q].y, colsum[i].z + r[q].z, colsum[i].w + r[q].w);
-        store_transposed(st + kg * lboA + ng * 64, halfA, g.x3, r);
-      }
-      // ---- B operand: X columns 0..Kx-1
-      for (int ng = g0; ng < ngB; ng += 16) {
-        float4 r[4];
+          colsum[i] = make_float4(colsum[i].x + v[q].x, colsum[i].y + v[q].y, colsum[i].z + v[q].z, colsum[i].w + v[q].w);
+        const float4 col[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
+                               make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t m = m0 + q;
-          r[q] = (m < g.M) ? ldg4(g.X + m * g.ldx + ng * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) {
+          float4 hi, lo;
+          split4(col[j], hi, lo);
+          const uint32_t off = sw128_off(4 * ng + j, kg);
+          *reinterpret_cast<float4*>(oA + off) = hi;
+          if (g.x3) *reinterpret_cast<float4*>(oA + opA + off) = lo;
         }
-        store_transposed(st + 2 * halfA + kg * lboB + ng * 64, halfB, g.x3, r);
+      }
+      for (int ng = g0; ng < ngB; ng += 16) {    // B operand rows = X columns
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          v[q] = *reinterpret_cast<const float4*>(rB + (4 * kg + q) * (g.Kx * 4) + ((ng ^ kg) << 4));
+        const float4 col[4] = {make_float4(v[0].x, v[1].x, v[2].x, v[3].x), make_float4(v[0].y, v[1].y, v[2].y, v[3].y),
+                               make_float4(v[0].z, v[1].z, v[2].z, v[3].z), make_float4(v[0].w, v[1].w, v[2].w, v[3].w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 hi, lo;
+          split4(col[j], hi, lo);
+          const uint32_t off = sw128_off(4 * ng + j, kg);
+          *reinterpret_cast<float4*>(oB + off) = hi;
+          if (g.x3) *reinterpret_cast<float4*>(oB + opB + off) = lo;
+        }
       }
       fence_proxy_async();
-      mbar_arrive(&full[s]);
+      mbar_arrive(&op_full[s]);
+      mbar_arrive(&raw_empty[r]);
     }
     if (g.db) {
 #pragma unroll
@@ -526,7 +555,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBlockM, g.Kx, 0, 0);
-      const uint32_t base = smem_u32(smem_raw);
+      const uint32_t base = smem_u32(sOp);
       uint32_t it = 0, fl = 0;
       for (int64_t c = c_beg; c < c_end; ++fl) {
         const int acc = fl & 1;
@@ -535,21 +564,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_tc_wgrad(const WgradArgs g) {
         const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Kx;
         const int64_t c_stop = min(c_end, c + kFlush);
         for (int first = 1; c < c_stop; ++c, ++it) {
-          const int s = it % g.stages;
-          mbar_wait(&full[s], (it / g.stages) & 1);
+          const int s = it % S;
+          mbar_wait(&op_full[s], (it / S) & 1);
           tc_fence_after();
-          const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + halfA, b_hi = a_hi + 2 * halfA, b_lo = b_hi + halfB;
+          const uint32_t a_hi = base + s * op_stage, a_lo = a_hi + opA, b_hi = a_hi + (g.x3 ? 2 : 1) * opA, b_lo = b_hi + opB;
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 8; ++kk) {
-            const uint64_t dAh = make_desc(a_hi + kk * 2 * lboA, lboA, 128), dBh = make_desc(b_hi + kk * 2 * lboB, lboB, 128);
+            const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
             umma_tf32(d, dAh, dBh, idesc, !first);
             if (g.x3) {
-              umma_tf32(dc, make_desc(a_lo + kk * 2 * lboA, lboA, 128), dBh, idesc, !first);
-              umma_tf32(dc, dAh, make_desc(b_lo + kk * 2 * lboB, lboB, 128), idesc, 1);
+              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, !first);
+              umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
             }
             first = 0;
           }
-          umma_commit(&empty[s]);
+          umma_commit(&op_empty[s]);
         }
         umma_commit(&tfull[acc]);
       }
@@ -651,25 +680,26 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   return LCAO_OK;
 }
 
-static size_t wgrad_smem(int Kx, int stages) {
-  const size_t halfA = (size_t)(kChunkK / 4) * (128 * 16 + 16), halfB = (size_t)(kChunkK / 4) * (Kx * 16 + 16);
-  return (size_t)stages * (2 * halfA + 2 * halfB) + 256;
+static size_t wgrad_smem(int Kx, int x3, int raw_stages, int op_stages) {
+  const size_t raw = (size_t)kChunkK * (512 + Kx * 4), op = (size_t)(x3 ? 2 : 1) * (128 * 128 + Kx * 128);
+  return (size_t)raw_stages * raw + (size_t)op_stages * op + 512 + 1024;
 }
 
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X) {
   return M >= 512 && Kx % 32 == 0 && Kx >= 32 && Kx <= 128 && ldy % 4 == 0 && ldx % 4 == 0 && al16(dY) && al16(X) &&
-         wgrad_smem(Kx, 2) <= kMaxSmem;
+         wgrad_smem(Kx, 1, 2, 2) <= kMaxSmem;
 }
 
-// dW (128 rows of the weight gradient, row stride ldw) += pro(dY[:, 0:128])^T X[:, 0:Kx]
-int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, const float* X, int64_t ldx, float* dW,
-                  int64_t ldw, float* db, int64_t M, int Kx, int x3, cudaStream_t st) {
+// dW (128 rows of the weight gradient, row stride ldw) += dY[:, 0:128]^T X[:, 0:Kx]
+int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
+                  int Kx, int x3, cudaStream_t st) {
   WgradArgs g{};
-  g.dY = dY; g.ldy = ldy; g.H = H; g.ldh = ldh; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db;
+  g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db;
   g.M = M; g.Kx = Kx; g.x3 = x3;
-  int stages = 4;
-  while (stages > 2 && wgrad_smem(Kx, stages) > kMaxSmem) --stages;
-  g.stages = stages;
+  g.op_stages = 2;
+  int raw_stages = 6;
+  while (raw_stages > 2 && wgrad_smem(Kx, x3, raw_stages, g.op_stages) > kMaxSmem) --raw_stages;
+  g.raw_stages = raw_stages;
   static bool attr_set = false;
   if (!attr_set) {
     LCAO_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -677,7 +707,7 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, con
   }
   const int64_t nchunks = (M + kChunkK - 1) / kChunkK;
   const unsigned grid = (unsigned)(nchunks < num_sms() ? nchunks : num_sms());
-  k_tc_wgrad<<<grid, kThreadsTC, wgrad_smem(Kx, stages), st>>>(g);
+  k_tc_wgrad<<<grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st>>>(g);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -14,8 +14,8 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
                  int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
                  int accumulate, int x3, cudaStream_t st);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
-int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, const float* X, int64_t ldx, float* dW,
-                  int64_t ldw, float* db, int64_t M, int Kx, int x3, cudaStream_t st);
+int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
+                  int Kx, int x3, cudaStream_t st);
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -39,11 +39,11 @@ extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, cons
   return LCAO_OK;
 }
 
-// run the un-fused SiLU' pass into the caller's scratch (CUDA-core path only)
+// dY * act'(H) is materialised once into the caller's scratch (all GEMM kernels take it as a plain operand)
 static int act_bwd_to_scratch(const float*& dY, int64_t& ldy, const float* H, int64_t ldh, int32_t act, int64_t M,
                               int32_t Nout, float* scratch, void* stream, const char* who) {
   if (act == LCAO_ACT_NONE || !H) return LCAO_OK;
-  LCAO_REQUIRE(scratch, "%s: the CUDA-core path needs an (M, Nout) scratch buffer for dY * act'(H)", who);
+  LCAO_REQUIRE(scratch, "%s: an (M, Nout) scratch buffer is needed for dY * act'(H)", who);
   int rc = lcao_act_bwd(dY, ldy, H, ldh, scratch, Nout, M, Nout, act, stream);
   if (rc) return rc;
   dY = scratch;
@@ -56,21 +56,17 @@ static bool dgrad_tc(const float* dY, int64_t ldy, const float* W, const float* 
   return mode != LCAO_GEMM_FP32 && Nout % 32 == 0 && K % 16 == 0 && al16(W) &&
          lcao_tc_rows_ok(M, imin(Nout, 128), imin(K, 128), ldy, ldx, dY, dX);
 }
-static bool wgrad_tc(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
-                     int64_t M, int32_t K, int32_t Nout, int32_t mode) {
-  const bool fuse = act != LCAO_ACT_NONE && H;
-  return mode != LCAO_GEMM_FP32 && Nout % 128 == 0 && (!fuse || (al16(H) && ldh % 4 == 0)) &&
-         lcao_tc_wgrad_ok(M, K, ldy, ldx, dY, X);
+static bool wgrad_tc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t M, int32_t K, int32_t Nout,
+                     int32_t mode) {
+  return mode != LCAO_GEMM_FP32 && Nout % 128 == 0 && lcao_tc_wgrad_ok(M, K, ldy, ldx, dY, X);
 }
 
 extern "C" int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act,
                                            const float* W, const float* X, int64_t ldx, const float* dX, int64_t lddx,
                                            int64_t M, int32_t K, int32_t Nout, int32_t mode) {
-  (void)W; (void)lddx;
-  if (act == LCAO_ACT_NONE || !H) return 0;
-  if (dX) return M * (int64_t)Nout;  // the row-streaming kernels take dY * act'(H) as a plain operand
-  const bool w_ok = !X || wgrad_tc(dY, ldy, H, ldh, act, X, ldx, M, K, Nout, mode);
-  return w_ok ? 0 : M * (int64_t)Nout;
+  (void)dY; (void)ldy; (void)ldh; (void)W; (void)X; (void)ldx; (void)dX; (void)lddx; (void)K; (void)mode;
+  // every GEMM kernel takes dY * act'(H) as a plain operand: one elementwise pass into scratch
+  return (act == LCAO_ACT_NONE || !H) ? 0 : M * (int64_t)Nout;
 }
 
 extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
@@ -105,16 +101,14 @@ extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(dY && X && dW, "lcao_linear_wgrad: null buffer");
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_wgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fuse = act != LCAO_ACT_NONE && H;
-  const bool tc = wgrad_tc(dY, ldy, H, ldh, act, X, ldx, M, K, Nout, mode);
-  if (!tc) {
+  {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_wgrad");
     if (rc) return rc;
-    return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
   }
+  if (!wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode)) return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
   for (int n0 = 0; n0 < Nout; n0 += 128) {
-    int rc = lcao_tc_wgrad(dY + n0, ldy, fuse ? H + n0 : nullptr, ldh, X, ldx, dW + (int64_t)n0 * K, K,
-                           db ? db + n0 : nullptr, M, K, mode == LCAO_GEMM_TF32X3, st);
+    int rc = lcao_tc_wgrad(dY + n0, ldy, X, ldx, dW + (int64_t)n0 * K, K, db ? db + n0 : nullptr, M, K,
+                           mode == LCAO_GEMM_TF32X3, st);
     if (rc) return rc;
   }
   return LCAO_OK;
