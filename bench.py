@@ -150,10 +150,15 @@ def run_reference(args):
 def algorithmic_bytes(name, shp):
     """Compulsory HBM bytes of one launch (FP32), per DESIGN.md §Kernels / SURVEY.md §8d."""
     E, N, O, C, K, NL = shp["E"], shp["N"], shp["O"], shp["C"], shp["K"], shp["NL"]
-    if name == "lcao_threebody_fwd":  # read B (E,NL,C) + unit + CSR + xk rows; write tbw (E,C)
-        return E * (4 * NL * C + 12 + 8 + 4 * C) + N * (4 * C + 8)
-    if name == "lcao_threebody_bwd":  # read B, d_tbw, unit, CSR, xk; write dB (E,NL,C), q (E,C)
-        return E * (4 * NL * C + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+    NP = NL * (NL + 1) // 2
+    if name == "lcao_threebody_fwd":  # read B (E,NL,C) + Gram + unit + CSR + xk rows; write tbw (E,C)
+        return E * (4 * NL * C + 8 * NP + 12 + 8 + 4 * C) + N * (4 * C + 8)
+    if name == "lcao_threebody_bwd":  # read B, Gram, d_tbw, unit, CSR, xk; write dB (E,NL,C), q (E,C)
+        return E * (4 * NL * C + 8 * NP + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+    if name == "lcao_pair_contract_fwd":  # read rb + pair id (table is L2 resident); write B + Gram
+        return E * (4 * O + 8 + 4 * NL * C + 8 * NP)
+    if name == "lcao_pair_contract_bwd":  # read dB + rb + perm; the (P,O,C) result is L2 sized
+        return E * (4 * NL * C + 4 * O + 4)
     if name == "lcao_coeff_contract_fwd":  # read cst' (E,O,C) + rb; write B
         return E * (4 * O * C + 4 * O + 4 * NL * C)
     if name == "lcao_coeff_contract_bwd":  # read dB + rb; write d_cst' (E,O,C)

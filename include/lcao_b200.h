@@ -111,19 +111,42 @@ int lcao_coeff_contract_bwd(const float* cst1, const float* rb, const float* vma
                             const float* dB, int64_t E, int32_t O, int32_t C, int32_t NL, int32_t valence,
                             float* d_cst1, float* d_rb, void* stream);
 
+/* ---- orbital contraction against the species-pair table (lcaonet.py:170 f_coeffs + :180-183,:200-203) --- */
+/* The coefficient rows cst[e] are a function of the element pair (z_s, z_t) only (embed.py:234-249) and
+ * f_coeffs is a bias-free row-wise MLP, so f_coeffs is evaluated on the P-row pair table by the caller and
+ *   B[e,l,:]  = sum_{o: l(o)=l} rb[e,o] * (tabA[pair[e],o,:] + m[e,o] tabV[pair[e],o,:])      l = 0..NL-1
+ *   B[e,NL,:] = sum_o rb[e,o] m[e,o] tabV[pair[e],o,:]                                        (only if valence)
+ * with tab (P,O,Cp) = [A | V].  gram (nullable): (E, NL(NL+1)/2) FP64 upper triangle of B[e,l,:].B[e,l',:]
+ * over the first NL groups (consumed by lcao_threebody_*). */
+int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, const float* rb, const float* vmask,
+                           const int32_t* lgrp, int64_t E, int32_t O, int32_t C, int32_t NL, int32_t valence,
+                           float* B, double* gram, void* stream);
+/* d_tab (P,O,Cp) = keyed reduction of rb[e,o] dB[e,l(o),:] over the edges of each pair, deterministic
+ * (two stages, no atomics); (kptr (P+1), kperm (E)) = edges grouped by pair (lcao_bucket_sort).
+ * d_rb (E,O) written if non-NULL (autograd forces).  scratch: lcao_pair_contract_bwd_scratch() BYTES. */
+int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, const int32_t* kptr, const int32_t* kperm,
+                           const float* rb, const float* vmask, const int32_t* lgrp, const float* dB, int64_t E,
+                           int64_t P, int32_t O, int32_t C, int32_t NL, int32_t valence, float* d_tab, float* d_rb,
+                           void* scratch, void* stream);
+int64_t lcao_pair_contract_bwd_scratch(int64_t E, int64_t P, int32_t O, int32_t C, int32_t valence);
+/* Gram matrices of an existing B (E,NG,C): gram (E, NL(NL+1)/2) FP64, for callers that built B themselves. */
+int lcao_coeff_gram(const float* B, int32_t NG, int64_t E, int32_t C, int32_t NL, double* gram, void* stream);
+
 /* ---- three-body message passing (lcaonet.py:173-189, shbf.py:75-87) --------------------------- */
 /* tbw[e,:] = sum_{e' in in(s_e), e' != e} normalize( sum_l Y_l(unit[e].unit[e']) B[e',l,:] ) * sigmoid(xk[src[e'],:])
- * B has NG groups per edge (row stride NG*C); xk (N,C) with row stride ldxk. */
-int lcao_threebody_fwd(const float* B, int32_t NG, const float* unit, const float* xk, int64_t ldxk,
-                       const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+ * B has NG groups per edge (row stride NG*C); gram = its per-edge Gram matrices (|v|^2 = Y^T G Y);
+ * xk (N,C) with row stride ldxk. */
+int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
+                       int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                        const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                        int32_t NL, float* tbw, void* stream);
-/* backward: dB (E,NG,C) groups 0..NL-1 are OVERWRITTEN with the three-body contribution (group NL is
- * zeroed when NG > NL); q (E,C) = per in-edge gradient of the sigmoid gate pre-activation
- * (d_xk[k] = sum_{e' in out(k)} q[e']); d_unit (E,3) written if non-NULL (needs 2 passes' scratch:
- * d_unit_st (E,3) partial for the s->t role). */
-int lcao_threebody_bwd(const float* B, int32_t NG, const float* unit, const float* xk, int64_t ldxk,
-                       const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+/* backward: dB (E,NG,C) groups 0..NL-1 are OVERWRITTEN with the three-body contribution, including the
+ * part that flows through the norms (gram is treated as a function of B); group NL is zeroed when
+ * NG > NL.  q (E,C) = per in-edge gradient of the sigmoid gate pre-activation
+ * (d_xk[k] = sum_{e' in out(k)} q[e']).  d_unit_ks / d_unit_st (E,3; both or neither): gradient w.r.t.
+ * unit[e] from its role as in-edge (k->s) and as out-edge (s->t); d_unit = their sum (autograd forces). */
+int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
+                       int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                        const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                        int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks, float* d_unit_st,
                        void* stream);

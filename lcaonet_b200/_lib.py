@@ -41,8 +41,12 @@ SIGNATURES = {
     "lcao_geom_basis_bwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p],
     "lcao_coeff_contract_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "lcao_coeff_contract_bwd": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
-    "lcao_threebody_fwd": [_p, _i32, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p],
-    "lcao_threebody_bwd": [_p, _i32, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p],
+    "lcao_pair_contract_fwd": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
+    "lcao_pair_contract_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
+    "lcao_coeff_gram": [_p, _i32, _i64, _i32, _i32, _p, _p],
+    "lcao_threebody_fwd": [_p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p],
+    "lcao_threebody_bwd": [_p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p,
+                           _p],
     "lcao_twobody_fwd": [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p],
     "lcao_twobody_bwd": [_p, _i32, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p],
     "lcao_edge_pair_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p],
@@ -72,6 +76,8 @@ def load():
     lib.lcao_launch_count.restype = C.c_int64
     lib.lcao_linear_bwd_scratch.restype = C.c_int64
     lib.lcao_linear_bwd_scratch.argtypes = [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32]
+    lib.lcao_pair_contract_bwd_scratch.restype = C.c_int64
+    lib.lcao_pair_contract_bwd_scratch.argtypes = [_i64, _i64, _i32, _i32, _i32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -1,0 +1,308 @@
+// Orbital contraction against the SPECIES-PAIR coefficient table (lcaonet.py:170,180-183,200-203).
+//
+// The reference evaluates f_coeffs on all E*O coefficient rows.  Those rows are a function of the
+// element pair (z_s, z_t) only (embed.py:234-249: cst[e] = BN(fe[z_t] * (1 + fz[z_s, z_t])), and
+// f_coeffs has no bias and acts row-wise), so the same numbers are obtained by running f_coeffs on the
+// P = (max_z+1)^2 table rows (a few thousand GEMM rows instead of E*O ~ 2 M) and contracting
+//     B[e,l,:] = sum_{o in l} rb[e,o] * tab[pair_e, o, :]
+// per edge.  The table (P*O*C' floats, 5.6 MB at the default sizes) is L2 resident, so this kernel's
+// HBM traffic is the B it writes.  Backward: d_tab[p,o,:] = sum_{e: pair_e = p} rb[e,o] dB[e,l(o),:]
+// is a keyed reduction done in two deterministic stages (per-chunk partials in sorted order, then a
+// per-key sum in chunk order): no atomics.
+//
+// The kernel also emits the per-edge Gram matrix G[e,l,l'] = B[e,l,:].B[e,l',:] (FP64, upper
+// triangle) that the three-body kernels use for the triplet norms (threebody.cu).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kChunk = 512;  // sorted entries per stage-1 CTA of the keyed reduction
+
+__device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4fma(float a, float4 x, float4 acc) {
+  acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y); acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+  return acc;
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ double dot4d(float4 a, float4 b) {
+  return (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per edge; lane owns float4 column lane (+32 for C > 128)
+template <int NL, bool VAL>
+__global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
+    const float* __restrict__ tab, const int64_t* __restrict__ pair, const float* __restrict__ rb,
+    const float* __restrict__ vmask, const int32_t* __restrict__ lgrp, int64_t E, int O, int C, float* __restrict__ B,
+    double* __restrict__ gram) {
+  __shared__ int s_l[LCAO_MAX_ORB];
+  if (threadIdx.x < O) s_l[threadIdx.x] = lgrp[threadIdx.x];
+  __syncthreads();
+  const int64_t e = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int NG = NL + (VAL ? 1 : 0), NP = NL * (NL + 1) / 2;
+  const int Cp = VAL ? 2 * C : C;
+  const float* row = tab + pair[e] * (int64_t)O * Cp;
+  double g[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) g[i] = 0.0;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 acc[NL + 1];
+#pragma unroll
+    for (int l = 0; l <= NL; ++l) acc[l] = f4z();
+#pragma unroll 4
+    for (int o = 0; o < O; ++o) {
+      const float r = __ldg(rb + e * O + o);
+      float4 t = ldg4(row + (int64_t)o * Cp + c);
+      t = make_float4(r * t.x, r * t.y, r * t.z, r * t.w);
+      if (VAL) {
+        const float rm = r * __ldg(vmask + e * O + o);
+        float4 v = ldg4(row + (int64_t)o * Cp + C + c);
+        v = make_float4(rm * v.x, rm * v.y, rm * v.z, rm * v.w);
+        acc[NL] = f4add(acc[NL], v);
+        t = f4add(t, v);
+      }
+      const int l = s_l[o];
+#pragma unroll
+      for (int k = 0; k < NL; ++k)
+        if (l == k) acc[k] = f4add(acc[k], t);
+    }
+#pragma unroll
+    for (int l = 0; l < NG; ++l) st4(B + (e * NG + l) * (int64_t)C + c, acc[l]);
+    if (gram) {
+      int i = 0;
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = a; b < NL; ++b) g[i++] += dot4d(acc[a], acc[b]);
+    }
+  }
+  if (gram) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const double s = warp_sum_d(g[i]);
+      if (lane == 0) gram[e * NP + i] = s;
+    }
+  }
+}
+
+// Gram matrix of an existing B (E,NG,C): upper triangle over the first NL groups, FP64
+template <int NL>
+__global__ void __launch_bounds__(kWarps * 32) k_gram(const float* __restrict__ B, int NG, int64_t E, int C,
+                                                      double* __restrict__ gram) {
+  const int64_t e = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int NP = NL * (NL + 1) / 2;
+  double g[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) g[i] = 0.0;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 b[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) b[l] = ldg4(B + (e * NG + l) * (int64_t)C + c);
+    int i = 0;
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int bb = a; bb < NL; ++bb) g[i++] += dot4d(b[a], b[bb]);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const double s = warp_sum_d(g[i]);
+    if (lane == 0) gram[e * NP + i] = s;
+  }
+}
+
+// d_rb[e,o] = tab[p,o,:C].dB[e,l(o),:] + m[e,o] tab[p,o,C:].(dB[e,l(o),:] + dB[e,NL,:])   (autograd forces)
+template <bool VAL>
+__global__ void __launch_bounds__(kWarps * 32) k_pair_contract_drb(
+    const float* __restrict__ tab, const int64_t* __restrict__ pair, const float* __restrict__ vmask,
+    const int32_t* __restrict__ lgrp, const float* __restrict__ dB, int64_t E, int O, int C, int NL,
+    float* __restrict__ d_rb) {
+  const int64_t e = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int Cp = VAL ? 2 * C : C, NG = NL + (VAL ? 1 : 0);
+  const float* row = tab + pair[e] * (int64_t)O * Cp;
+  for (int o = 0; o < O; ++o) {
+    const int l = lgrp[o];
+    const float m = VAL ? __ldg(vmask + e * O + o) : 0.f;
+    float dot = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 g = ldg4(dB + (e * NG + l) * (int64_t)C + c);
+      const float4 a = ldg4(row + (int64_t)o * Cp + c);
+      dot += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+      if (VAL) {
+        const float4 gv = f4add(g, ldg4(dB + (e * NG + NL) * (int64_t)C + c));
+        const float4 v = ldg4(row + (int64_t)o * Cp + C + c);
+        dot += m * (v.x * gv.x + v.y * gv.y + v.z * gv.z + v.w * gv.w);
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) d_rb[e * O + o] = dot;
+  }
+}
+
+// ---- keyed reduction, stage 0: cptr[k] = exclusive scan of ceil(count_k / kChunk)   (single CTA)
+__global__ void __launch_bounds__(1024) k_chunk_ptr(const int32_t* __restrict__ kptr, int P, int32_t* __restrict__ cptr) {
+  __shared__ int32_t part[1024];
+  const int per = (P + 1023) / 1024;
+  const int lo = min(P, (int)threadIdx.x * per), hi = min(P, lo + per);
+  int32_t s = 0;
+  for (int k = lo; k < hi; ++k) s += (kptr[k + 1] - kptr[k] + kChunk - 1) / kChunk;
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    const int32_t v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int32_t run = part[threadIdx.x] - s;
+  for (int k = lo; k < hi; ++k) {
+    cptr[k] = run;
+    run += (kptr[k + 1] - kptr[k] + kChunk - 1) / kChunk;
+  }
+  if (threadIdx.x == 1023) cptr[P] = part[1023];
+}
+
+// ---- stage 1: CTA = one chunk of one key; thread = one (o, float4 column); partial[chunk][o][Cp]
+template <bool VAL>
+__global__ void __launch_bounds__(256) k_pair_reduce_partial(
+    const int32_t* __restrict__ kptr, const int32_t* __restrict__ kperm, const int32_t* __restrict__ cptr, int P,
+    const float* __restrict__ rb, const float* __restrict__ vmask, const int32_t* __restrict__ lgrp,
+    const float* __restrict__ dB, int O, int C, int NL, float* __restrict__ partial) {
+  const int chunk = blockIdx.x;
+  if (chunk >= cptr[P]) return;
+  int lo = 0, hi = P;  // last key with cptr[key] <= chunk (keys without entries have empty chunk ranges)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cptr[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  const int key = lo;
+  const int C4 = C >> 2;
+  const int w = blockIdx.y * 256 + threadIdx.x;
+  if (w >= O * C4) return;
+  const int o = w / C4, c = (w - o * C4) * 4;
+  const int l = lgrp[o];
+  const int NG = NL + (VAL ? 1 : 0), Cp = VAL ? 2 * C : C;
+  const int32_t j0 = kptr[key] + (chunk - cptr[key]) * kChunk;
+  const int32_t j1 = min(j0 + kChunk, kptr[key + 1]);
+  float4 accA = f4z(), accV = f4z();
+#pragma unroll 4
+  for (int32_t j = j0; j < j1; ++j) {
+    const int64_t e = kperm[j];
+    const float r = __ldg(rb + e * O + o);
+    const float4 g = ldg4(dB + (e * NG + l) * (int64_t)C + c);
+    accA = f4fma(r, g, accA);
+    if (VAL) {
+      const float rm = r * __ldg(vmask + e * O + o);
+      accV = f4fma(rm, f4add(g, ldg4(dB + (e * NG + NL) * (int64_t)C + c)), accV);
+    }
+  }
+  float* out = partial + ((int64_t)chunk * O + o) * Cp + c;
+  st4(out, accA);
+  if (VAL) st4(out + C, accV);
+}
+
+// ---- stage 2: d_tab[key][o][:] = sum of the key's partials in chunk order (zeros for absent keys)
+__global__ void __launch_bounds__(256) k_pair_reduce_final(const int32_t* __restrict__ cptr, int P, int W4,
+                                                           const float* __restrict__ partial,
+                                                           float* __restrict__ d_tab) {
+  const int64_t t = blockIdx.x * 256ll + threadIdx.x;
+  if (t >= (int64_t)P * W4) return;
+  const int key = (int)(t / W4);
+  const int c = (int)(t - (int64_t)key * W4) * 4;
+  float4 acc = f4z();
+  for (int32_t q = cptr[key]; q < cptr[key + 1]; ++q) acc = f4add(acc, ldg4(partial + (int64_t)q * W4 * 4 + c));
+  st4(d_tab + (int64_t)key * W4 * 4 + c, acc);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, const float* rb, const float* vmask,
+                                      const int32_t* lgrp, int64_t E, int32_t O, int32_t C, int32_t NL,
+                                      int32_t valence, float* B, double* gram, void* stream) {
+  if (E == 0) return LCAO_OK;
+  LCAO_REQUIRE(tab && pair && rb && lgrp && B && (!valence || vmask), "lcao_pair_contract_fwd: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && C > 0 && O > 0 && O <= LCAO_MAX_ORB && NL >= 1 && NL <= 4,
+               "lcao_pair_contract_fwd: need C %% 4 == 0, O <= %d, 1 <= NL <= 4 (got C=%d O=%d NL=%d)", LCAO_MAX_ORB, C, O, NL);
+  LCAO_REQUIRE(al16(tab) && al16(B), "lcao_pair_contract_fwd: buffers must be 16-byte aligned");
+  const unsigned grid = (unsigned)ceil_div64(E, kWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PC_CALL(nl, val) k_pair_contract_fwd<nl, val><<<grid, kWarps * 32, 0, st>>>(tab, pair, rb, vmask, lgrp, E, O, C, B, gram)
+  if (valence) {
+    switch (NL) { case 1: PC_CALL(1, true); break; case 2: PC_CALL(2, true); break; case 3: PC_CALL(3, true); break; default: PC_CALL(4, true); }
+  } else {
+    switch (NL) { case 1: PC_CALL(1, false); break; case 2: PC_CALL(2, false); break; case 3: PC_CALL(3, false); break; default: PC_CALL(4, false); }
+  }
+#undef PC_CALL
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_coeff_gram(const float* B, int32_t NG, int64_t E, int32_t C, int32_t NL, double* gram, void* stream) {
+  if (E == 0) return LCAO_OK;
+  LCAO_REQUIRE(B && gram, "lcao_coeff_gram: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && C > 0 && NL >= 1 && NL <= 4 && NG >= NL && al16(B), "lcao_coeff_gram: need C %% 4 == 0, 1 <= NL <= 4, NG >= NL");
+  const unsigned grid = (unsigned)ceil_div64(E, kWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (NL) {
+    case 1: k_gram<1><<<grid, kWarps * 32, 0, st>>>(B, NG, E, C, gram); break;
+    case 2: k_gram<2><<<grid, kWarps * 32, 0, st>>>(B, NG, E, C, gram); break;
+    case 3: k_gram<3><<<grid, kWarps * 32, 0, st>>>(B, NG, E, C, gram); break;
+    default: k_gram<4><<<grid, kWarps * 32, 0, st>>>(B, NG, E, C, gram); break;
+  }
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int64_t lcao_pair_contract_bwd_scratch(int64_t E, int64_t P, int32_t O, int32_t C, int32_t valence) {
+  const int64_t chunks = ceil_div64(E, kChunk) + P;
+  const int64_t Cp = valence ? 2 * (int64_t)C : C;
+  return ((P + 1 + 3) / 4) * 16 + chunks * O * Cp * (int64_t)sizeof(float);  // bytes: cptr (padded to 16) + partials
+}
+
+extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, const int32_t* kptr, const int32_t* kperm,
+                                      const float* rb, const float* vmask, const int32_t* lgrp, const float* dB,
+                                      int64_t E, int64_t P, int32_t O, int32_t C, int32_t NL, int32_t valence,
+                                      float* d_tab, float* d_rb, void* scratch, void* stream) {
+  LCAO_REQUIRE(P > 0 && P < (1 << 30) && d_tab && scratch && kptr, "lcao_pair_contract_bwd: null buffer");
+  LCAO_REQUIRE(E == 0 || (kperm && rb && lgrp && dB && (!valence || vmask)), "lcao_pair_contract_bwd: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && C > 0 && O > 0 && O <= LCAO_MAX_ORB && NL >= 1 && NL <= 4,
+               "lcao_pair_contract_bwd: need C %% 4 == 0, O <= %d, 1 <= NL <= 4", LCAO_MAX_ORB);
+  LCAO_REQUIRE(al16(dB) && al16(d_tab) && al16(scratch), "lcao_pair_contract_bwd: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* cptr = static_cast<int32_t*>(scratch);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((P + 1 + 3) / 4) * 16);
+  const int Cp = valence ? 2 * C : C;
+  const int64_t chunks = ceil_div64(E, kChunk) + P;
+  k_chunk_ptr<<<1, 1024, 0, st>>>(kptr, (int)P, cptr);
+  LCAO_LAUNCH_CHECK();
+  if (E > 0) {
+    dim3 grid((unsigned)chunks, (unsigned)ceil_div64((int64_t)O * (C / 4), 256));
+    if (valence) k_pair_reduce_partial<true><<<grid, 256, 0, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
+    else k_pair_reduce_partial<false><<<grid, 256, 0, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
+    LCAO_LAUNCH_CHECK();
+  }
+  const int W4 = O * Cp / 4;
+  k_pair_reduce_final<<<(unsigned)ceil_div64(P * W4, 256), 256, 0, st>>>(cptr, (int)P, W4, partial, d_tab);
+  LCAO_LAUNCH_CHECK();
+  if (d_rb && E > 0) {
+    LCAO_REQUIRE(tab && pair, "lcao_pair_contract_bwd: d_rb needs tab and pair");
+    const unsigned grid = (unsigned)ceil_div64(E, kWarps);
+    if (valence) k_pair_contract_drb<true><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
+    else k_pair_contract_drb<false><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
+    LCAO_LAUNCH_CHECK();
+  }
+  return LCAO_OK;
+}

@@ -162,11 +162,28 @@ class EmbedCoeffs(nn.Module):
         self.bn = nn.BatchNorm1d(emb_size * n_orb)
 
 
+class PairCoeffs:
+    """The reference's coefficient tensor `cst` (E, O, K) (embed.py:234-249) in factored form.
+
+    cst[e] depends on the element pair (z_s, z_t) of the edge only, so it is kept as the P = (max_z+1)^2
+    row table plus the pair index of every edge.  The interaction blocks apply their bias-free,
+    row-wise f_coeffs MLP to the table rows and contract against the radial basis per edge
+    (`ops.pair_contract`): the (E, O, K) tensor and the E*O-row GEMMs of the reference never exist.
+    `materialize()` returns the reference-shaped tensor for callers that want it."""
+
+    def __init__(self, table: Tensor, pair: Tensor, kptr: Tensor | None, kperm: Tensor | None):
+        self.table, self.pair, self.kptr, self.kperm = table, pair, kptr, kperm
+
+    def materialize(self) -> Tensor:
+        P, O, K = self.table.shape
+        return ops.gather_rows(self.table.reshape(P, O * K), self.pair, self.kptr, self.kperm).reshape(-1, O, K)
+
+
 class LCAOEmbedding(nn.Module):
     """Embedding block (reference lcaonet.py:30-74, embed.py).  Everything here depends on the atomic
     numbers only: x[n] on z_n, cst[e] on the pair (z_s, z_t).  The dense layers and both BatchNorms
-    therefore run on the (max_z+1)- and (max_z+1)^2-row tables (count-weighted statistics), and the only
-    edge-sized work is one row gather (forward) / one keyed reduction (backward) in CUDA."""
+    therefore run on the (max_z+1)- and (max_z+1)^2-row tables (count-weighted statistics); the
+    coefficient tensor is returned in factored form (`PairCoeffs`), so no edge-sized work happens here."""
 
     def __init__(self, emb_size, emb_size_coeff, elec_info, max_z, use_elec, extend_orb, activation=nn.SiLU(),
                  weight_init=None):
@@ -211,8 +228,7 @@ class LCAOEmbedding(nn.Module):
             kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
         else:
             kptr = kperm = None
-        cst = ops.gather_rows(ctab, pair, kptr, kperm).reshape(-1, O, K)
-        return x, cst
+        return x, PairCoeffs(ctab.reshape(Zd * Zd, O, K), pair, kptr, kperm)
 
 
 class LCAOInteraction(nn.Module):
@@ -240,9 +256,13 @@ class LCAOInteraction(nn.Module):
         C = self.emb_size_conv
         nw = self.node_weight(x)  # (N, 2C): [:, :C] feeds f_node, [:, C:] is the three-body gate
         xc, xk = nw[:, :C], nw[:, C:]
-        cst1 = _mlp(self.f_coeffs, cst)  # (E, O, C')
-        B = ops.coeff_contract(cst1, rb, vmask, lgrp, NL, C)  # (E, NL(+1), C)
-        tbw = ops.threebody(B, unit, xk, gi, NL)  # (E, C)
+        if isinstance(cst, PairCoeffs):  # f_coeffs on the species-pair table, contracted per edge
+            tab = _mlp(self.f_coeffs, cst.table)  # (P, O, C')
+            B, gram = ops.pair_contract(tab, cst.pair, cst.kptr, cst.kperm, rb, vmask, lgrp, NL, C)  # (E, NL(+1), C)
+        else:  # a materialised (E, O, K) coefficient tensor, as in the reference signature
+            cst1 = _mlp(self.f_coeffs, cst)  # (E, O, C')
+            B, gram = ops.coeff_contract(cst1, rb, vmask, lgrp, NL, C), None
+        tbw = ops.threebody(B, unit, xk, gi, NL, gram)  # (E, C)
         g = self.f_three[0](tbw)  # (E, C')
         lw = ops.twobody(B, g, NL, 1 if self.add_valence else 0)  # (E, C)
         bw = self.basis_weight(lw)

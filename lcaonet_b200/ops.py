@@ -14,7 +14,7 @@ from torch import Tensor
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SILU, call, ptr, require_cuda, stream_ptr
+from ._lib import ACT_NONE, ACT_SILU, LcaoError, call, ptr, require_cuda, stream_ptr
 
 # GEMM arithmetic mode for the dense layers: fp32 CUDA cores, 3xTF32 tcgen05 (fp32-equivalent), 1xTF32
 GEMM_MODES = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "tf32": _lib.GEMM_TF32}
@@ -244,43 +244,100 @@ def coeff_contract(cst1, rb, vmask, lgrp, NL, C):
     return _CoeffContract.apply(cst1, rb.contiguous(), vmask, lgrp, NL, C)
 
 
+class _PairContract(torch.autograd.Function):
+    """B and its Gram matrices from the species-pair coefficient table (see lcao_pair_contract_fwd)."""
+
+    @staticmethod
+    def forward(ctx, tab, pair, kptr, kperm, rb, vmask, lgrp, NL: int, C: int):
+        require_cuda(tab, pair, rb)
+        tab = tab.contiguous()
+        P, O, Cp = tab.shape
+        E = pair.numel()
+        valence = 1 if vmask is not None else 0
+        assert Cp == C * (1 + valence) and pair.dtype == torch.int64
+        NG = NL + valence
+        B = torch.empty(E, NG, C, device=tab.device)
+        gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=tab.device)
+        _call("lcao_pair_contract_fwd", ptr(tab), ptr(pair), ptr(rb), ptr(vmask), ptr(lgrp), E, O, C, NL, valence, ptr(B),
+              ptr(gram), stream_ptr())
+        ctx.dims = (E, P, O, C, NL, valence)
+        ctx.save_for_backward(tab, pair, kptr, kperm, rb, vmask, lgrp)
+        ctx.mark_non_differentiable(gram)
+        return B, gram
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dB, _dgram):
+        tab, pair, kptr, kperm, rb, vmask, lgrp = ctx.saved_tensors
+        E, P, O, C, NL, valence = ctx.dims
+        if kptr is None:
+            raise LcaoError("pair_contract: the (kptr, kperm) grouping of edges by pair is needed for the backward pass")
+        dB = dB.contiguous()
+        d_tab = torch.empty_like(tab)
+        d_rb = torch.empty_like(rb) if ctx.needs_input_grad[4] else None
+        nbytes = int(_lib.load().lcao_pair_contract_bwd_scratch(E, P, O, C, valence))
+        scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.int32, device=tab.device)
+        _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB),
+              E, P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), stream_ptr())
+        return d_tab, None, None, None, d_rb, None, None, None, None
+
+
+def pair_contract(tab, pair, kptr, kperm, rb, vmask, lgrp, NL, C):
+    """(B, gram): B[e,l,:] = sum_{o in l} rb[e,o] tab[pair[e],o,:] (+ valence slot) — the orbital sums of
+    lcaonet.py:180-183 and :200-203 with f_coeffs (lcaonet.py:170) evaluated on the species-pair table."""
+    return _PairContract.apply(tab, pair, kptr, kperm, rb.contiguous(), vmask, lgrp, NL, C)
+
+
+def coeff_gram(B, NL):
+    """(E, NL(NL+1)/2) FP64 Gram matrices B[e,l,:].B[e,l',:] of the first NL groups (no autograd: the
+    three-body backward differentiates through them itself)."""
+    require_cuda(B)
+    E, NG, C = B.shape
+    gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=B.device)
+    _call("lcao_coeff_gram", ptr(B.detach().contiguous()), NG, E, C, NL, ptr(gram), stream_ptr())
+    return gram
+
+
 class _ThreeBody(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, B, unit, xk, gi: GraphIndex, NL: int):
+    def forward(ctx, B, gram, unit, xk, gi: GraphIndex, NL: int):
         require_cuda(B, unit, xk)
+        B, unit = B.contiguous(), unit.contiguous()
         E, NG, C = B.shape
-        assert xk.stride(1) == 1
+        assert xk.stride(1) == 1 and gram.dtype == torch.float64 and gram.is_contiguous()
         tbw = torch.empty(E, C, device=B.device)
-        _call("lcao_threebody_fwd", ptr(B), NG, ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr), ptr(gi.in_edge),
-              ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(tbw), stream_ptr())
+        _call("lcao_threebody_fwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr),
+              ptr(gi.in_edge), ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(tbw), stream_ptr())
         ctx.gi, ctx.NL = gi, NL
-        ctx.save_for_backward(B, unit, xk)
+        ctx.save_for_backward(B, gram, unit, xk)
         return tbw
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_tbw):
-        B, unit, xk = ctx.saved_tensors
+        B, gram, unit, xk = ctx.saved_tensors
         gi, NL = ctx.gi, ctx.NL
         E, NG, C = B.shape
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("gradients w.r.t. edge directions (autograd forces through the three-body "
-                                      "term) are not implemented yet")
         d_tbw = d_tbw.contiguous()
         dB = torch.empty_like(B)
         q = torch.empty(E, C, device=B.device)
         st = stream_ptr()
-        _call("lcao_threebody_bwd", ptr(B), NG, ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr), ptr(gi.in_edge),
-              ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(d_tbw), ptr(dB), ptr(q), None,
-              None, st)
+        forces = ctx.needs_input_grad[2]
+        du_ks = torch.empty(E, 3, device=B.device) if forces else None
+        du_st = torch.empty(E, 3, device=B.device) if forces else None
+        _call("lcao_threebody_bwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr),
+              ptr(gi.in_edge), ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(d_tbw), ptr(dB),
+              ptr(q), ptr(du_ks), ptr(du_st), st)
         d_xk = torch.empty(gi.N, C, device=B.device)
         _call("lcao_segment_sum", ptr(q), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, C, 0, ptr(d_xk), C, st)
-        return dB, None, d_xk, None, None
+        return dB, None, (du_ks + du_st) if forces else None, d_xk, None, None
 
 
-def threebody(B, unit, xk, gi, NL):
+def threebody(B, unit, xk, gi, NL, gram=None):
     """Fused gather / angular basis / normalise / gate / triplet->edge sum (lcaonet.py:173-189)."""
-    return _ThreeBody.apply(B, unit, xk, gi, NL)
+    if gram is None:
+        gram = coeff_gram(B, NL)
+    return _ThreeBody.apply(B, gram, unit, xk, gi, NL)
 
 
 class _TwoBody(torch.autograd.Function):

@@ -58,6 +58,11 @@ def run_case(name, kwargs, graph, training=True):
             loss = (energy**2).mean()
         res[f"energy_{tag}"] = energy.detach().clone()
         res[f"loss_{tag}"] = loss.detach().clone()
+        if isinstance(out, tuple) and tag == "f64":
+            # gradient of the ENERGY term alone: what an implementation without double backward can be checked on
+            ge = torch.autograd.grad((energy**2).mean(), list(model.parameters()), retain_graph=True, allow_unused=True)
+            res["grads_energy_f64"] = {n: (v.to(torch.float32) if v is not None else None)
+                                       for (n, _), v in zip(model.named_parameters(), ge)}
         loss.backward()
         grads = {n: (q.grad.detach().double() if q.grad is not None else None) for n, q in model.named_parameters()}
         if tag == "f64":

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from lcaonet_b200 import ops  # noqa: E402
+from lcaonet_b200 import _lib, ops  # noqa: E402
 from lcaonet_b200.synth import qm9_like_batch  # noqa: E402
 
 DEV = "cuda"
@@ -57,22 +57,44 @@ def edge():
     g = qm9_like_batch(1024, seed=1000).to(DEV)
     N, E, C, NL, O = g["z"].shape[0], g["edge_index"].shape[1], 128, 3, 8
     gi = ops.GraphIndex(g["edge_index"], N)
-    B = torch.randn(E, NL, C, device=DEV)
+    P, st = ops.ptr, ops.stream_ptr
+    # ---- pair-table contraction (f_coeffs evaluated on the (max_z+1)^2 species-pair table)
+    Zd = 37
+    z = g["z"]
+    pair = (z[g["edge_index"][0]] * Zd + z[g["edge_index"][1]]).contiguous()
+    tab = torch.randn(Zd * Zd, O, C, device=DEV)
+    rb = torch.randn(E, O, device=DEV)
+    lgrp = torch.tensor([0, 0, 1, 0, 1, 0, 2, 1], dtype=torch.int32, device=DEV)
+    B = torch.empty(E, NL, C, device=DEV)
+    gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=DEV)
+    t_pf = timeit(lambda: ops._call("lcao_pair_contract_fwd", P(tab), P(pair), P(rb), None, P(lgrp), E, O, C, NL, 0, P(B), P(gram), st()))
+    kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
+    dBr = torch.randn(E, NL, C, device=DEV)
+    d_tab = torch.empty_like(tab)
+    nbytes = int(_lib.load().lcao_pair_contract_bwd_scratch(E, Zd * Zd, O, C, 0))
+    scratch = torch.empty(nbytes // 4 + 4, dtype=torch.int32, device=DEV)
+    t_pb = timeit(lambda: ops._call("lcao_pair_contract_bwd", P(tab), P(pair), P(kptr), P(kperm), P(rb), None, P(lgrp), P(dBr), E,
+                                    Zd * Zd, O, C, NL, 0, P(d_tab), None, P(scratch), st()))
+    bpf = E * (4 * NL * C + 4 * O + 8 + 8 * 6)
+    bpb = E * (4 * NL * C + 4 * O + 4)
+    print(f"pair_contract E={E}: fwd {t_pf:.3f} ms ({bpf/t_pf/1e6:.0f} GB/s) | bwd {t_pb:.3f} ms ({bpb/t_pb/1e6:.0f} GB/s)", flush=True)
+    # ---- three-body
     unit = torch.nn.functional.normalize(torch.randn(E, 3, device=DEV), dim=1)
     xk = torch.randn(N, 2 * C, device=DEV)[:, C:]
     tbw, dB, q = torch.empty(E, C, device=DEV), torch.empty(E, NL, C, device=DEV), torch.empty(E, C, device=DEV)
+    du1, du2 = torch.empty(E, 3, device=DEV), torch.empty(E, 3, device=DEV)
     d_tbw = torch.randn(E, C, device=DEV)
-    P, st = ops.ptr, ops.stream_ptr
-    t_f = timeit(lambda: ops._call("lcao_threebody_fwd", P(B), NL, P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge),
-                                   P(gi.in_src), P(gi.out_ptr), P(gi.out_edge), N, E, C, NL, P(tbw), st()))
-    t_b = timeit(lambda: ops._call("lcao_threebody_bwd", P(B), NL, P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge),
-                                   P(gi.in_src), P(gi.out_ptr), P(gi.out_edge), N, E, C, NL, P(d_tbw), P(dB), P(q), None,
-                                   None, st()))
+    args = (P(B), NL, P(gram), P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge), P(gi.in_src), P(gi.out_ptr),
+            P(gi.out_edge), N, E, C, NL)
+    t_f = timeit(lambda: ops._call("lcao_threebody_fwd", *args, P(tbw), st()))
+    t_b = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), P(dB), P(q), None, None, st()))
+    t_bf = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), P(dB), P(q), P(du1), P(du2), st()))
     T = gi.num_triplets()
-    bf = E * (4 * NL * C + 12 + 8 + 4 * C) + N * (4 * C + 8)
-    bb = E * (4 * NL * C + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
-    print(f"threebody N={N} E={E} T={T}: fwd {t_f:.3f} ms ({bf/t_f/1e6:.0f} GB/s, {T/t_f/1e6:.2f} Gtriplets/s) | "
-          f"bwd {t_b:.3f} ms ({bb/t_b/1e6:.0f} GB/s, {T/t_b/1e6:.2f} Gtriplets/s)", flush=True)
+    bf = E * (4 * NL * C + 48 + 12 + 8 + 4 * C) + N * (4 * C + 8)
+    bb = E * (4 * NL * C + 48 + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+    print(f"threebody N={N} E={E} T={T} TI={os.environ.get('LCAO_TB_TI', 'dflt')}/{os.environ.get('LCAO_TB_TI_BWD', 'dflt')}: "
+          f"fwd {t_f:.3f} ms ({bf/t_f/1e6:.0f} GB/s, {T/t_f/1e6:.2f} Gtriplets/s) | "
+          f"bwd {t_b:.3f} ms ({bb/t_b/1e6:.0f} GB/s, {T/t_b/1e6:.2f} Gtriplets/s) | bwd+forces {t_bf:.3f} ms", flush=True)
     t_i = timeit(lambda: ops.GraphIndex(g["edge_index"], N))
     print(f"graph index build: {t_i:.3f} ms", flush=True)
 

@@ -14,8 +14,8 @@ import math
 
 import torch
 
-F32, I32, I64 = torch.float32, torch.int32, torch.int64
-_SZ = {F32: 4, I32: 4, I64: 8}
+F32, I32, I64, F64 = torch.float32, torch.int32, torch.int64, torch.float64
+_SZ = {F32: 4, I32: 4, I64: 8, F64: 8}
 
 
 def view(ptr, rows, cols=None, dtype=F32, ld=None):
@@ -246,6 +246,75 @@ def _sph(c, NL):
     return torch.stack(y[:NL], 1)  # (T, NL)
 
 
+def _pair_rows(tab, pair, E, P_rows, O, Cp):
+    pr = view(pair, E, dtype=I64)
+    return pr, view(tab, P_rows, O * Cp).reshape(P_rows, O, Cp)
+
+
+def _gram(Bt, NL):
+    cols = [(Bt[:, a].double() * Bt[:, b].double()).sum(-1) for a in range(NL) for b in range(a, NL)]
+    return torch.stack(cols, 1)
+
+
+def lcao_pair_contract_fwd(tab, pair, rb, vmask, lgrp, E, O, C, NL, valence, B, gram, stream):
+    Cp = C * (1 + valence)
+    pr = view(pair, E, dtype=I64)
+    T = view(tab, int(pr.max()) + 1, O * Cp).reshape(-1, O, Cp)
+    c = T[pr]
+    r = view(rb, E, O)
+    G = _groups(lgrp, O, NL)
+    t = r.unsqueeze(-1) * c[..., :C]
+    NG = NL + valence
+    out = view(B, E, NG * C).reshape(E, NG, C)
+    if valence:
+        v = (r * view(vmask, E, O)).unsqueeze(-1) * c[..., C:]
+        t = t + v
+        out[:, NL] = v.sum(1)
+    out[:, :NL] = torch.einsum("eoc,ol->elc", t, G)
+    if gram:
+        view(gram, E, NL * (NL + 1) // 2, dtype=torch.float64).copy_(_gram(out, NL))
+
+
+def lcao_coeff_gram(B, NG, E, C, NL, gram, stream):
+    Bt = view(B, E, NG * C).reshape(E, NG, C)
+    view(gram, E, NL * (NL + 1) // 2, dtype=torch.float64).copy_(_gram(Bt, NL))
+
+
+def lcao_pair_contract_bwd(tab, pair, kptr, kperm, rb, vmask, lgrp, dB, E, P, O, C, NL, valence, d_tab, d_rb, scratch, stream):
+    Cp = C * (1 + valence)
+    NG = NL + valence
+    kp = view(kptr, P + 1, dtype=I32).long()
+    pm = view(kperm, E, dtype=I32).long() if E else torch.empty(0, dtype=I64)
+    key_of = torch.empty(E, dtype=I64)
+    key_of[pm] = torch.repeat_interleave(torch.arange(P), kp[1:] - kp[:-1])
+    r = view(rb, E, O)
+    G = _groups(lgrp, O, NL)
+    d = view(dB, E, NG * C).reshape(E, NG, C)
+    dl = torch.einsum("elc,ol->eoc", d[:, :NL], G)
+    contrib = torch.zeros(E, O, Cp)
+    contrib[..., :C] = r.unsqueeze(-1) * dl
+    if valence:
+        m = view(vmask, E, O)
+        dv = dl + d[:, NL].unsqueeze(1)
+        contrib[..., C:] = (r * m).unsqueeze(-1) * dv
+    out = view(d_tab, P, O * Cp)
+    out.zero_()
+    out.index_add_(0, key_of, contrib.reshape(E, O * Cp))
+    if d_rb:
+        pr = view(pair, E, dtype=I64)
+        c = view(tab, P, O * Cp).reshape(P, O, Cp)[pr]
+        g = (c[..., :C] * dl).sum(-1)
+        if valence:
+            g = g + m * (c[..., C:] * dv).sum(-1)
+        view(d_rb, E, O).copy_(g)
+
+
+def _sph_grad(c, NL):
+    y = [torch.zeros_like(c), torch.full_like(c, 0.4886025119029199), 2 * 0.9461746957575601 * c,
+         0.3731763325901154 * (15 * c * c - 3)]
+    return torch.stack(y[:NL], 1)
+
+
 def _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL):
     Bt = view(B, E, NG * C).reshape(E, NG, C)
     u = view(unit, E, 3)
@@ -255,23 +324,25 @@ def _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge
     src = torch.empty(E, dtype=I64)
     src[ie] = view(in_src, E, dtype=I32).long()
     e, ep = _pairs(ip, ie, op, oe, N)
-    Y = _sph((u[e] * u[ep]).sum(-1), NL)
+    cos = (u[e] * u[ep]).sum(-1)
+    Y = _sph(cos, NL)
     v = torch.einsum("tl,tlc->tc", Y, Bt[ep][:, :NL])
     nrm = v.norm(dim=1, keepdim=True)
     sg = torch.sigmoid(X[src[ep]])
-    return Bt, e, ep, Y, v, nrm, sg, src
+    return Bt, e, ep, Y, v, nrm, sg, src, cos, u
 
 
-def lcao_threebody_fwd(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, tbw, stream):
-    Bt, e, ep, Y, v, nrm, sg, src = _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL)
+def lcao_threebody_fwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, tbw, stream):
+    Bt, e, ep, Y, v, nrm, sg, src, _, _ = _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL)
     y = v / nrm.clamp(min=1e-12)
     view(tbw, E, C).copy_(torch.zeros(E, C).index_add(0, e, y * sg))
 
 
-def lcao_threebody_bwd(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, d_tbw, dB, q,
+def lcao_threebody_bwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, d_tbw, dB, q,
                        du_ks, du_st, stream):
-    assert not du_ks and not du_st
-    Bt, e, ep, Y, v, nrm, sg, src = _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL)
+    """reference-style chain (v, normalise, gate) differentiated directly — independent of the Gram formulation
+    the CUDA kernel uses."""
+    Bt, e, ep, Y, v, nrm, sg, src, cos, u = _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL)
     G = view(d_tbw, E, C)[e]
     inv = 1.0 / nrm.clamp(min=1e-12)
     dy = G * sg
@@ -284,6 +355,11 @@ def lcao_threebody_bwd(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, 
     X = view(xk, N, C, ld=ldxk)
     s_all = torch.sigmoid(X[src])
     view(q, E, C).copy_(gy * s_all * (1 - s_all))
+    if du_ks:
+        dYl = torch.einsum("tlc,tc->tl", Bt[ep][:, :NL], dv)  # dL/dY_l per triplet
+        dc = (dYl * _sph_grad(cos, NL)).sum(1, keepdim=True)
+        view(du_st, E, 3).copy_(torch.zeros(E, 3).index_add(0, e, dc * u[ep]))
+        view(du_ks, E, 3).copy_(torch.zeros(E, 3).index_add(0, ep, dc * u[e]))
 
 
 def _tw_load(B, NG, g, E, C, NL, valence):
@@ -418,6 +494,10 @@ class _FakeLib:
     @staticmethod
     def lcao_linear_bwd_scratch(*a):
         return 0
+
+    @staticmethod
+    def lcao_pair_contract_bwd_scratch(*a):
+        return 64
 
 
 def install(monkeypatch):

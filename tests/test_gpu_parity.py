@@ -120,22 +120,74 @@ def _edge_problem(seed=0, n_mol=6, C=32, NL=3, valence=0, crystal=False):
     return g, B, unit, xk
 
 
-@pytest.mark.parametrize("C,NL,valence,crystal", [(32, 3, 0, False), (128, 3, 0, False), (128, 3, 1, True), (64, 4, 0, True),
-                                                  (12, 2, 1, False), (256, 1, 0, False)])
-def test_threebody_fwd_bwd_vs_restatement(C, NL, valence, crystal, monkeypatch):
+@pytest.mark.parametrize("C,NL,valence,crystal,forces", [(32, 3, 0, False, False), (128, 3, 0, False, False), (128, 3, 0, False, True),
+                                                         (128, 3, 1, True, True), (64, 4, 0, True, False), (12, 2, 1, False, True),
+                                                         (256, 1, 0, False, False), (160, 4, 0, False, True)])
+def test_threebody_fwd_bwd_vs_restatement(C, NL, valence, crystal, forces, monkeypatch):
+    """Gram-matrix kernels vs the reference-style per-triplet chain (tests/cpu_abi.py) incl. dL/d unit."""
     g, B, unit, xk = _edge_problem(C=C, NL=NL, valence=valence, crystal=crystal)
     ei, N = g["edge_index"], g["z"].shape[0]
+    B[::13] = 0.0  # edges beyond the cutoff: zero rows take the eps-clamped branch
 
     def fn(ei, B, unit, xk):
         B = B.clone().requires_grad_(True)
         xk = xk.clone().requires_grad_(True)
+        unit = unit.clone().requires_grad_(forces)
         gi = ops.GraphIndex(ei, N)
         tbw = ops.threebody(B, unit, xk[:, C:], gi, NL)
         (tbw * torch.linspace(-1, 1, C, device=tbw.device)).sum().backward()
-        return tbw.detach(), B.grad, xk.grad
+        return tbw.detach(), B.grad, xk.grad, (unit.grad if forces else tbw.detach())
 
-    (t_g, dB_g, dx_g), (t_c, dB_c, dx_c), _ = _both(fn, monkeypatch, ei, B, unit, xk)
+    (t_g, dB_g, dx_g, du_g), (t_c, dB_c, dx_c, du_c), _ = _both(fn, monkeypatch, ei, B, unit, xk)
+    assert torch.isfinite(dB_g).all() and torch.isfinite(du_g).all()
     assert rel_l2(t_g, t_c) < 2e-6 and rel_l2(dB_g, dB_c) < 1e-5 and rel_l2(dx_g, dx_c) < 1e-5
+    assert rel_l2(du_g, du_c) < 1e-5
+
+
+def test_threebody_chunked_degrees(monkeypatch):
+    """a hub node with more in/out edges than one shared-memory chunk (32) plus directed leftovers"""
+    torch.manual_seed(5)
+    hub, n = 0, 80
+    s = torch.cat([torch.zeros(n - 1, dtype=torch.long), torch.arange(1, n), torch.tensor([3, 4, 5])])
+    t = torch.cat([torch.arange(1, n), torch.zeros(n - 1, dtype=torch.long), torch.tensor([4, 5, 5])])
+    ei = torch.stack([s, t])
+    E, C, NL = ei.shape[1], 128, 3
+    B, unit, xk = torch.randn(E, NL, C), torch.nn.functional.normalize(torch.randn(E, 3), dim=1), torch.randn(n, C)
+
+    def fn(ei, B, unit, xk):
+        B, xk, unit = B.clone().requires_grad_(True), xk.clone().requires_grad_(True), unit.clone().requires_grad_(True)
+        tbw = ops.threebody(B, unit, xk, ops.GraphIndex(ei, n), NL)
+        (tbw * torch.linspace(-1, 1, C, device=tbw.device)).sum().backward()
+        return tbw.detach(), B.grad, xk.grad, unit.grad
+
+    out_g, out_c, _ = _both(fn, monkeypatch, ei, B, unit, xk)
+    for a, b, tol in zip(out_g, out_c, (2e-6, 1e-5, 1e-5, 1e-5)):
+        assert rel_l2(a, b) < tol
+
+
+@pytest.mark.parametrize("C,NL,valence,O,P", [(128, 3, 0, 8, 37 * 37), (128, 3, 1, 16, 400), (32, 4, 1, 5, 9), (256, 2, 0, 8, 30)])
+def test_pair_contract_vs_restatement(C, NL, valence, O, P, monkeypatch):
+    torch.manual_seed(7)
+    E = 20000
+    Cp = C * (1 + valence)
+    tab = torch.randn(P, O, Cp)
+    pair = torch.randint(0, P, (E,))
+    pair[: E // 2] = pair[0]  # one dominant key (many chunks) plus a long tail, some keys absent
+    rb = torch.randn(E, O)
+    vmask = (torch.rand(E, O) > 0.5).float() if valence else None
+    lgrp = torch.randint(0, NL, (O,), dtype=torch.int32)
+    lgrp[0] = NL - 1
+
+    def fn(tab, pair, rb, vmask, lgrp):
+        tab, rb = tab.clone().requires_grad_(True), rb.clone().requires_grad_(True)
+        kptr, kperm = ops.bucket_sort(pair, P, stable=False)
+        B, gram = ops.pair_contract(tab, pair, kptr, kperm, rb, vmask, lgrp, NL, C)
+        (B * torch.linspace(-1, 2, C, device=B.device)).sum().backward()
+        return B.detach(), gram, tab.grad, rb.grad
+
+    out_g, out_c, _ = _both(fn, monkeypatch, tab, pair, rb, vmask, lgrp)
+    for a, b, tol in zip(out_g, out_c, (2e-6, 1e-6, 2e-5, 2e-5)):
+        assert torch.isfinite(a).all() and rel_l2(a, b) < tol
 
 
 @pytest.mark.parametrize("C,NL,valence", [(128, 3, 0), (128, 3, 1), (32, 4, 1), (256, 2, 0)])
@@ -223,6 +275,16 @@ def test_model_matches_reference_golden(name):
         sd = model.state_dict()
         for k, v in gold["bn_after_f64"].items():
             assert torch.allclose(sd[k].cpu().double(), v, rtol=1e-4, atol=1e-5), k
+
+
+def test_autograd_forces_match_reference_golden():
+    from tests.test_host_logic_cpu import _check_autograd_forces
+    gold = load_golden("crystal_autograd_forces")
+    model = LCAONet(**gold["kwargs"])
+    model.load_state_dict(gold["state_dict"], strict=True)
+    model = model.to(DEV).train(gold["training"])
+    out = model(GraphBatch(gold["graph"]).to(DEV))
+    _check_autograd_forces(gold, model, out, 1e-5, 5e-5)
 
 
 def test_node_features_match_oracle_layer_by_layer():

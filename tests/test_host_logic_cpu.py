@@ -58,6 +58,27 @@ def test_forward_backward_match_reference(name, monkeypatch):
         assert int(sd["emb_layer.coeff_embed.bn.num_batches_tracked"]) == 1
 
 
+def _check_autograd_forces(gold, model, out, tol_f, tol_g):
+    """regress_forces with direct_forces=False: forces = -dE/dpos through the geometry, radial basis,
+    three-body and two-body kernels (reference lcaonet.py:310-317); parameter gradients of the energy term."""
+    energy, forces = out
+    assert rel_l2(energy, gold["energy_f64"]) < 1e-5
+    assert forces.shape == gold["forces_f64"].shape and rel_l2(forces, gold["forces_f64"]) < tol_f
+    (energy**2).mean().backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        ref = gold["grads_energy_f64"][n]
+        if ref is None or float(ref.norm()) == 0.0:
+            continue
+        worst = max(worst, rel_l2(p.grad, ref))
+    assert worst < tol_g, worst
+
+
+def test_autograd_forces_match_reference(monkeypatch):
+    gold, model, g, out = _run("crystal_autograd_forces", monkeypatch)
+    _check_autograd_forces(gold, model, out, 2e-5, 2e-4)
+
+
 def test_same_seed_gives_reference_initialisation():
     gold = load_golden("qm9_valence_ext_2perorb")
     torch.manual_seed(0)
