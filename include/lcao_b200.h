@@ -133,20 +133,23 @@ int64_t lcao_pair_contract_bwd_scratch(int64_t E, int64_t P, int32_t O, int32_t 
 int lcao_coeff_gram(const float* B, int32_t NG, int64_t E, int32_t C, int32_t NL, double* gram, void* stream);
 
 /* ---- three-body message passing (lcaonet.py:173-189, shbf.py:75-87) --------------------------- */
-/* tbw[e,:] = sum_{e' in in(s_e), e' != e} normalize( sum_l Y_l(unit[e].unit[e']) B[e',l,:] ) * sigmoid(xk[src[e'],:])
+/* gate[n,:] = sigmoid(xk[n,:]) per node (lcaonet.py:186-188), computed once per layer */
+int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t M, int32_t C, void* stream);
+/* tbw[e,:] = sum_{e' in in(s_e), e' != e} normalize( sum_l Y_l(unit[e].unit[e']) B[e',l,:] ) * gate[src[e'],:]
  * B has NG groups per edge (row stride NG*C); gram = its per-edge Gram matrices (|v|^2 = Y^T G Y);
- * xk (N,C) with row stride ldxk. */
-int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
-                       int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+ * gate (N,C) with row stride ldg. */
+int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
+                       int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                        const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                        int32_t NL, float* tbw, void* stream);
 /* backward: dB (E,NG,C) groups 0..NL-1 are OVERWRITTEN with the three-body contribution, including the
  * part that flows through the norms (gram is treated as a function of B); group NL is zeroed when
- * NG > NL.  q (E,C) = per in-edge gradient of the sigmoid gate pre-activation
- * (d_xk[k] = sum_{e' in out(k)} q[e']).  d_unit_ks / d_unit_st (E,3; both or neither): gradient w.r.t.
- * unit[e] from its role as in-edge (k->s) and as out-edge (s->t); d_unit = their sum (autograd forces). */
-int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
-                       int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+ * NG > NL.  q (E,C) = per in-edge gradient of the gate PRE-activation xk (the sigmoid derivative is
+ * applied here): d_xk[k] = sum_{e' in out(k)} q[e'].  d_unit_ks / d_unit_st (E,3; both or neither):
+ * gradient w.r.t. unit[e] from its role as in-edge (k->s) and as out-edge (s->t); d_unit = their sum
+ * (autograd forces). */
+int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
+                       int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                        const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                        int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks, float* d_unit_st,
                        void* stream);

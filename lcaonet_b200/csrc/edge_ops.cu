@@ -322,6 +322,16 @@ __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float
   st4(dH + i * ldd + c, g);
 }
 
+__global__ void k_sigmoid_rows(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int64_t M,
+                               int C4) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= M * C4) return;
+  const int64_t i = t / C4;
+  const int c = (int)(t - i * C4) * 4;
+  const float4 v = ldg4(x + i * ldx + c);
+  st4(out + i * ldo + c, make_float4(sigmoidf_acc(v.x), sigmoidf_acc(v.y), sigmoidf_acc(v.z), sigmoidf_acc(v.w)));
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -468,6 +478,16 @@ extern "C" int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_
   LCAO_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && ldd % 4 == 0 && (act == LCAO_ACT_NONE || ldh % 4 == 0),
                "lcao_act_bwd: need C and strides multiples of 4");
   k_act_bwd<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t M, int32_t C, void* stream) {
+  if (M == 0 || C == 0) return LCAO_OK;
+  LCAO_REQUIRE(x && out, "lcao_sigmoid_rows: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out),
+               "lcao_sigmoid_rows: need C and strides multiples of 4, 16-byte aligned buffers");
+  k_sigmoid_rows<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, M, C / 4);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

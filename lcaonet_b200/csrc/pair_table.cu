@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kChunk = 512;  // sorted entries per stage-1 CTA of the keyed reduction
+constexpr int kChunk = 256;  // sorted entries per stage-1 CTA of the keyed reduction
 
 __device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4fma(float a, float4 x, float4 acc) {
@@ -34,7 +34,51 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// one warp per edge; lane owns float4 column lane (+32 for C > 128)
+// Sum up to 8 per-lane FP64 partials over the 32 lanes with 9 shuffles (see bfly8 in threebody.cu);
+// lane L ends up with the total of element 4*bit4(L) + 2*bit3(L) + bit2(L).
+__device__ __forceinline__ double bfly8d(const double (&p)[8], int lane) {
+  double q4[4], q2[2];
+  bool up = (lane & 16) != 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double recv = __shfl_xor_sync(0xffffffffu, up ? p[k] : p[k + 4], 16);
+    q4[k] = (up ? p[k + 4] : p[k]) + recv;
+  }
+  up = (lane & 8) != 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double recv = __shfl_xor_sync(0xffffffffu, up ? q4[k] : q4[k + 2], 8);
+    q2[k] = (up ? q4[k + 2] : q4[k]) + recv;
+  }
+  up = (lane & 4) != 0;
+  const double recv = __shfl_xor_sync(0xffffffffu, up ? q2[0] : q2[1], 4);
+  double r = (up ? q2[1] : q2[0]) + recv;
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+__device__ __forceinline__ int bfly8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// Writes the NP <= 10 Gram entries of one edge from per-lane FP64 partials.
+template <int NP>
+__device__ __forceinline__ void store_gram(const double (&g)[NP], int lane, double* __restrict__ out) {
+  double p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = i < NP ? g[i] : 0.0;
+  const double r = bfly8d(p, lane);
+  const int idx = bfly8_index(lane);
+  if ((lane & 3) == 0 && idx < NP) out[idx] = r;
+  if (NP > 8) {  // NL = 4: entries 8, 9
+    double p2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p2[i] = (8 + i) < NP ? g[(8 + i) < NP ? 8 + i : 0] : 0.0;
+    const double r2 = bfly8d(p2, lane);
+    if ((lane & 3) == 0 && 8 + idx < NP) out[8 + idx] = r2;
+  }
+}
+
+// one warp per edge; lane owns float4 column lane (+32 for C > 128).  The group selection is folded into
+// the scale factor (rb[e,o] for the orbital's own l, 0 otherwise): NL FMAs per orbital, no branches.
 template <int NL, bool VAL>
 __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     const float* __restrict__ tab, const int64_t* __restrict__ pair, const float* __restrict__ rb,
@@ -56,22 +100,24 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     float4 acc[NL + 1];
 #pragma unroll
     for (int l = 0; l <= NL; ++l) acc[l] = f4z();
-#pragma unroll 4
+#pragma unroll 8
     for (int o = 0; o < O; ++o) {
       const float r = __ldg(rb + e * O + o);
-      float4 t = ldg4(row + (int64_t)o * Cp + c);
-      t = make_float4(r * t.x, r * t.y, r * t.z, r * t.w);
+      const int l = s_l[o];
+      const float4 t = ldg4(row + (int64_t)o * Cp + c);
       if (VAL) {
         const float rm = r * __ldg(vmask + e * O + o);
-        float4 v = ldg4(row + (int64_t)o * Cp + C + c);
-        v = make_float4(rm * v.x, rm * v.y, rm * v.z, rm * v.w);
-        acc[NL] = f4add(acc[NL], v);
-        t = f4add(t, v);
-      }
-      const int l = s_l[o];
+        const float4 v = ldg4(row + (int64_t)o * Cp + C + c);
+        acc[NL] = f4fma(rm, v, acc[NL]);
 #pragma unroll
-      for (int k = 0; k < NL; ++k)
-        if (l == k) acc[k] = f4add(acc[k], t);
+        for (int k = 0; k < NL; ++k) {
+          acc[k] = f4fma(l == k ? r : 0.f, t, acc[k]);
+          acc[k] = f4fma(l == k ? rm : 0.f, v, acc[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) acc[k] = f4fma(l == k ? r : 0.f, t, acc[k]);
+      }
     }
 #pragma unroll
     for (int l = 0; l < NG; ++l) st4(B + (e * NG + l) * (int64_t)C + c, acc[l]);
@@ -83,13 +129,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
         for (int b = a; b < NL; ++b) g[i++] += dot4d(acc[a], acc[b]);
     }
   }
-  if (gram) {
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const double s = warp_sum_d(g[i]);
-      if (lane == 0) gram[e * NP + i] = s;
-    }
-  }
+  if (gram) store_gram<NP>(g, lane, gram + e * NP);
 }
 
 // Gram matrix of an existing B (E,NG,C): upper triangle over the first NL groups, FP64
@@ -113,11 +153,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_gram(const float* __restrict__ 
 #pragma unroll
       for (int bb = a; bb < NL; ++bb) g[i++] += dot4d(b[a], b[bb]);
   }
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const double s = warp_sum_d(g[i]);
-    if (lane == 0) gram[e * NP + i] = s;
-  }
+  store_gram<NP>(g, lane, gram + e * NP);
 }
 
 // d_rb[e,o] = tab[p,o,:C].dB[e,l(o),:] + m[e,o] tab[p,o,C:].(dB[e,l(o),:] + dB[e,NL,:])   (autograd forces)
@@ -173,12 +209,18 @@ __global__ void __launch_bounds__(1024) k_chunk_ptr(const int32_t* __restrict__ 
   if (threadIdx.x == 1023) cptr[P] = part[1023];
 }
 
-// ---- stage 1: CTA = one chunk of one key; thread = one (o, float4 column); partial[chunk][o][Cp]
+// ---- stage 1: CTA = one chunk of one key; thread = one (o, float4 column); partial[chunk][o][Cp].
+// The chunk's edge ids and radial values are staged in shared memory first, so the main loop's dB loads
+// are independent of each other and 8 of them are in flight per thread.
 template <bool VAL>
 __global__ void __launch_bounds__(256) k_pair_reduce_partial(
     const int32_t* __restrict__ kptr, const int32_t* __restrict__ kperm, const int32_t* __restrict__ cptr, int P,
     const float* __restrict__ rb, const float* __restrict__ vmask, const int32_t* __restrict__ lgrp,
     const float* __restrict__ dB, int O, int C, int NL, float* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_e = reinterpret_cast<int32_t*>(smem_raw);            // kChunk
+  float* s_r = reinterpret_cast<float*>(s_e + kChunk);            // O x kChunk   rb[e,o]
+  float* s_m = s_r + (size_t)O * kChunk;                          // VAL: O x kChunk   rb[e,o] * vmask[e,o]
   const int chunk = blockIdx.x;
   if (chunk >= cptr[P]) return;
   int lo = 0, hi = P;  // last key with cptr[key] <= chunk (keys without entries have empty chunk ranges)
@@ -187,29 +229,49 @@ __global__ void __launch_bounds__(256) k_pair_reduce_partial(
     if (cptr[mid] <= chunk) lo = mid; else hi = mid;
   }
   const int key = lo;
-  const int C4 = C >> 2;
-  const int w = blockIdx.y * 256 + threadIdx.x;
-  if (w >= O * C4) return;
-  const int o = w / C4, c = (w - o * C4) * 4;
-  const int l = lgrp[o];
-  const int NG = NL + (VAL ? 1 : 0), Cp = VAL ? 2 * C : C;
   const int32_t j0 = kptr[key] + (chunk - cptr[key]) * kChunk;
-  const int32_t j1 = min(j0 + kChunk, kptr[key + 1]);
-  float4 accA = f4z(), accV = f4z();
-#pragma unroll 4
-  for (int32_t j = j0; j < j1; ++j) {
-    const int64_t e = kperm[j];
-    const float r = __ldg(rb + e * O + o);
-    const float4 g = ldg4(dB + (e * NG + l) * (int64_t)C + c);
-    accA = f4fma(r, g, accA);
-    if (VAL) {
-      const float rm = r * __ldg(vmask + e * O + o);
-      accV = f4fma(rm, f4add(g, ldg4(dB + (e * NG + NL) * (int64_t)C + c)), accV);
+  const int n = min(kChunk, kptr[key + 1] - j0);
+  for (int t = threadIdx.x; t < n; t += 256) {
+    const int64_t e = kperm[j0 + t];
+    s_e[t] = (int32_t)e;
+    for (int o = 0; o < O; ++o) {
+      const float r = __ldg(rb + e * O + o);
+      s_r[o * kChunk + t] = r;
+      if (VAL) s_m[o * kChunk + t] = r * __ldg(vmask + e * O + o);
     }
   }
-  float* out = partial + ((int64_t)chunk * O + o) * Cp + c;
-  st4(out, accA);
-  if (VAL) st4(out + C, accV);
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int NG = NL + (VAL ? 1 : 0), Cp = VAL ? 2 * C : C;
+  for (int w = threadIdx.x; w < O * C4; w += 256) {
+    const int o = w / C4, c = (w - o * C4) * 4;
+    const int l = lgrp[o];
+    const float* sr = s_r + o * kChunk;
+    const float* sm = s_m + o * kChunk;
+    float4 accA = f4z(), accV = f4z();
+    int t = 0;
+    for (; t + 8 <= n; t += 8) {
+      float4 g[8], gv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        g[u] = ldg4(dB + ((int64_t)s_e[t + u] * NG + l) * C + c);
+        if (VAL) gv[u] = ldg4(dB + ((int64_t)s_e[t + u] * NG + NL) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        accA = f4fma(sr[t + u], g[u], accA);
+        if (VAL) accV = f4fma(sm[t + u], f4add(g[u], gv[u]), accV);
+      }
+    }
+    for (; t < n; ++t) {
+      const float4 g = ldg4(dB + ((int64_t)s_e[t] * NG + l) * C + c);
+      accA = f4fma(sr[t], g, accA);
+      if (VAL) accV = f4fma(sm[t], f4add(g, ldg4(dB + ((int64_t)s_e[t] * NG + NL) * C + c)), accV);
+    }
+    float* out = partial + ((int64_t)chunk * O + o) * Cp + c;
+    st4(out, accA);
+    if (VAL) st4(out + C, accV);
+  }
 }
 
 // ---- stage 2: d_tab[key][o][:] = sum of the key's partials in chunk order (zeros for absent keys)
@@ -289,9 +351,13 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
   k_chunk_ptr<<<1, 1024, 0, st>>>(kptr, (int)P, cptr);
   LCAO_LAUNCH_CHECK();
   if (E > 0) {
-    dim3 grid((unsigned)chunks, (unsigned)ceil_div64((int64_t)O * (C / 4), 256));
-    if (valence) k_pair_reduce_partial<true><<<grid, 256, 0, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
-    else k_pair_reduce_partial<false><<<grid, 256, 0, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
+    const size_t smem = sizeof(int32_t) * kChunk + sizeof(float) * (size_t)O * kChunk * (valence ? 2 : 1);
+    if (smem > 48 * 1024) {
+      LCAO_CUDA(cudaFuncSetAttribute(valence ? k_pair_reduce_partial<true> : k_pair_reduce_partial<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (valence) k_pair_reduce_partial<true><<<(unsigned)chunks, 256, smem, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
+    else k_pair_reduce_partial<false><<<(unsigned)chunks, 256, smem, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
     LCAO_LAUNCH_CHECK();
   }
   const int W4 = O * Cp / 4;

@@ -14,20 +14,28 @@
 // (the reference's (T,O,C) gather, cos(theta), Y_l(T,O)) exists; cos(theta) = unit[e].unit[e'] and Y_l
 // are recomputed per (e,e') pair by one thread and broadcast through shared memory.
 //
-// Thread mapping: lane <-> float4 channel column (C = 128 -> 32 lanes), warp <-> a set of out-edges
-// (forward: up to 8 register accumulators) or in-edges (backward: 2 at a time).  Sums over triplets
-// accumulate in registers and are written once: no atomics, deterministic.
+// Thread mapping: lane <-> float4 channel column (C = 128 -> 32 lanes), warp <-> 8 out-edges of a node
+// (forward: 8 register accumulators) or 2 in-edges (backward).  Warps are independent: B / gate / d_tbw
+// rows are read straight from global memory (L1/L2 serve the re-reads by the sibling warps of the same
+// node), the per-pair coefficients are computed by the lanes of the warp itself (one pair per lane)
+// and broadcast through a 512-byte per-warp scratch.  There is no block-level staging and no
+// __syncthreads on the energy path, so many nodes are in flight per SM and the latency of one node's
+// index -> row chain is hidden by the others.  Sums over triplets accumulate in registers and are
+// written once: no atomics, deterministic.
+//
+// `gate` is sigmoid(xk) per NODE (N x C, computed once per layer by lcao_sigmoid_rows).
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;  // 4 warps
-constexpr int kWarpsTb = kThreads / 32;
-constexpr int kTO = 32;        // out-edges per pass (forward: 4 warps x 8 accumulators)
+constexpr int kFwdWarps = 2;   // forward CTA: 2 warps x 8 out-edges per pass
+constexpr int kBwdWarps = 4;   // backward CTA: 4 warps x 2 in-edges per pass
 constexpr int kR = 8;          // forward: out-edge accumulators per warp
 constexpr int kRI = 2;         // backward: in-edges per warp at a time
+constexpr int kIB = 4;         // forward: in-edges per coefficient batch (kR * kIB = 32 pairs = one per lane)
+constexpr int kJS = 64;        // backward (forces): out-edges whose d_unit partials live in shared memory
 constexpr float kEps = 1e-12f; // F.normalize eps (lcaonet.py:184)
 
 template <int NL>
@@ -116,99 +124,85 @@ __device__ __forceinline__ int bfly8_index(int lane) { return ((lane >> 4) & 1) 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// Out-of-range slots (out-edge r >= nr, in-edge beyond the node's list) are handled by CLAMPING the
+// index to a valid row and zeroing the pair's coefficient, so the row loads and the FMA block are
+// branch- and predicate-free.
 template <int NL, int V4>
-__global__ void __launch_bounds__(kThreads) k_threebody_fwd(
+__global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
-    const float* __restrict__ xk, int64_t ldxk, const int32_t* __restrict__ in_ptr,
+    const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int C, int TI, float* __restrict__ tbw) {
+    const int32_t* __restrict__ out_edge, int C, float* __restrict__ tbw) {
   constexpr int NP = NL * (NL + 1) / 2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* g_in = reinterpret_cast<double*>(smem_raw);                 // TI x NP
-  float* GB = reinterpret_cast<float*>(g_in + (size_t)TI * NP);      // TI x NL x C
-  float* A = GB + (size_t)TI * NL * C;                               // kTO x TI x 4
-  float* u_in = A + (size_t)kTO * TI * 4;                            // TI x 3
-  float* u_out = u_in + TI * 3;                                      // kTO x 3
-  int* eid_in = reinterpret_cast<int*>(u_out + kTO * 3);             // TI
-  int* eid_out = eid_in + TI;                                        // kTO
-
+  __shared__ __align__(16) float s_a[kFwdWarps][32 * 4];  // per-warp coefficient scratch: pair (t, r) at slot t*8 + r
   const int s = blockIdx.x;
-  const int ib = in_ptr[s], ie = in_ptr[s + 1], ob = out_ptr[s], oe = out_ptr[s + 1];
-  if (oe == ob) return;
+  const int ib = in_ptr[s], dI = in_ptr[s + 1] - ib, ob = out_ptr[s], dO = out_ptr[s + 1] - ob;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_mine = lane & 7, t_mine = lane >> 3;
+  float* sa = s_a[warp];
+  bool okc[V4];
+#pragma unroll
+  for (int v = 0; v < V4; ++v) okc[v] = (lane + 32 * v) * 4 < C;
 
-  for (int p0 = ob; p0 < oe; p0 += kTO) {
-    const int nO = min(kTO, oe - p0);
-    __syncthreads();  // previous pass has finished reading u_out / eid_out
-    if (threadIdx.x < nO) {
-      const int e = out_edge[p0 + threadIdx.x];
-      eid_out[threadIdx.x] = e;
-      u_out[3 * threadIdx.x] = unit[3 * (int64_t)e];
-      u_out[3 * threadIdx.x + 1] = unit[3 * (int64_t)e + 1];
-      u_out[3 * threadIdx.x + 2] = unit[3 * (int64_t)e + 2];
-    }
-    __syncthreads();
-    const int nr = (nO > warp) ? (nO - warp + kWarpsTb - 1) / kWarpsTb : 0;  // this warp's out-edges: j = r*4 + warp
+  for (int jb = warp * kR; jb < dO; jb += kFwdWarps * kR) {
+    const int nr = min(kR, dO - jb);
+    // lane (r, t) keeps out-edge r of this block: id and direction
+    const int e_mine = out_edge[ob + jb + min(r_mine, nr - 1)];
+    const float ux = unit[3 * (int64_t)e_mine], uy = unit[3 * (int64_t)e_mine + 1], uz = unit[3 * (int64_t)e_mine + 2];
     float4 acc[kR][V4];
 #pragma unroll
     for (int r = 0; r < kR; ++r)
 #pragma unroll
       for (int v = 0; v < V4; ++v) acc[r][v] = zero4();
 
-    for (int c0 = ib; c0 < ie; c0 += TI) {
-      const int nI = min(TI, ie - c0);
-      __syncthreads();  // previous chunk's consumers are done with GB / A
-      // ---- stage the in-edges of this chunk: gated B rows, directions, ids, Gram matrices
-      for (int i = warp; i < nI; i += kWarpsTb) {
-        const int ep = in_edge[c0 + i];
-        const int k = in_src[c0 + i];
+    for (int ic = 0; ic < dI; ic += 32) {  // the node's in-edge ids, 32 at a time, one per lane
+      const int nI = min(32, dI - ic);
+      const int my_ep = in_edge[ib + ic + min(lane, nI - 1)];
+      const int my_k = in_src[ib + ic + min(lane, nI - 1)];
+      for (int i0 = 0; i0 < nI; i0 += kIB) {
+        // ---- coefficients of the 8 x 4 pairs of this batch, one per lane
+        const int ep_c = __shfl_sync(0xffffffffu, my_ep, min(i0 + t_mine, nI - 1));
+        float4 a = zero4();
+        {
+          const float c = fmaf(ux, unit[3 * (int64_t)ep_c], fmaf(uy, unit[3 * (int64_t)ep_c + 1], uz * unit[3 * (int64_t)ep_c + 2]));
+          float Y[4];
+          sph_harm<NL>(c, Y);
+          double g[NP];
 #pragma unroll
-        for (int v = 0; v < V4; ++v) {
-          const int c = (lane + 32 * v) * 4;
-          if (c < C) {
-            const float4 gate = sigmoid4(ldg4(xk + (int64_t)k * ldxk + c));
-#pragma unroll
-            for (int l = 0; l < NL; ++l)
-              st4(GB + ((size_t)i * NL + l) * C + c, mul4(gate, ldg4(B + ((int64_t)ep * NG + l) * C + c)));
-          }
+          for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)ep_c * NP + p];
+          float w = 1.0f / fmaxf(sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f)), kEps);
+          if (r_mine >= nr || i0 + t_mine >= nI || ep_c == e_mine) w = 0.f;
+          a = make_float4(w * Y[0], w * Y[1], w * Y[2], w * Y[3]);
         }
-        if (lane < 3) u_in[i * 3 + lane] = unit[3 * (int64_t)ep + lane];
-        if (lane == 3) eid_in[i] = ep;
-        if (lane >= 4 && lane < 4 + NP) g_in[i * NP + lane - 4] = gram[(int64_t)ep * NP + lane - 4];
-      }
-      __syncthreads();
-      // ---- per (out-edge j, in-edge i): a_l = Y_l(c) / max(|v|, eps), 0 for the excluded pair e' == e
-      for (int t = threadIdx.x; t < nO * nI; t += kThreads) {
-        const int j = t / nI, i = t - j * nI;
-        const float c = fmaf(u_out[3 * j], u_in[3 * i], fmaf(u_out[3 * j + 1], u_in[3 * i + 1], u_out[3 * j + 2] * u_in[3 * i + 2]));
-        float Y[4];
-        sph_harm<NL>(c, Y);
-        const float n2 = fmaxf((float)quad_form<NL>(g_in + i * NP, Y), 0.f);
-        const float w = (eid_out[j] != eid_in[i]) ? 1.0f / fmaxf(sqrtf(n2), kEps) : 0.f;
-        st4(A + ((size_t)j * TI + i) * 4, make_float4(w * Y[0], w * Y[1], w * Y[2], w * Y[3]));
-      }
-      __syncthreads();
-      // ---- tbw[j,:] += sum_i sum_l a[j,i,l] GB[i,l,:]
-      if (nr > 0) {
-        for (int i = 0; i < nI; ++i) {
-          float4 gb[NL][V4];
+        __syncwarp();  // previous batch's readers are done
+        st4(sa + lane * 4, a);
+        __syncwarp();
+        // ---- rows of the batch: issue every load first, then the FMAs
+        float4 gb[kIB][NL][V4];
+#pragma unroll
+        for (int t = 0; t < kIB; ++t) {
+          const int src = min(i0 + t, nI - 1);
+          const int ep = __shfl_sync(0xffffffffu, my_ep, src);
+          const int k = __shfl_sync(0xffffffffu, my_k, src);
 #pragma unroll
           for (int v = 0; v < V4; ++v) {
             const int c = (lane + 32 * v) * 4;
+            const float4 gt = okc[v] ? ldg4(gate + (int64_t)k * ldg + c) : zero4();
 #pragma unroll
-            for (int l = 0; l < NL; ++l) gb[l][v] = (c < C) ? lds4(GB + ((size_t)i * NL + l) * C + c) : zero4();
+            for (int l = 0; l < NL; ++l) gb[t][l][v] = okc[v] ? mul4(gt, ldg4(B + ((int64_t)ep * NG + l) * C + c)) : zero4();
           }
+        }
+#pragma unroll
+        for (int t = 0; t < kIB; ++t) {
 #pragma unroll
           for (int r = 0; r < kR; ++r) {
-            if (r < nr) {
-              const float4 a = lds4(A + ((size_t)(r * kWarpsTb + warp) * TI + i) * 4);
+            const float4 ar = lds4(sa + (t * 8 + r) * 4);
 #pragma unroll
-              for (int v = 0; v < V4; ++v) {
-                acc[r][v] = fma4(a.x, gb[0][v], acc[r][v]);
-                if (NL > 1) acc[r][v] = fma4(a.y, gb[1][v], acc[r][v]);
-                if (NL > 2) acc[r][v] = fma4(a.z, gb[2][v], acc[r][v]);
-                if (NL > 3) acc[r][v] = fma4(a.w, gb[3][v], acc[r][v]);
-              }
+            for (int v = 0; v < V4; ++v) {
+              acc[r][v] = fma4(ar.x, gb[t][0][v], acc[r][v]);
+              if (NL > 1) acc[r][v] = fma4(ar.y, gb[t][1][v], acc[r][v]);
+              if (NL > 2) acc[r][v] = fma4(ar.z, gb[t][2][v], acc[r][v]);
+              if (NL > 3) acc[r][v] = fma4(ar.w, gb[t][3][v], acc[r][v]);
             }
           }
         }
@@ -216,12 +210,12 @@ __global__ void __launch_bounds__(kThreads) k_threebody_fwd(
     }
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
+      const int e = __shfl_sync(0xffffffffu, e_mine, r);
       if (r < nr) {
-        const int e = eid_out[r * kWarpsTb + warp];
 #pragma unroll
         for (int v = 0; v < V4; ++v) {
           const int c = (lane + 32 * v) * 4;
-          if (c < C) st4(tbw + (int64_t)e * C + c, acc[r][v]);
+          if (okc[v]) st4(tbw + (int64_t)e * C + c, acc[r][v]);
         }
       }
     }
@@ -235,38 +229,32 @@ __global__ void __launch_bounds__(kThreads) k_threebody_fwd(
 //   H_i[l,l'] -= dot a_l a_l'            (norm path; skipped when |v| <= eps)  ->  dB[i,l] += sum_l' H[l,l'] B[i,l']
 //   dB[i,l,:] += gate * dGB[i,l,:] ;  q[i,:] = gate (1-gate) sum_l B[i,l,:] dGB[i,l,:]   (d xk[k] = sum_{e' in out(k)} q[e'])
 //   FORCES: dc = Gt[j,:] . sum_l (w Y'_l) GB[i,l,:] - w^2 dot sum_l Y'_l (G Y)_l ;  d unit[e_j] += dc unit[e_i] and v.v.
+// Same clamping convention as the forward: dead slots read a valid row and carry zero coefficients.
 // ---------------------------------------------------------------------------------------------
 template <int NL, int V4, bool FORCES>
-__global__ void __launch_bounds__(kThreads) k_threebody_bwd(
+__global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
-    const float* __restrict__ xk, int64_t ldxk, const int32_t* __restrict__ in_ptr,
+    const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int C, int TI, const float* __restrict__ d_tbw, float* __restrict__ dB,
+    const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, float* __restrict__ dB,
     float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* g_in = reinterpret_cast<double*>(smem_raw);              // TI x NP
-  float* Gt = reinterpret_cast<float*>(g_in + (size_t)TI * NP);   // kTO x C
-  float* A = Gt + (size_t)kTO * C;                                // kTO x TI x 4   a_l = w Y_l
-  float* Fl = A + (size_t)kTO * TI * 4;                           // kTO x TI       1 if the norm path is live
-  float* A2 = Fl + (size_t)kTO * TI;                              // FORCES: kTO x TI x 4   w Y'_l
-  float* Cc = A2 + (FORCES ? (size_t)kTO * TI * 4 : 0);           // FORCES: kTO x TI       cos, then dL/dcos
-  float* Ww = Cc + (FORCES ? (size_t)kTO * TI : 0);               // FORCES: kTO x TI       w
-  float* u_in = Ww + (FORCES ? (size_t)kTO * TI : 0);             // TI x 3
-  float* u_out = u_in + TI * 3;                                   // kTO x 3
-  int* eid_in = reinterpret_cast<int*>(u_out + kTO * 3);          // TI
-  int* eid_out = eid_in + TI;                                     // kTO
+  // per-warp scratch, pair (rr, jj) at slot rr*8 + jj: a_l = w Y_l | norm-path flag | (forces) w Y'_l
+  __shared__ __align__(16) float s_a[kBwdWarps][16 * 4];
+  __shared__ float s_f[kBwdWarps][16];
+  __shared__ __align__(16) float s_a2[FORCES ? kBwdWarps : 1][16 * 4];
+  __shared__ float s_st[FORCES ? kBwdWarps : 1][FORCES ? kJS * 3 : 1];  // per-warp partials of d unit[e_j] (s->t role)
 
   const int s = blockIdx.x;
-  const int ib = in_ptr[s], ie = in_ptr[s + 1], ob = out_ptr[s], oe = out_ptr[s + 1];
+  const int ib = in_ptr[s], dI = in_ptr[s + 1] - ib, ob = out_ptr[s], dO = out_ptr[s + 1] - ob;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (ie == ib) {  // no in-edges: only the s->t role gradients of the out-edges exist, and they are zero
+  if (dI == 0) {  // no in-edges: only the s->t role gradients of the out-edges exist, and they are zero
     if (FORCES)
-      for (int t = threadIdx.x; t < (oe - ob) * 3; t += kThreads) du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = 0.f;
+      for (int t = threadIdx.x; t < dO * 3; t += kBwdWarps * 32) du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = 0.f;
     return;
   }
-  if (oe == ob) {  // in-edges that feed no triplet: zero gradients
-    for (int i = warp; i < ie - ib; i += kWarpsTb) {
+  if (dO == 0) {  // in-edges that feed no triplet: zero gradients
+    for (int i = warp; i < dI; i += kBwdWarps) {
       const int ep = in_edge[ib + i];
       for (int c = lane * 4; c < C; c += 128) {
         for (int l = 0; l < NG; ++l) st4(dB + ((int64_t)ep * NG + l) * C + c, zero4());
@@ -276,246 +264,228 @@ __global__ void __launch_bounds__(kThreads) k_threebody_bwd(
     }
     return;
   }
-
-  for (int p0 = ob; p0 < oe; p0 += kTO) {
-    const int nO = min(kTO, oe - p0);
-    const bool first_out = (p0 == ob);
+  if constexpr (FORCES) {
+    for (int t = lane; t < kJS * 3; t += 32) s_st[warp][t] = 0.f;
+    for (int t = threadIdx.x; t < dO * 3; t += kBwdWarps * 32)
+      if (t >= kJS * 3) du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = 0.f;  // rare overflow rows: global atomics below
     __syncthreads();
-    for (int j = warp; j < nO; j += kWarpsTb) {
-      const int e = out_edge[p0 + j];
-      for (int c = lane * 4; c < C; c += 128) st4(Gt + (size_t)j * C + c, ldg4(d_tbw + (int64_t)e * C + c));
-      if (lane < 3) u_out[j * 3 + lane] = unit[3 * (int64_t)e + lane];
-      if (lane == 3) eid_out[j] = e;
+  }
+  float* sa = s_a[warp];
+  float* sf = s_f[warp];
+  const int jj_mine = lane & 7, rr_mine = (lane >> 3) & 1;  // coefficient duty: pair (out j0+jj, in i0+rr); lanes >= 16 mirror
+  const int jsub = bfly8_index(lane);
+  bool okc[V4];
+#pragma unroll
+  for (int v = 0; v < V4; ++v) okc[v] = (lane + 32 * v) * 4 < C;
+
+  for (int i0 = warp * kRI; i0 < dI; i0 += kBwdWarps * kRI) {
+    float4 gb[kRI][NL][V4], dacc[kRI][NL][V4], gt[kRI][V4];
+    float h[kRI][NP];
+    int ep[kRI];
+#pragma unroll
+    for (int rr = 0; rr < kRI; ++rr) {
+      const int pos = ib + min(i0 + rr, dI - 1);
+      ep[rr] = in_edge[pos];
+      const int k = in_src[pos];
+#pragma unroll
+      for (int v = 0; v < V4; ++v) {
+        const int c = (lane + 32 * v) * 4;
+        gt[rr][v] = okc[v] ? ldg4(gate + (int64_t)k * ldg + c) : zero4();
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          gb[rr][l][v] = okc[v] ? mul4(gt[rr][v], ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c)) : zero4();
+          dacc[rr][l][v] = zero4();
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) h[rr][p] = 0.f;
     }
-    for (int c0 = ib; c0 < ie; c0 += TI) {
-      const int nI = min(TI, ie - c0);
-      const bool first_in = (c0 == ib);
-      __syncthreads();
-      for (int t = threadIdx.x; t < nI; t += kThreads) {
-        const int ep = in_edge[c0 + t];
-        eid_in[t] = ep;
-        u_in[3 * t] = unit[3 * (int64_t)ep];
-        u_in[3 * t + 1] = unit[3 * (int64_t)ep + 1];
-        u_in[3 * t + 2] = unit[3 * (int64_t)ep + 2];
+    // this lane's in-edge for the coefficient duty
+    const int epc = rr_mine == 0 ? ep[0] : ep[1];
+    const bool in_live = i0 + rr_mine < dI;
+    const float vx = unit[3 * (int64_t)epc], vy = unit[3 * (int64_t)epc + 1], vz = unit[3 * (int64_t)epc + 2];
+    double g[NP];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) g_in[t * NP + p] = gram[(int64_t)ep * NP + p];
-      }
-      __syncthreads();
-      for (int t = threadIdx.x; t < nO * nI; t += kThreads) {
-        const int j = t / nI, i = t - j * nI;
-        const float c = fmaf(u_out[3 * j], u_in[3 * i], fmaf(u_out[3 * j + 1], u_in[3 * i + 1], u_out[3 * j + 2] * u_in[3 * i + 2]));
+    for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)epc * NP + p];
+    float ks_x = 0.f, ks_y = 0.f, ks_z = 0.f;  // FORCES: d unit[e_i] partial of this lane (k->s role)
+
+    for (int oc = 0; oc < dO; oc += 32) {  // the node's out-edge ids, 32 at a time, one per lane
+      const int nO = min(32, dO - oc);
+      const int my_ej = out_edge[ob + oc + min(lane, nO - 1)];
+      for (int j0 = 0; j0 < nO; j0 += 8) {
+        // ---- coefficients of the 2 x 8 pairs of this batch
+        const int ej = __shfl_sync(0xffffffffu, my_ej, min(j0 + jj_mine, nO - 1));
+        const float ox = unit[3 * (int64_t)ej], oy = unit[3 * (int64_t)ej + 1], oz = unit[3 * (int64_t)ej + 2];
+        const float cc = fmaf(ox, vx, fmaf(oy, vy, oz * vz));
         float Y[4];
-        sph_harm<NL>(c, Y);
-        const float nrm = sqrtf(fmaxf((float)quad_form<NL>(g_in + i * NP, Y), 0.f));
-        const bool live = eid_out[j] != eid_in[i];
-        const float w = live ? 1.0f / fmaxf(nrm, kEps) : 0.f;
-        const size_t o = (size_t)j * TI + i;
-        st4(A + o * 4, make_float4(w * Y[0], w * Y[1], w * Y[2], w * Y[3]));
-        Fl[o] = (live && nrm > kEps) ? 1.f : 0.f;
-        if (FORCES) {
-          float dY[4];
-          sph_harm_grad<NL>(c, dY);
-          st4(A2 + o * 4, make_float4(w * dY[0], w * dY[1], w * dY[2], w * dY[3]));
-          Cc[o] = c;
-          Ww[o] = w;
-        }
-      }
-      __syncthreads();
-      // ---- each warp owns in-edges i0 .. i0+kRI-1 of the chunk
-      for (int i0 = warp * kRI; i0 < nI; i0 += kWarpsTb * kRI) {
-        float4 gb[kRI][NL][V4], dacc[kRI][NL][V4], gate[kRI][V4];
-        float h[kRI][NP];
-        int ep[kRI];
-#pragma unroll
-        for (int rr = 0; rr < kRI; ++rr) {
-          const bool valid = i0 + rr < nI;
-          ep[rr] = valid ? eid_in[i0 + rr] : -1;
-          const int k = valid ? in_src[c0 + i0 + rr] : 0;
-#pragma unroll
-          for (int v = 0; v < V4; ++v) {
-            const int c = (lane + 32 * v) * 4;
-            const bool ok = valid && c < C;
-            gate[rr][v] = ok ? sigmoid4(ldg4(xk + (int64_t)k * ldxk + c)) : zero4();
-#pragma unroll
-            for (int l = 0; l < NL; ++l) {
-              gb[rr][l][v] = ok ? mul4(gate[rr][v], ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c)) : zero4();
-              dacc[rr][l][v] = zero4();
-            }
+        sph_harm<NL>(cc, Y);
+        const float nrm = sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f));
+        const bool live = in_live && j0 + jj_mine < nO && ej != epc;
+        const float ww = live ? 1.0f / fmaxf(nrm, kEps) : 0.f;
+        const float fl = (live && nrm > kEps) ? 1.f : 0.f;
+        const float4 a = make_float4(ww * Y[0], ww * Y[1], ww * Y[2], ww * Y[3]);
+        __syncwarp();
+        if (lane < 16) {
+          st4(sa + lane * 4, a);
+          sf[lane] = fl;
+          if constexpr (FORCES) {
+            float dY[4];
+            sph_harm_grad<NL>(cc, dY);
+            st4(s_a2[warp] + lane * 4, make_float4(ww * dY[0], ww * dY[1], ww * dY[2], ww * dY[3]));
           }
-#pragma unroll
-          for (int p = 0; p < NP; ++p) h[rr][p] = 0.f;
         }
-        const int jsub = bfly8_index(lane);
-        for (int j0 = 0; j0 < nO; j0 += 8) {
-          float part[kRI][8], part2[FORCES ? kRI : 1][8];
+        __syncwarp();
+        // ---- d_tbw rows of the batch (all loads first)
+        float4 gr[8][V4];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < 8; ++jj) {
+          const int e = __shfl_sync(0xffffffffu, my_ej, min(j0 + jj, nO - 1));
 #pragma unroll
-            for (int rr = 0; rr < kRI; ++rr) {
-              part[rr][jj] = 0.f;
-              if constexpr (FORCES) part2[rr][jj] = 0.f;
-            }
-            if (j0 + jj < nO) {  // warp-uniform
-              const int j = j0 + jj;
-              float4 g[V4];
+          for (int v = 0; v < V4; ++v) gr[jj][v] = okc[v] ? ldg4(d_tbw + (int64_t)e * C + (lane + 32 * v) * 4) : zero4();
+        }
+        float part[kRI][8], part2[FORCES ? kRI : 1][8];
 #pragma unroll
-              for (int v = 0; v < V4; ++v) {
-                const int c = (lane + 32 * v) * 4;
-                g[v] = (c < C) ? lds4(Gt + (size_t)j * C + c) : zero4();
-              }
-#pragma unroll
-              for (int rr = 0; rr < kRI; ++rr) {
-                if (i0 + rr < nI) {  // warp-uniform
-                  const float4 a = lds4(A + ((size_t)j * TI + i0 + rr) * 4);
-                  float4 a2;
-                  if constexpr (FORCES) a2 = lds4(A2 + ((size_t)j * TI + i0 + rr) * 4);
-                  float d = 0.f, d2 = 0.f;
-#pragma unroll
-                  for (int v = 0; v < V4; ++v) {
-                    float4 t = scale4(a.x, gb[rr][0][v]);
-                    if (NL > 1) t = fma4(a.y, gb[rr][1][v], t);
-                    if (NL > 2) t = fma4(a.z, gb[rr][2][v], t);
-                    if (NL > 3) t = fma4(a.w, gb[rr][3][v], t);
-                    d += dot4(t, g[v]);
-                    if constexpr (FORCES) {
-                      float4 t2 = scale4(a2.x, gb[rr][0][v]);
-                      if (NL > 1) t2 = fma4(a2.y, gb[rr][1][v], t2);
-                      if (NL > 2) t2 = fma4(a2.z, gb[rr][2][v], t2);
-                      if (NL > 3) t2 = fma4(a2.w, gb[rr][3][v], t2);
-                      d2 += dot4(t2, g[v]);
-                    }
-                    dacc[rr][0][v] = fma4(a.x, g[v], dacc[rr][0][v]);
-                    if (NL > 1) dacc[rr][1][v] = fma4(a.y, g[v], dacc[rr][1][v]);
-                    if (NL > 2) dacc[rr][2][v] = fma4(a.z, g[v], dacc[rr][2][v]);
-                    if (NL > 3) dacc[rr][3][v] = fma4(a.w, g[v], dacc[rr][3][v]);
-                  }
-                  part[rr][jj] = d;
-                  if constexpr (FORCES) part2[rr][jj] = d2;
-                }
-              }
-            }
-          }
+        for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
           for (int rr = 0; rr < kRI; ++rr) {
-            const float dot = bfly8(part[rr], lane);
-            float dot2 = 0.f;
-            if constexpr (FORCES) dot2 = bfly8(part2[rr], lane);
-            const int j = j0 + jsub;
-            if (j < nO && i0 + rr < nI) {
-              const size_t o = (size_t)j * TI + i0 + rr;
-              const float4 a = lds4(A + o * 4);
-              const float sc = -Fl[o] * dot;
-              int p = 0;
+            const float4 ar = lds4(sa + (rr * 8 + jj) * 4);
+            float4 ar2;
+            if constexpr (FORCES) ar2 = lds4(s_a2[warp] + (rr * 8 + jj) * 4);
+            float d = 0.f, d2 = 0.f;
 #pragma unroll
-              for (int x = 0; x < NL; ++x)
-#pragma unroll
-                for (int y = x; y < NL; ++y) h[rr][p++] += sc * comp4(a, x) * comp4(a, y);
-              if (FORCES && (lane & 3) == 0) {
-                const float c = Cc[o], w = Ww[o];
-                float Y[4], dY[4];
-                sph_harm<NL>(c, Y);
-                sph_harm_grad<NL>(c, dY);
-                const float corr = (float)bilin_form<NL>(g_in + (i0 + rr) * NP, dY, Y);
-                Cc[o] = dot2 - Fl[o] * w * w * dot * corr;  // dL/dcos of this pair
+            for (int v = 0; v < V4; ++v) {
+              float4 t = scale4(ar.x, gb[rr][0][v]);
+              if (NL > 1) t = fma4(ar.y, gb[rr][1][v], t);
+              if (NL > 2) t = fma4(ar.z, gb[rr][2][v], t);
+              if (NL > 3) t = fma4(ar.w, gb[rr][3][v], t);
+              d += dot4(t, gr[jj][v]);
+              if constexpr (FORCES) {
+                float4 t2 = scale4(ar2.x, gb[rr][0][v]);
+                if (NL > 1) t2 = fma4(ar2.y, gb[rr][1][v], t2);
+                if (NL > 2) t2 = fma4(ar2.z, gb[rr][2][v], t2);
+                if (NL > 3) t2 = fma4(ar2.w, gb[rr][3][v], t2);
+                d2 += dot4(t2, gr[jj][v]);
               }
+              dacc[rr][0][v] = fma4(ar.x, gr[jj][v], dacc[rr][0][v]);
+              if (NL > 1) dacc[rr][1][v] = fma4(ar.y, gr[jj][v], dacc[rr][1][v]);
+              if (NL > 2) dacc[rr][2][v] = fma4(ar.z, gr[jj][v], dacc[rr][2][v]);
+              if (NL > 3) dacc[rr][3][v] = fma4(ar.w, gr[jj][v], dacc[rr][3][v]);
             }
+            part[rr][jj] = d;
+            if constexpr (FORCES) part2[rr][jj] = d2;
           }
         }
-        // ---- finish the in-edges of this warp
+        // ---- per pair scalars: the quad `jsub` of the warp finishes pair (j0 + jsub, i0 + rr)
+        float dotv[kRI], dot2v[FORCES ? kRI : 1];
 #pragma unroll
         for (int rr = 0; rr < kRI; ++rr) {
-          if (i0 + rr >= nI) continue;
+          dotv[rr] = bfly8(part[rr], lane);
+          if constexpr (FORCES) dot2v[rr] = bfly8(part2[rr], lane);
+          const int slot = rr * 8 + jsub;
+          const float4 ar = lds4(sa + slot * 4);
+          const float sc = -sf[slot] * dotv[rr];  // 0 for dead / clamped pairs
+          int p = 0;
 #pragma unroll
-          for (int p = 0; p < NP; ++p) {  // h was accumulated by one lane quad per out-edge slot: add the 8 slots
-            float x = h[rr][p];
-            x += __shfl_xor_sync(0xffffffffu, x, 4);
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            h[rr][p] = x;
-          }
-          float H[NL][NL];
-          {
-            int p = 0;
+          for (int x = 0; x < NL; ++x)
 #pragma unroll
-            for (int x = 0; x < NL; ++x)
+            for (int y = x; y < NL; ++y) h[rr][p++] += sc * comp4(ar, x) * comp4(ar, y);
+        }
+        if constexpr (FORCES) {
+          // dL/dcos of pair (j0 + jj, i0 + rr) is finished on its coefficient lane rr*8 + jj, which still holds the
+          // pair's cos / w / flag, both directions and the Gram matrix; the two dots come from the quad that owns
+          // butterfly element jj (lane bits 4,3,2 = bits 2,1,0 of jj).
+          const int srcl = (((jj_mine >> 2) & 1) << 4) | (((jj_mine >> 1) & 1) << 3) | ((jj_mine & 1) << 2);
 #pragma unroll
-              for (int y = x; y < NL; ++y) { H[x][y] = h[rr][p]; H[y][x] = h[rr][p]; ++p; }
-          }
-#pragma unroll
-          for (int v = 0; v < V4; ++v) {
-            const int c = (lane + 32 * v) * 4;
-            if (c < C) {
-              float4 b[NL];
-#pragma unroll
-              for (int l = 0; l < NL; ++l) b[l] = ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c);
-              float4 qq = zero4();
-#pragma unroll
-              for (int l = 0; l < NL; ++l) {
-                float4 o4 = mul4(gate[rr][v], dacc[rr][l][v]);
-#pragma unroll
-                for (int l2 = 0; l2 < NL; ++l2) o4 = fma4(H[l][l2], b[l2], o4);
-                float* dst = dB + ((int64_t)ep[rr] * NG + l) * C + c;
-                if (!first_out) o4 = add4(o4, *reinterpret_cast<const float4*>(dst));
-                st4(dst, o4);
-                qq = add4(qq, mul4(b[l], dacc[rr][l][v]));
+          for (int rr = 0; rr < kRI; ++rr) {
+            const float dt = __shfl_sync(0xffffffffu, dotv[rr], srcl);
+            const float dt2 = __shfl_sync(0xffffffffu, dot2v[rr], srcl);
+            if (lane < 16 && rr_mine == rr && live) {
+              float dY[4];
+              sph_harm_grad<NL>(cc, dY);
+              const float corr = (float)bilin_form<NL>(g, dY, Y);
+              const float dc = dt2 - fl * ww * ww * dt * corr;
+              ks_x = fmaf(dc, ox, ks_x); ks_y = fmaf(dc, oy, ks_y); ks_z = fmaf(dc, oz, ks_z);
+              const int j = oc + j0 + jj_mine;
+              if (j < kJS) {
+                s_st[warp][3 * j] = fmaf(dc, vx, s_st[warp][3 * j]);
+                s_st[warp][3 * j + 1] = fmaf(dc, vy, s_st[warp][3 * j + 1]);
+                s_st[warp][3 * j + 2] = fmaf(dc, vz, s_st[warp][3 * j + 2]);
+              } else {
+                atomicAdd(du_st + 3 * (int64_t)ej, dc * vx);
+                atomicAdd(du_st + 3 * (int64_t)ej + 1, dc * vy);
+                atomicAdd(du_st + 3 * (int64_t)ej + 2, dc * vz);
               }
-              const float4 sg = gate[rr][v];
-              qq = mul4(qq, make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w)));
-              float* qd = q + (int64_t)ep[rr] * C + c;
-              if (!first_out) qq = add4(qq, *reinterpret_cast<const float4*>(qd));
-              st4(qd, qq);
-              if (first_out)
-                for (int l = NL; l < NG; ++l) st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, zero4());
             }
+            __syncwarp();  // the two rr passes update the same s_st rows
           }
         }
       }
-      if (FORCES) {
-        __syncthreads();  // all dL/dcos of this (out chunk, in chunk) are in Cc
-        if (threadIdx.x < nO) {
-          const int j = threadIdx.x;
-          float ax = 0.f, ay = 0.f, az = 0.f;
-          for (int i = 0; i < nI; ++i) {
-            const float dc = Cc[(size_t)j * TI + i];
-            ax = fmaf(dc, u_in[3 * i], ax); ay = fmaf(dc, u_in[3 * i + 1], ay); az = fmaf(dc, u_in[3 * i + 2], az);
+    }
+    // ---- finish the in-edges of this warp
+    if constexpr (FORCES) {
+      // lanes 0-7 hold in-edge i0, lanes 8-15 in-edge i0+1: sum the 8 out-edge slots of each
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        ks_x += __shfl_xor_sync(0xffffffffu, ks_x, o);
+        ks_y += __shfl_xor_sync(0xffffffffu, ks_y, o);
+        ks_z += __shfl_xor_sync(0xffffffffu, ks_z, o);
+      }
+      if (lane < 16 && jj_mine == 0 && in_live) {
+        du_ks[3 * (int64_t)epc] = ks_x; du_ks[3 * (int64_t)epc + 1] = ks_y; du_ks[3 * (int64_t)epc + 2] = ks_z;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kRI; ++rr) {
+      if (i0 + rr >= dI) continue;  // warp-uniform
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {  // h was accumulated by one lane quad per out-edge slot: add the 8 slots
+        float x = h[rr][p];
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        h[rr][p] = x;
+      }
+      float H[NL][NL];
+      {
+        int p = 0;
+#pragma unroll
+        for (int x = 0; x < NL; ++x)
+#pragma unroll
+          for (int y = x; y < NL; ++y) { H[x][y] = h[rr][p]; H[y][x] = h[rr][p]; ++p; }
+      }
+#pragma unroll
+      for (int v = 0; v < V4; ++v) {
+        const int c = (lane + 32 * v) * 4;
+        if (okc[v]) {
+          float4 b[NL];
+#pragma unroll
+          for (int l = 0; l < NL; ++l) b[l] = ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c);
+          float4 qq = zero4();
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            float4 o4 = mul4(gt[rr][v], dacc[rr][l][v]);
+#pragma unroll
+            for (int l2 = 0; l2 < NL; ++l2) o4 = fma4(H[l][l2], b[l2], o4);
+            st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, o4);
+            qq = add4(qq, mul4(b[l], dacc[rr][l][v]));
           }
-          float* d = du_st + 3 * (int64_t)eid_out[j];
-          if (!first_in) { ax += d[0]; ay += d[1]; az += d[2]; }
-          d[0] = ax; d[1] = ay; d[2] = az;
-        } else if (threadIdx.x >= 64 && threadIdx.x - 64 < nI) {
-          const int i = threadIdx.x - 64;
-          float ax = 0.f, ay = 0.f, az = 0.f;
-          for (int j = 0; j < nO; ++j) {
-            const float dc = Cc[(size_t)j * TI + i];
-            ax = fmaf(dc, u_out[3 * j], ax); ay = fmaf(dc, u_out[3 * j + 1], ay); az = fmaf(dc, u_out[3 * j + 2], az);
-          }
-          float* d = du_ks + 3 * (int64_t)eid_in[i];
-          if (!first_out) { ax += d[0]; ay += d[1]; az += d[2]; }
-          d[0] = ax; d[1] = ay; d[2] = az;
+          const float4 sg = gt[rr][v];
+          qq = mul4(qq, make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w)));
+          st4(q + (int64_t)ep[rr] * C + c, qq);
+          for (int l = NL; l < NG; ++l) st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, zero4());
         }
       }
     }
   }
-}
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) {
-      lcao_set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
-      return LCAO_E_CUDA;
+  if constexpr (FORCES) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < min(dO, kJS) * 3; t += kBwdWarps * 32) {
+      float x = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBwdWarps; ++w) x += s_st[w][t];
+      du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = x;
     }
   }
-  return LCAO_OK;
-}
-
-// in-edges staged per chunk; LCAO_TB_TI overrides the default for tuning runs (multiple of 4, <= 64)
-int tile_in(const char* env, int dflt) {
-  const char* s = getenv(env);
-  int v = s ? atoi(s) : dflt;
-  if (v < 4 || v > 64 || v % 4) v = dflt;
-  return v;
 }
 
 }  // namespace
@@ -532,61 +502,49 @@ int tile_in(const char* env, int dflt) {
     default: { CALL(4, 2); } break; \
   }
 
-extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
-                                  int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
+                                  int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                                   const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                                   int32_t NL, float* tbw, void* stream) {
   if (N == 0 || E == 0) return LCAO_OK;
-  LCAO_REQUIRE(B && gram && unit && xk && in_ptr && in_edge && in_src && out_ptr && out_edge && tbw,
+  LCAO_REQUIRE(B && gram && unit && gate && in_ptr && in_edge && in_src && out_ptr && out_edge && tbw,
                "lcao_threebody_fwd: null buffer");
-  LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldxk % 4 == 0,
+  LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldg % 4 == 0,
                "lcao_threebody_fwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL (C=%d NL=%d NG=%d)", C, NL, NG);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int TI = tile_in("LCAO_TB_TI", 32);
-  const int NP = NL * (NL + 1) / 2;
-  const size_t smem = (size_t)TI * NP * 8 + sizeof(float) * ((size_t)TI * NL * C + (size_t)kTO * TI * 4 + TI * 3 + kTO * 3 + TI + kTO);
   const int V4 = C <= 128 ? 1 : 2;
-#define CALL(nl, v4)                                                                                             \
-  if (int rc = set_smem(k_threebody_fwd<nl, v4>, smem)) return rc;                                               \
-  k_threebody_fwd<nl, v4><<<(unsigned)N, kThreads, smem, st>>>(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, \
-                                                               out_ptr, out_edge, C, TI, tbw)
+#define CALL(nl, v4)                                                                                              \
+  k_threebody_fwd<nl, v4><<<(unsigned)N, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, \
+                                                                  out_ptr, out_edge, C, tbw)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
 
-extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* xk,
-                                  int64_t ldxk, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
+extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
+                                  int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                                   const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
                                   int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks,
                                   float* d_unit_st, void* stream) {
   if (N == 0 || E == 0) return LCAO_OK;
-  LCAO_REQUIRE(B && gram && unit && xk && in_ptr && in_edge && in_src && out_ptr && out_edge && d_tbw && dB && q,
+  LCAO_REQUIRE(B && gram && unit && gate && in_ptr && in_edge && in_src && out_ptr && out_edge && d_tbw && dB && q,
                "lcao_threebody_bwd: null buffer");
-  LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldxk % 4 == 0,
+  LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldg % 4 == 0,
                "lcao_threebody_bwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL");
   LCAO_REQUIRE((d_unit_ks == nullptr) == (d_unit_st == nullptr), "lcao_threebody_bwd: pass both d_unit buffers or neither");
   cudaStream_t st = (cudaStream_t)stream;
-  static const int TI = tile_in("LCAO_TB_TI_BWD", 32);
-  const int NP = NL * (NL + 1) / 2;
   const bool forces = d_unit_ks != nullptr;
-  const size_t pairs = (size_t)kTO * TI;
-  const size_t smem = (size_t)TI * NP * 8 +
-                      sizeof(float) * ((size_t)kTO * C + pairs * 4 + pairs + (forces ? pairs * 6 : 0) + TI * 3 + kTO * 3 + TI + kTO);
   const int V4 = C <= 128 ? 1 : 2;
-#define CALL(nl, v4)                                                                                                  \
-  if (forces) {                                                                                                       \
-    if (int rc = set_smem(k_threebody_bwd<nl, v4, true>, smem)) return rc;                                            \
-    k_threebody_bwd<nl, v4, true><<<(unsigned)N, kThreads, smem, st>>>(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge,  \
-                                                                       in_src, out_ptr, out_edge, C, TI, d_tbw, dB, q, \
-                                                                       d_unit_ks, d_unit_st);                         \
-  } else {                                                                                                            \
-    if (int rc = set_smem(k_threebody_bwd<nl, v4, false>, smem)) return rc;                                           \
-    k_threebody_bwd<nl, v4, false><<<(unsigned)N, kThreads, smem, st>>>(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, \
-                                                                        in_src, out_ptr, out_edge, C, TI, d_tbw, dB,  \
-                                                                        q, nullptr, nullptr);                         \
-  }
+#define CALL(nl, v4)                                                                                                   \
+  if (forces)                                                                                                          \
+    k_threebody_bwd<nl, v4, true><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
+                                                                          in_src, out_ptr, out_edge, C, d_tbw, dB, q,  \
+                                                                          d_unit_ks, d_unit_st);                       \
+  else                                                                                                                 \
+    k_threebody_bwd<nl, v4, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,       \
+                                                                           in_edge, in_src, out_ptr, out_edge, C,      \
+                                                                           d_tbw, dB, q, nullptr, nullptr)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();

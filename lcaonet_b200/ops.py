@@ -305,17 +305,20 @@ class _ThreeBody(torch.autograd.Function):
         B, unit = B.contiguous(), unit.contiguous()
         E, NG, C = B.shape
         assert xk.stride(1) == 1 and gram.dtype == torch.float64 and gram.is_contiguous()
+        st = stream_ptr()
+        gate = torch.empty(gi.N, C, device=B.device)  # sigmoid(xk) once per node
+        _call("lcao_sigmoid_rows", ptr(xk), xk.stride(0), ptr(gate), C, gi.N, C, st)
         tbw = torch.empty(E, C, device=B.device)
-        _call("lcao_threebody_fwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr),
-              ptr(gi.in_edge), ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(tbw), stream_ptr())
+        _call("lcao_threebody_fwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(gate), C, ptr(gi.in_ptr),
+              ptr(gi.in_edge), ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(tbw), st)
         ctx.gi, ctx.NL = gi, NL
-        ctx.save_for_backward(B, gram, unit, xk)
+        ctx.save_for_backward(B, gram, unit, gate)
         return tbw
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_tbw):
-        B, gram, unit, xk = ctx.saved_tensors
+        B, gram, unit, gate = ctx.saved_tensors
         gi, NL = ctx.gi, ctx.NL
         E, NG, C = B.shape
         d_tbw = d_tbw.contiguous()
@@ -325,7 +328,7 @@ class _ThreeBody(torch.autograd.Function):
         forces = ctx.needs_input_grad[2]
         du_ks = torch.empty(E, 3, device=B.device) if forces else None
         du_st = torch.empty(E, 3, device=B.device) if forces else None
-        _call("lcao_threebody_bwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(xk), xk.stride(0), ptr(gi.in_ptr),
+        _call("lcao_threebody_bwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(gate), C, ptr(gi.in_ptr),
               ptr(gi.in_edge), ptr(gi.in_src), ptr(gi.out_ptr), ptr(gi.out_edge), gi.N, E, C, NL, ptr(d_tbw), ptr(dB),
               ptr(q), ptr(du_ks), ptr(du_st), st)
         d_xk = torch.empty(gi.N, C, device=B.device)

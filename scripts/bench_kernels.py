@@ -15,6 +15,8 @@ FLUSH = None
 
 def timeit(fn, reps=5, warm=2):
     global FLUSH
+    if os.environ.get("LCAO_BENCH_ONCE"):  # one launch per kernel: for ncu captures
+        reps, warm = 1, 0
     if FLUSH is None:
         FLUSH = torch.empty(128 * 1024 * 1024, device=DEV)
     for _ in range(warm):
@@ -80,7 +82,7 @@ def edge():
     print(f"pair_contract E={E}: fwd {t_pf:.3f} ms ({bpf/t_pf/1e6:.0f} GB/s) | bwd {t_pb:.3f} ms ({bpb/t_pb/1e6:.0f} GB/s)", flush=True)
     # ---- three-body
     unit = torch.nn.functional.normalize(torch.randn(E, 3, device=DEV), dim=1)
-    xk = torch.randn(N, 2 * C, device=DEV)[:, C:]
+    xk = torch.sigmoid(torch.randn(N, C, device=DEV))  # gate rows
     tbw, dB, q = torch.empty(E, C, device=DEV), torch.empty(E, NL, C, device=DEV), torch.empty(E, C, device=DEV)
     du1, du2 = torch.empty(E, 3, device=DEV), torch.empty(E, 3, device=DEV)
     d_tbw = torch.randn(E, C, device=DEV)

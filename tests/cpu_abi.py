@@ -309,6 +309,10 @@ def lcao_pair_contract_bwd(tab, pair, kptr, kperm, rb, vmask, lgrp, dB, E, P, O,
         view(d_rb, E, O).copy_(g)
 
 
+def lcao_sigmoid_rows(x, ldx, out, ldo, M, C, stream):
+    view(out, M, C, ld=ldo).copy_(torch.sigmoid(view(x, M, C, ld=ldx)))
+
+
 def _sph_grad(c, NL):
     y = [torch.zeros_like(c), torch.full_like(c, 0.4886025119029199), 2 * 0.9461746957575601 * c,
          0.3731763325901154 * (15 * c * c - 3)]
@@ -328,7 +332,7 @@ def _tb_common(B, NG, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge
     Y = _sph(cos, NL)
     v = torch.einsum("tl,tlc->tc", Y, Bt[ep][:, :NL])
     nrm = v.norm(dim=1, keepdim=True)
-    sg = torch.sigmoid(X[src[ep]])
+    sg = X[src[ep]]  # the gate rows are sigmoid(xk) already (lcao_sigmoid_rows)
     return Bt, e, ep, Y, v, nrm, sg, src, cos, u
 
 
@@ -353,7 +357,7 @@ def lcao_threebody_bwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out
     out[:, :NL] = torch.zeros(E, NL, C).index_add(0, ep, Y.unsqueeze(-1) * dv.unsqueeze(1))
     gy = torch.zeros(E, C).index_add(0, ep, G * v * inv)
     X = view(xk, N, C, ld=ldxk)
-    s_all = torch.sigmoid(X[src])
+    s_all = X[src]
     view(q, E, C).copy_(gy * s_all * (1 - s_all))
     if du_ks:
         dYl = torch.einsum("tlc,tc->tl", Bt[ep][:, :NL], dv)  # dL/dY_l per triplet

@@ -46,5 +46,5 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
     rc = lib.lcao_twobody_fwd(None, 3, None, 10, 128, 3, 0, None, None)
     assert rc == -1 and b"null buffer" in lib.lcao_last_error()
-    rc = lib.lcao_threebody_fwd(1, 3, 1, 1, 1, 6, 1, 1, 1, 1, 1, 4, 4, 130, 3, 1, None)
+    rc = lib.lcao_threebody_fwd(1, 3, 1, 1, 1, 8, 1, 1, 1, 1, 1, 4, 4, 130, 3, 1, None)
     assert rc == -1 and b"C % 4" in lib.lcao_last_error()
