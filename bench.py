@@ -217,12 +217,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps  # CPU time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -238,6 +242,7 @@ def run_ours(args):
         sampler.start()
     l0 = _lib.launch_count()
     ms_dev = timed(lambda: step(GraphClone(resident), y_dev), args.steps)
+    host_enqueue_ms = host_ms[0]
     launches = (_lib.launch_count() - l0) // max(args.steps, 1)
 
     # ---- end-to-end timing (e2e): pinned host batch -> H2D -> step -> D2H loss
@@ -250,6 +255,20 @@ def run_ours(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+
+    if args.profile_host and rank == 0:  # where does the CPU time of one step go?
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        torch.cuda.synchronize()
+        pr.enable()
+        for _ in range(5):
+            step(GraphClone(resident), y_dev)
+        pr.disable()
+        torch.cuda.synchronize()
+        st_ = pstats.Stats(pr, stream=sys.stderr)
+        st_.sort_stats("tottime").print_stats(35)
+        st_.sort_stats("cumtime").print_stats(45)
 
     # ---- per-kernel profile of one step (CUDA events around every C-ABI call on the launching stream)
     prof = profile_step(ops, lambda: step(GraphClone(resident), y_dev), reps=3)
@@ -287,13 +306,15 @@ def run_ours(args):
         line = {
             "metric": "molecules/sec fwd+bwd (QM9-shape)", "value": total_mols / (ms_dev * 1e-3), "unit": "molecules/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+            "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(m=args.mol_per_gpu), "N": sizes["N"], "E": sizes["E"], "T": sizes["T"],
                        "gemm_mode": ops.get_gemm_mode(), "side_effect_keys": model.side_effect_keys,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": total_mols / (ms_e2e * 1e-3), "unit": "molecules/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline,
+            "kernels": kernels if os.environ.get("LCAO_BENCH_SHAPES") else kernels[:12], "cpu_baseline": cpu,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -334,6 +355,8 @@ def profile_step(ops, fn, reps=3):
         elif name == "lcao_linear_wgrad":
             M, K, Nout = a[9], a[10], a[11]
             meta = (4 * M * (K + Nout), 2 * M * K * Nout)
+        if meta and os.environ.get("LCAO_BENCH_SHAPES"):
+            name = f"{name}[M={a[8] if name != 'lcao_linear_wgrad' else a[9]},K={a[9] if name != 'lcao_linear_wgrad' else a[10]},N={a[10] if name != 'lcao_linear_wgrad' else a[11]}]"
         records.append((name, e0, e1, meta))
 
     ops._call = timed_call
@@ -366,6 +389,7 @@ def main():
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-side-effect-keys", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--profile-host", action="store_true", help="cProfile of 5 steps (host side) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

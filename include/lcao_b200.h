@@ -147,20 +147,24 @@ int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram, const flo
  * NG > NL.  q (E,C) = per in-edge gradient of the gate PRE-activation xk (the sigmoid derivative is
  * applied here): d_xk[k] = sum_{e' in out(k)} q[e'].  d_unit_ks / d_unit_st (E,3; both or neither):
  * gradient w.r.t. unit[e] from its role as in-edge (k->s) and as out-edge (s->t); d_unit = their sum
- * (autograd forces). */
+ * (autograd forces).  dP (nullable): the COMPACT two-body gradient of lcao_twobody_bwd (E, 1 + valence, C);
+ * when given, dB = three-body part + dP[e,0,:] for every l < NL and dB[e,NL,:] = dP[e,1,:], i.e. the sum
+ * autograd would otherwise form with a separate (E,NG,C) pass. */
 int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
                        int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                        const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
-                       int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks, float* d_unit_st,
-                       void* stream);
+                       int32_t NL, const float* d_tbw, const float* dP, float* dB, float* q, float* d_unit_ks,
+                       float* d_unit_st, void* stream);
 
 /* ---- two-body weight (lcaonet.py:192-204) ----------------------------------------------------- */
 /* p = (1+g[:, :C]) * PA + (1+g[:, C:]) * PV ;  lw = p / max(|p|, 1e-12)
  * PA = sum_l B[e,l,:] - B[e,NL,:],  PV = B[e,NL,:] (valence) ;  PA = sum_l B[e,l,:] otherwise. */
 int lcao_twobody_fwd(const float* B, int32_t NG, const float* g, int64_t E, int32_t C, int32_t NL,
                      int32_t valence, float* lw, void* stream);
+/* compact = 0: dB is (E,NG,C) (the same row repeated for every l < NL, then the valence slot);
+ * compact = 1: dB is (E, 1 + valence, C): [row shared by all l < NL | valence slot]. */
 int lcao_twobody_bwd(const float* B, int32_t NG, const float* g, const float* d_lw, int64_t E, int32_t C,
-                     int32_t NL, int32_t valence, float* dB, float* d_g, void* stream);
+                     int32_t NL, int32_t valence, int32_t compact, float* dB, float* d_g, void* stream);
 
 /* ---- edge <- node gathers and node <- edge segment sums (torch_scatter sites lcaonet.py:208,293,307;
  *      ATen index sites lcaonet.py:209) --------------------------------------------------------- */

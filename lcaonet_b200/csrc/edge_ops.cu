@@ -151,7 +151,7 @@ template <bool VAL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* __restrict__ B, int NG,
                                                                    const float* __restrict__ g,
                                                                    const float* __restrict__ d_lw, int64_t E, int C,
-                                                                   int NL, float* __restrict__ dB,
+                                                                   int NL, int compact, float* __restrict__ dB,
                                                                    float* __restrict__ d_g) {
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
@@ -184,10 +184,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* 
     if (c < C) {
       float4 dp = f4_scale(inv, f4_sub(dl[v], f4_scale(coef, p[v])));
       const float4 dPA = make_float4(fmaf(gA[v].x, dp.x, dp.x), fmaf(gA[v].y, dp.y, dp.y), fmaf(gA[v].z, dp.z, dp.z), fmaf(gA[v].w, dp.w, dp.w));
-      for (int l = 0; l < NL; ++l) st4(dB + (e * NG + l) * (int64_t)C + c, dPA);
+      const int NGo = compact ? (VAL ? 2 : 1) : NG, NLo = compact ? 1 : NL;  // compact: one row for all l < NL
+      for (int l = 0; l < NLo; ++l) st4(dB + (e * NGo + l) * (int64_t)C + c, dPA);
       if (VAL) {
         const float4 dPV = make_float4(fmaf(gV[v].x, dp.x, dp.x), fmaf(gV[v].y, dp.y, dp.y), fmaf(gV[v].z, dp.z, dp.z), fmaf(gV[v].w, dp.w, dp.w));
-        st4(dB + (e * NG + NL) * (int64_t)C + c, f4_sub(dPV, dPA));
+        st4(dB + (e * NGo + NLo) * (int64_t)C + c, f4_sub(dPV, dPA));
         st4(d_g + e * 2 * (int64_t)C + c, f4_mul(dp, PA[v]));
         st4(d_g + e * 2 * (int64_t)C + C + c, f4_mul(dp, PV[v]));
       } else {
@@ -400,15 +401,15 @@ extern "C" int lcao_twobody_fwd(const float* B, int32_t NG, const float* g, int6
 }
 
 extern "C" int lcao_twobody_bwd(const float* B, int32_t NG, const float* g, const float* d_lw, int64_t E, int32_t C,
-                                int32_t NL, int32_t valence, float* dB, float* d_g, void* stream) {
+                                int32_t NL, int32_t valence, int32_t compact, float* dB, float* d_g, void* stream) {
   if (E == 0) return LCAO_OK;
   LCAO_REQUIRE(B && g && d_lw && dB && d_g, "lcao_twobody_bwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NG == NL + (valence ? 1 : 0),
                "lcao_twobody_bwd: need C %% 4 == 0, C <= 256, NG == NL + valence");
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-  if (valence) k_twobody_bwd<true><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, dB, d_g);
-  else k_twobody_bwd<false><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, dB, d_g);
+  if (valence) k_twobody_bwd<true><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+  else k_twobody_bwd<false><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

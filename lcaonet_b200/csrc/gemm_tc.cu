@@ -405,6 +405,7 @@ struct WgradArgs {
   const float* X; int64_t ldx;
   float* dW; int64_t ldw;
   float* db;
+  float* part;     // per-CTA partial sums: [grid][Kx][128] then [grid][128] column sums (deterministic two-stage reduction)
   int64_t M; int Kx; int x3, raw_stages, op_stages;
 };
 
@@ -455,7 +456,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (c_beg >= c_end) {  // more CTAs than row chunks: nothing to do
+  if (c_beg >= c_end) {  // more CTAs than row chunks: nothing to do but to zero this CTA's partial slot
+    for (int i = threadIdx.x; i < g.Kx * 128; i += kRowsThreads) g.part[(size_t)blockIdx.x * g.Kx * 128 + i] = 0.f;
+    if (g.db && threadIdx.x < 128) g.part[(size_t)gridDim.x * g.Kx * 128 + (size_t)blockIdx.x * 128 + threadIdx.x] = 0.f;
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
     return;
@@ -544,11 +547,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
       mbar_arrive(&op_full[s]);
       mbar_arrive(&raw_empty[r]);
     }
-    if (g.db) {
+    if (g.db) {  // the 8 row-group threads (kg = lane & 7) of a column group are adjacent lanes
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        float* d = g.db + (g0 + 16 * i) * 4;
-        atomicAdd(d + 0, colsum[i].x); atomicAdd(d + 1, colsum[i].y); atomicAdd(d + 2, colsum[i].z); atomicAdd(d + 3, colsum[i].w);
+        float4 c = colsum[i];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          c.x += __shfl_xor_sync(0xffffffffu, c.x, o); c.y += __shfl_xor_sync(0xffffffffu, c.y, o);
+          c.z += __shfl_xor_sync(0xffffffffu, c.z, o); c.w += __shfl_xor_sync(0xffffffffu, c.w, o);
+        }
+        if (kg == 0)
+          *reinterpret_cast<float4*>(g.part + (size_t)gridDim.x * g.Kx * 128 + (size_t)blockIdx.x * 128 + (g0 + 16 * i) * 4) = c;
       }
     }
   } else if (warp == 8) {
@@ -614,15 +623,31 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
       mbar_arrive(&tempty[acc]);
     }
     const int n = warp * 32 + lane;
+    float* pp = g.part + (size_t)blockIdx.x * g.Kx * 128 + n;   // [cta][j][n]: coalesced over the 128 rows n
 #pragma unroll
     for (int j = 0; j < kMaxCols; ++j)
-      if (j < g.Kx) atomicAdd(g.dW + (int64_t)n * g.ldw + j, sum[j]);
+      if (j < g.Kx) pp[(size_t)j * 128] = sum[j];
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// stage 2 of the weight gradient: dW[n, j] += sum_cta part[cta][j][n] ; db[n] += sum_cta part_db[cta][n]  (fixed order)
+__global__ void __launch_bounds__(128) k_wgrad_reduce(const float* __restrict__ part, int ncta, int Kx, float* __restrict__ dW,
+                                                      int64_t ldw, float* __restrict__ db) {
+  const int j = blockIdx.x, n = threadIdx.x;
+  if (j < Kx) {
+    float acc = 0.f;
+    for (int c = 0; c < ncta; ++c) acc += part[((size_t)c * Kx + j) * 128 + n];
+    dW[(int64_t)n * ldw + j] += acc;
+  } else if (db) {
+    float acc = 0.f;
+    for (int c = 0; c < ncta; ++c) acc += part[(size_t)ncta * Kx * 128 + (size_t)c * 128 + n];
+    db[n] += acc;
   }
 }
 
@@ -690,11 +715,19 @@ bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* d
          wgrad_smem(Kx, 1, 2, 2) <= kMaxSmem;
 }
 
+// CTAs of the weight-gradient kernel: at least 1024 rows each (the per-CTA cost is the 64 KB partial tile)
+static unsigned wgrad_grid(int64_t M) {
+  const int64_t want = (M + 1023) / 1024;
+  return (unsigned)(want < 1 ? 1 : want < num_sms() ? want : num_sms());
+}
+// floats of scratch lcao_tc_wgrad needs
+int64_t lcao_tc_wgrad_scratch(int64_t M, int Kx) { return (int64_t)wgrad_grid(M) * ((int64_t)Kx * 128 + 128); }
+
 // dW (128 rows of the weight gradient, row stride ldw) += dY[:, 0:128]^T X[:, 0:Kx]
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
-                  int Kx, int x3, cudaStream_t st) {
+                  int Kx, int x3, float* part, cudaStream_t st) {
   WgradArgs g{};
-  g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db;
+  g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db; g.part = part;
   g.M = M; g.Kx = Kx; g.x3 = x3;
   g.op_stages = 2;
   int raw_stages = 6;
@@ -705,9 +738,10 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
     LCAO_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     attr_set = true;
   }
-  const int64_t nchunks = (M + kChunkK - 1) / kChunkK;
-  const unsigned grid = (unsigned)(nchunks < num_sms() ? nchunks : num_sms());
+  const unsigned grid = wgrad_grid(M);
   k_tc_wgrad<<<grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st>>>(g);
+  LCAO_LAUNCH_CHECK();
+  k_wgrad_reduce<<<Kx + (db ? 1 : 0), 128, 0, st>>>(part, (int)grid, Kx, dW, ldw, db);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

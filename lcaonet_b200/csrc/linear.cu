@@ -15,7 +15,8 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
                  int accumulate, int x3, cudaStream_t st);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
-                  int Kx, int x3, cudaStream_t st);
+                  int Kx, int x3, float* part, cudaStream_t st);
+int64_t lcao_tc_wgrad_scratch(int64_t M, int Kx);
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -64,9 +65,12 @@ static bool wgrad_tc(const float* dY, int64_t ldy, const float* X, int64_t ldx, 
 extern "C" int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act,
                                            const float* W, const float* X, int64_t ldx, const float* dX, int64_t lddx,
                                            int64_t M, int32_t K, int32_t Nout, int32_t mode) {
-  (void)dY; (void)ldy; (void)ldh; (void)W; (void)X; (void)ldx; (void)dX; (void)lddx; (void)K; (void)mode;
-  // every GEMM kernel takes dY * act'(H) as a plain operand: one elementwise pass into scratch
-  return (act == LCAO_ACT_NONE || !H) ? 0 : M * (int64_t)Nout;
+  (void)ldh; (void)W; (void)dX; (void)lddx;
+  // every GEMM kernel takes dY * act'(H) as a plain operand: one elementwise pass into scratch; the tcgen05
+  // weight-gradient kernel additionally needs room for its per-CTA partial tiles (deterministic reduction)
+  int64_t n = (act == LCAO_ACT_NONE || !H) ? 0 : M * (int64_t)Nout;
+  if (X && wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode)) n += lcao_tc_wgrad_scratch(M, K);
+  return n;
 }
 
 extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,
@@ -101,14 +105,17 @@ extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(dY && X && dW, "lcao_linear_wgrad: null buffer");
   LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_wgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode);  // decided on the caller's dY, like the scratch query
+  float* part = (act == LCAO_ACT_NONE || !H) ? scratch : scratch + M * (int64_t)Nout;
   {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_wgrad");
     if (rc) return rc;
   }
-  if (!wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode)) return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
+  if (!tc || !wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode)) return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
+  LCAO_REQUIRE(scratch, "lcao_linear_wgrad: scratch of lcao_linear_bwd_scratch() floats is needed (per-CTA partial tiles)");
   for (int n0 = 0; n0 < Nout; n0 += 128) {
     int rc = lcao_tc_wgrad(dY + n0, ldy, X, ldx, dW + (int64_t)n0 * K, K, db ? db + n0 : nullptr, M, K,
-                           mode == LCAO_GEMM_TF32X3, st);
+                           mode == LCAO_GEMM_TF32X3, part, st);
     if (rc) return rc;
   }
   return LCAO_OK;

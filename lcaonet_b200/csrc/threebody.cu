@@ -236,9 +236,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, float* __restrict__ dB,
-    float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
+    const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
+    float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
+  const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
   // per-warp scratch, pair (rr, jj) at slot rr*8 + jj: a_l = w Y_l | norm-path flag | (forces) w Y'_l
   __shared__ __align__(16) float s_a[kBwdWarps][16 * 4];
   __shared__ float s_f[kBwdWarps][16];
@@ -257,7 +258,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     for (int i = warp; i < dI; i += kBwdWarps) {
       const int ep = in_edge[ib + i];
       for (int c = lane * 4; c < C; c += 128) {
-        for (int l = 0; l < NG; ++l) st4(dB + ((int64_t)ep * NG + l) * C + c, zero4());
+        for (int l = 0; l < NG; ++l)
+          st4(dB + ((int64_t)ep * NG + l) * C + c, dP ? ldg4(dP + ((int64_t)ep * NGP + (l < NL ? 0 : 1)) * C + c) : zero4());
         st4(q + (int64_t)ep * C + c, zero4());
       }
       if (FORCES && lane < 3) du_ks[3 * (int64_t)ep + lane] = 0.f;
@@ -461,9 +463,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
 #pragma unroll
           for (int l = 0; l < NL; ++l) b[l] = ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c);
           float4 qq = zero4();
+          const float4 two_body = dP ? ldg4(dP + (int64_t)ep[rr] * NGP * C + c) : zero4();  // same for every l < NL
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
-            float4 o4 = mul4(gt[rr][v], dacc[rr][l][v]);
+            float4 o4 = fma4(1.0f, mul4(gt[rr][v], dacc[rr][l][v]), two_body);
 #pragma unroll
             for (int l2 = 0; l2 < NL; ++l2) o4 = fma4(H[l][l2], b[l2], o4);
             st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, o4);
@@ -472,7 +475,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
           const float4 sg = gt[rr][v];
           qq = mul4(qq, make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w)));
           st4(q + (int64_t)ep[rr] * C + c, qq);
-          for (int l = NL; l < NG; ++l) st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, zero4());
+          for (int l = NL; l < NG; ++l)
+            st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, dP ? ldg4(dP + ((int64_t)ep[rr] * NGP + 1) * C + c) : zero4());
         }
       }
     }
@@ -525,7 +529,7 @@ extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram
 extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate,
                                   int64_t ldg, const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src,
                                   const int32_t* out_ptr, const int32_t* out_edge, int64_t N, int64_t E, int32_t C,
-                                  int32_t NL, const float* d_tbw, float* dB, float* q, float* d_unit_ks,
+                                  int32_t NL, const float* d_tbw, const float* dP, float* dB, float* q, float* d_unit_ks,
                                   float* d_unit_st, void* stream) {
   if (N == 0 || E == 0) return LCAO_OK;
   LCAO_REQUIRE(B && gram && unit && gate && in_ptr && in_edge && in_src && out_ptr && out_edge && d_tbw && dB && q,
@@ -533,18 +537,19 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldg % 4 == 0,
                "lcao_threebody_bwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL");
   LCAO_REQUIRE((d_unit_ks == nullptr) == (d_unit_st == nullptr), "lcao_threebody_bwd: pass both d_unit buffers or neither");
+  LCAO_REQUIRE(NG <= NL + 1, "lcao_threebody_bwd: at most one valence group (NG <= NL + 1)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
 #define CALL(nl, v4)                                                                                                   \
   if (forces)                                                                                                          \
     k_threebody_bwd<nl, v4, true><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
-                                                                          in_src, out_ptr, out_edge, C, d_tbw, dB, q,  \
-                                                                          d_unit_ks, d_unit_st);                       \
+                                                                          in_src, out_ptr, out_edge, C, d_tbw, dP, dB, \
+                                                                          q, d_unit_ks, d_unit_st);                    \
   else                                                                                                                 \
     k_threebody_bwd<nl, v4, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,       \
                                                                            in_edge, in_src, out_ptr, out_edge, C,      \
-                                                                           d_tbw, dB, q, nullptr, nullptr)
+                                                                           d_tbw, dP, dB, q, nullptr, nullptr)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();

@@ -249,11 +249,19 @@ class LCAOInteraction(nn.Module):
         self.f_node = nn.Sequential(Dense(2 * C, C, True, weight_init), activation,
                                     Dense(C, C, True, weight_init), activation)
         self.out_weight = Dense(C, emb_size, False, weight_init)
+        # run the block as ONE autograd node (ops.interaction_layer); False = one node per kernel (same arithmetic)
+        self.fused_node = True
 
     def forward(self, x, cst, vmask, rb, unit, gi, lgrp, NL) -> Tensor:
         if self.add_valence and vmask is None:
             raise ValueError("valence_mask must be provided when add_valence=True")
         C = self.emb_size_conv
+        if isinstance(cst, PairCoeffs) and self.fused_node and x.shape[1] % 4 == 0:
+            fc, fn = self.f_coeffs, self.f_node
+            return ops.interaction_layer(x, cst.table, rb, unit, self.node_weight.weight, self.node_weight.bias, fc[0].weight,
+                                         fc[2].weight, self.f_three[0].weight, self.basis_weight.weight, fn[0].weight,
+                                         fn[0].bias, fn[2].weight, fn[2].bias, self.out_weight.weight, cst.pair, cst.kptr,
+                                         cst.kperm, vmask, lgrp, gi, NL, C)
         nw = self.node_weight(x)  # (N, 2C): [:, :C] feeds f_node, [:, C:] is the three-body gate
         xc, xk = nw[:, :C], nw[:, C:]
         if isinstance(cst, PairCoeffs):  # f_coeffs on the species-pair table, contracted per edge
@@ -262,9 +270,10 @@ class LCAOInteraction(nn.Module):
         else:  # a materialised (E, O, K) coefficient tensor, as in the reference signature
             cst1 = _mlp(self.f_coeffs, cst)  # (E, O, C')
             B, gram = ops.coeff_contract(cst1, rb, vmask, lgrp, NL, C), None
-        tbw = ops.threebody(B, unit, xk, gi, NL, gram)  # (E, C)
+        link = ops.BodyLink()  # the two consumers of B share one gradient pass
+        tbw = ops.threebody(B, unit, xk, gi, NL, gram, link)  # (E, C)
         g = self.f_three[0](tbw)  # (E, C')
-        lw = ops.twobody(B, g, NL, 1 if self.add_valence else 0)  # (E, C)
+        lw = ops.twobody(B, g, NL, 1 if self.add_valence else 0, link)  # (E, C)
         bw = self.basis_weight(lw)
         w1 = self.f_node[0].weight  # (C, 2C) acting on [x_s ; x_t]  ->  W1a x_s + W1b x_t, per NODE
         u = ops.linear(xc, torch.cat([w1[:, :C], w1[:, C:]], dim=0))  # (N, 2C)

@@ -89,8 +89,8 @@ def edge():
     args = (P(B), NL, P(gram), P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge), P(gi.in_src), P(gi.out_ptr),
             P(gi.out_edge), N, E, C, NL)
     t_f = timeit(lambda: ops._call("lcao_threebody_fwd", *args, P(tbw), st()))
-    t_b = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), P(dB), P(q), None, None, st()))
-    t_bf = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), P(dB), P(q), P(du1), P(du2), st()))
+    t_b = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), None, P(dB), P(q), None, None, st()))
+    t_bf = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), None, P(dB), P(q), P(du1), P(du2), st()))
     T = gi.num_triplets()
     bf = E * (4 * NL * C + 48 + 12 + 8 + 4 * C) + N * (4 * C + 8)
     bb = E * (4 * NL * C + 48 + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)

@@ -342,7 +342,7 @@ def lcao_threebody_fwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out
     view(tbw, E, C).copy_(torch.zeros(E, C).index_add(0, e, y * sg))
 
 
-def lcao_threebody_bwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, d_tbw, dB, q,
+def lcao_threebody_bwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out_ptr, out_edge, N, E, C, NL, d_tbw, dP, dB, q,
                        du_ks, du_st, stream):
     """reference-style chain (v, normalise, gate) differentiated directly — independent of the Gram formulation
     the CUDA kernel uses."""
@@ -355,6 +355,11 @@ def lcao_threebody_bwd(B, NG, gram, unit, xk, ldxk, in_ptr, in_edge, in_src, out
     out = view(dB, E, NG * C).reshape(E, NG, C)
     out.zero_()
     out[:, :NL] = torch.zeros(E, NL, C).index_add(0, ep, Y.unsqueeze(-1) * dv.unsqueeze(1))
+    if dP:
+        two = view(dP, E, (NG - NL + 1) * C).reshape(E, NG - NL + 1, C)
+        out[:, :NL] += two[:, :1]
+        if NG > NL:
+            out[:, NL] = two[:, 1]
     gy = torch.zeros(E, C).index_add(0, ep, G * v * inv)
     X = view(xk, N, C, ld=ldxk)
     s_all = X[src]
@@ -382,7 +387,7 @@ def lcao_twobody_fwd(B, NG, g, E, C, NL, valence, lw, stream):
     view(lw, E, C).copy_(p / p.norm(dim=1, keepdim=True).clamp(min=1e-12))
 
 
-def lcao_twobody_bwd(B, NG, g, d_lw, E, C, NL, valence, dB, d_g, stream):
+def lcao_twobody_bwd(B, NG, g, d_lw, E, C, NL, valence, compact, dB, d_g, stream):
     PA, PV, gA, gV = _tw_load(B, NG, g, E, C, NL, valence)
     p = (1 + gA) * PA + (1 + gV) * PV
     nrm = p.norm(dim=1, keepdim=True)
@@ -390,11 +395,12 @@ def lcao_twobody_bwd(B, NG, g, d_lw, E, C, NL, valence, dB, d_g, stream):
     dl = view(d_lw, E, C)
     coef = torch.where(nrm > 1e-12, (p * dl).sum(1, keepdim=True) * inv * inv, torch.zeros_like(nrm))
     dp = (dl - coef * p) * inv
-    out = view(dB, E, NG * C).reshape(E, NG, C)
+    NGo, NLo = ((1 + valence), 1) if compact else (NG, NL)
+    out = view(dB, E, NGo * C).reshape(E, NGo, C)
     dPA = (1 + gA) * dp
-    out[:, :NL] = dPA.unsqueeze(1)
+    out[:, :NLo] = dPA.unsqueeze(1)
     if valence:
-        out[:, NL] = (1 + gV) * dp - dPA
+        out[:, NLo] = (1 + gV) * dp - dPA
         dg = view(d_g, E, 2 * C)
         dg[:, :C] = dp * PA
         dg[:, C:] = dp * PV

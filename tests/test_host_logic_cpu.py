@@ -79,6 +79,31 @@ def test_autograd_forces_match_reference(monkeypatch):
     _check_autograd_forces(gold, model, out, 2e-5, 2e-4)
 
 
+@pytest.mark.parametrize("name", ["qm9_valence_ext_2perorb", "crystal_autograd_forces"])
+def test_op_by_op_path_equals_single_node_path(name, monkeypatch):
+    """LCAOInteraction as one autograd node (ops.interaction_layer) vs one node per kernel: same kernels, same
+    order -> identical energies and gradients."""
+    res = []
+    for fused in (True, False):
+        cpu_abi.install(monkeypatch)
+        gold = load_golden(name)
+        model = LCAONet(**gold["kwargs"])
+        model.load_state_dict(gold["state_dict"], strict=True)
+        for layer in model.int_layers:
+            layer.fused_node = fused
+        out = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+        energy = out[0] if isinstance(out, tuple) else out
+        (energy**2).mean().backward()
+        res.append((out, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (o1, g1), (o2, g2) = res
+    if isinstance(o1, tuple):
+        assert rel_l2(o1[1], o2[1]) < 1e-6
+        o1, o2 = o1[0], o2[0]
+    assert rel_l2(o1, o2) < 1e-6 and g1.keys() == g2.keys()
+    for n in g1:
+        assert rel_l2(g1[n], g2[n]) < 1e-5, n
+
+
 def test_same_seed_gives_reference_initialisation():
     gold = load_golden("qm9_valence_ext_2perorb")
     torch.manual_seed(0)
