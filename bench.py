@@ -119,6 +119,42 @@ def cpu_oracle_step_time(n_mol: int, reps: int, threads: int | None = None):
     return min(times[1:]), times
 
 
+def gpu_oracle_step_time(n_mol: int, reps: int, dev):
+    """The reference algorithm (oracle port: materialises the (T,O,C) tensors like lcaonet.py:173-189) run by
+    PyTorch eager ON THE GPU — the denominator of BASELINE.json's ">= 20x reference-PyTorch-on-B200" target.
+    Baseline only; halves the batch on out-of-memory."""
+    from lcaonet_b200 import LCAONet
+    from lcaonet_b200.synth import qm9_like_batch
+    from oracle import lcao_oracle as O
+
+    cfg = dict(emb_size=128, emb_size_coeff=128, emb_size_conv=128, out_size=1, n_interaction=3, n_per_orb=1, cutoff=6.0,
+               rbf_type="hydrogen", cutoff_net="envelope", max_z=36, min_orb=None, max_orb=None, elec_to_node=True,
+               add_valence=False, extend_orb=False, is_extensive=True, regress_forces=False, direct_forces=True)
+    cfg.update(MODEL_KW)
+    torch.manual_seed(0)
+    sd = {k: v.to(dev) for k, v in LCAONet(**MODEL_KW).state_dict().items()}
+    while n_mol >= 8:
+        try:
+            p = O.cast_params(sd, torch.float32, requires_grad=True)
+            g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in qm9_like_batch(n_mol, seed=0, cutoff=5.0).items()}
+            times = []
+            for _ in range(reps + 1):
+                for v in p.values():
+                    v.grad = None
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = O.forward(p, cfg, g, training=True)
+                torch.nn.functional.mse_loss(out, g["y"]).backward()
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            return n_mol, min(times[1:])
+        except torch.OutOfMemoryError:
+            del p, g
+            torch.cuda.empty_cache()
+            n_mol //= 2
+    return 0, float("inf")
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU algorithm (oracle port; the reference tree itself is
     Python and does not travel to the GPU box) timed on the host cores, same metric and config."""
@@ -242,8 +278,16 @@ def run_ours(args):
         sampler.start()
     l0 = _lib.launch_count()
     ms_dev = timed(lambda: step(GraphClone(resident), y_dev), args.steps)
-    host_enqueue_ms = host_ms[0]
     launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    # CPU time to enqueue ONE step into an empty stream (median of 5): if it approaches ms_per_step the host is the limit
+    hs = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(GraphClone(resident), y_dev)
+        hs.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    host_enqueue_ms = sorted(hs)[2]
 
     # ---- end-to-end timing (e2e): pinned host batch -> H2D -> step -> D2H loss
     def e2e_step():
@@ -303,18 +347,27 @@ def run_ours(args):
             best, _ = cpu_oracle_step_time(32, reps=args.cpu_reps, threads=os.cpu_count())
             cpu = {"value": 32 / best, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"32 QM9-shape molecules (BASELINE configs[0]), fwd+bwd, best of {args.cpu_reps}, oracle port of the reference"}
+        ref_gpu = None
+        sek = model.side_effect_keys
+        if world == 1 and args.ref_gpu_mols > 0:
+            torch.cuda.empty_cache()
+            n_ref, t_ref = gpu_oracle_step_time(args.ref_gpu_mols, 3, dev)
+            if n_ref:
+                ref_gpu = {"value": n_ref / t_ref, "unit": "molecules/s", "kind": "oracle port, PyTorch eager on cuda:0 (FP32)",
+                           "sample": f"{n_ref} QM9-shape molecules, fwd+bwd, best of 3"}
         line = {
             "metric": "molecules/sec fwd+bwd (QM9-shape)", "value": total_mols / (ms_dev * 1e-3), "unit": "molecules/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(m=args.mol_per_gpu), "N": sizes["N"], "E": sizes["E"], "T": sizes["T"],
-                       "gemm_mode": ops.get_gemm_mode(), "side_effect_keys": model.side_effect_keys,
+                       "gemm_mode": ops.get_gemm_mode(), "side_effect_keys": sek,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": total_mols / (ms_e2e * 1e-3), "unit": "molecules/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "roofline": roofline,
             "kernels": kernels if os.environ.get("LCAO_BENCH_SHAPES") else kernels[:12], "cpu_baseline": cpu,
+            "reference_on_gpu": ref_gpu,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -386,9 +439,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mol-per-gpu", type=int, default=1024)
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--gemm", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="dense-layer arithmetic: tf32x3 = tcgen05 3xTF32 split (FP32-equivalent, parity-tested), fp32 = CUDA cores")
     ap.add_argument("--no-side-effect-keys", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--ref-gpu-mols", type=int, default=128,
+                    help="also time the oracle port with PyTorch eager on the GPU at this batch (0 = skip)")
     ap.add_argument("--profile-host", action="store_true", help="cProfile of 5 steps (host side) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":

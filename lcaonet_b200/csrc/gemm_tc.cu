@@ -715,9 +715,10 @@ bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* d
          wgrad_smem(Kx, 1, 2, 2) <= kMaxSmem;
 }
 
-// CTAs of the weight-gradient kernel: at least 1024 rows each (the per-CTA cost is the 64 KB partial tile)
+// CTAs of the weight-gradient kernel: at least 128 rows (4 pipeline chunks) each; the per-CTA cost is one 64 KB
+// partial tile, the per-chunk cost ~1.5 us of transform latency, so small M wants many CTAs
 static unsigned wgrad_grid(int64_t M) {
-  const int64_t want = (M + 1023) / 1024;
+  const int64_t want = (M + 127) / 128;
   return (unsigned)(want < 1 ? 1 : want < num_sms() ? want : num_sms());
 }
 // floats of scratch lcao_tc_wgrad needs
