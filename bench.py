@@ -135,7 +135,7 @@ def gpu_oracle_step_time(n_mol: int, reps: int, dev):
     sd = {k: v.to(dev) for k, v in LCAONet(**MODEL_KW).state_dict().items()}
     while n_mol >= 8:
         try:
-            p = O.cast_params(sd, torch.float32, requires_grad=True)
+            p = O.cast_params(sd, torch.float32, device=dev, requires_grad=True)
             g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in qm9_like_batch(n_mol, seed=0, cutoff=5.0).items()}
             times = []
             for _ in range(reps + 1):
