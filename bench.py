@@ -225,14 +225,27 @@ def run_ours(args):
     _lib.load()  # fail loudly when the CUDA library is missing
     ops.set_gemm_mode(args.gemm)
 
+    # --workload: the headline config (BASELINE.json configs[1]) or one of the other named configs (not bench lines:
+    # used to report their throughput in profiles/)
+    model_kw, workload, make_batch = MODEL_KW, WORKLOAD.format(m=args.mol_per_gpu), None
+    if args.workload == "valence":  # configs[2]
+        model_kw = dict(MODEL_KW, add_valence=True, extend_orb=True, n_per_orb=2, max_z=36)
+        workload = (f"QM9-shape synthetic, {args.mol_per_gpu} molecules/GPU, LCAONet add_valence extend_orb n_per_orb=2 "
+                    "(16 orbitals, C'=256), energy MSE training step")
+    elif args.workload == "crystal":  # configs[3]: energy + autograd forces (first order), energy-loss gradients
+        from lcaonet_b200.synth import crystal_like_batch
+        model_kw = dict(cutoff=6.0, cutoff_net="polynomial", regress_forces=True, direct_forces=False)
+        workload = (f"periodic crystals, {args.mol_per_gpu} cells/GPU x 64 atoms, cutoff 6.0 (~49 neighbours/atom), energy + "
+                    "autograd forces + energy-loss gradients (units = cells)")
+        make_batch = lambda seed: crystal_like_batch(args.mol_per_gpu, seed=seed, cutoff=6.0)  # noqa: E731
     torch.manual_seed(0)
-    model = LCAONet(**MODEL_KW).to(dev).train()
+    model = LCAONet(**model_kw).to(dev).train()
     model.side_effect_keys = not args.no_side_effect_keys
     broadcast_module(model)
     bucket = FlatGradBucket(model)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
 
-    host = qm9_like_batch(args.mol_per_gpu, seed=1000 + rank, cutoff=5.0).pin_memory()
+    host = (make_batch(1000 + rank) if make_batch else qm9_like_batch(args.mol_per_gpu, seed=1000 + rank, cutoff=5.0)).pin_memory()
     sizes = graph_sizes(host)
     resident = host.to(dev)
     y_dev = resident["y"]
@@ -241,6 +254,8 @@ def run_ours(args):
     def step(batch, y):
         bucket.zero()
         out = model(batch)
+        if isinstance(out, tuple):  # (energy, forces): the forces are evaluated, the loss is on the energy
+            out = out[0]
         loss = torch.nn.functional.mse_loss(out, y)
         loss.backward()
         bucket.all_reduce_mean()
@@ -349,7 +364,7 @@ def run_ours(args):
                    "sample": f"32 QM9-shape molecules (BASELINE configs[0]), fwd+bwd, best of {args.cpu_reps}, oracle port of the reference"}
         ref_gpu = None
         sek = model.side_effect_keys
-        if world == 1 and args.ref_gpu_mols > 0:
+        if world == 1 and args.ref_gpu_mols > 0 and args.workload == "qm9":
             torch.cuda.empty_cache()
             n_ref, t_ref = gpu_oracle_step_time(args.ref_gpu_mols, 3, dev)
             if n_ref:
@@ -360,7 +375,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(m=args.mol_per_gpu), "N": sizes["N"], "E": sizes["E"], "T": sizes["T"],
+            "config": {"workload": workload, "N": sizes["N"], "E": sizes["E"], "T": sizes["T"],
                        "gemm_mode": ops.get_gemm_mode(), "side_effect_keys": sek,
                        "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": total_mols / (ms_e2e * 1e-3), "unit": "molecules/s", "ms_per_step": ms_e2e,
@@ -439,6 +454,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mol-per-gpu", type=int, default=1024)
+    ap.add_argument("--workload", default="qm9", choices=["qm9", "valence", "crystal"],
+                    help="qm9 = BASELINE.json configs[1] (the bench line); valence / crystal = configs[2] / configs[3]")
     ap.add_argument("--gemm", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="dense-layer arithmetic: tf32x3 = tcgen05 3xTF32 split (FP32-equivalent, parity-tested), fp32 = CUDA cores")
     ap.add_argument("--no-side-effect-keys", action="store_true")

@@ -176,6 +176,10 @@ int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, int64_t ldb,
  * scale_r = 1 (mean=0) or 1/max(count,1) (mean=1).  Deterministic, no atomics. */
 int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int64_t ldy, const int32_t* ptr,
                      const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo, void* stream);
+/* backward of the message sum  agg[s] = sum_{e in out(s)} bw[e] * h[e],  h = SiLU(pre_h)  (lcaonet.py:207-214):
+ *   d_bw[e,:] = d_agg[src[e],:] * h[e,:] ;  d_pre_h[e,:] = d_agg[src[e],:] * bw[e,:] * SiLU'(pre_h[e,:]) */
+int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
+                 const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream);
 /* out[i,:] = table[idx[i],:] * (mul ? mul[i,:] : 1)   (idx int64 or int32 chosen by idx_is64) */
 int lcao_gather_rows(const float* table, int64_t ldt, const void* idx, int32_t idx_is64, const float* mul, int64_t ldm,
                      int64_t n, int32_t W, float* out, int64_t ldo, void* stream);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lcao_twobody_bwd": [_p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
     "lcao_edge_pair_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p],
     "lcao_segment_sum": [_p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p],
+    "lcao_msg_bwd": [_p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _p],
     "lcao_gather_rows": [_p, _i64, _p, _i32, _p, _i64, _i64, _i32, _p, _i64, _p],
     "lcao_reduce_by_key": [_p, _i64, _p, _p, _i64, _i64, _i32, _p, _p],
     "lcao_linear_fwd": [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p],

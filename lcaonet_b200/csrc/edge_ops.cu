@@ -323,6 +323,25 @@ __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float
   st4(dH + i * ldd + c, g);
 }
 
+// backward of  agg[s] = sum_{e in out(s)} bw[e] * h[e]  with  h = SiLU(pre_h):
+//   d_bw[e] = d_agg[src[e]] * h[e] ;  d_pre_h[e] = d_agg[src[e]] * bw[e] * SiLU'(pre_h[e])
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
+    const float* __restrict__ d_agg, int64_t lda, const int32_t* __restrict__ src32, const float* __restrict__ h,
+    const float* __restrict__ bw, const float* __restrict__ pre_h, int64_t E, int C, float* __restrict__ d_bw,
+    float* __restrict__ d_pre_h) {
+  const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  const float* pa = d_agg + src32[e] * lda;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 g = ldg4(pa + c), hv = ldg4(h + e * (int64_t)C + c), b = ldg4(bw + e * (int64_t)C + c);
+    const float4 p = ldg4(pre_h + e * (int64_t)C + c);
+    st4(d_bw + e * (int64_t)C + c, f4_mul(g, hv));
+    st4(d_pre_h + e * (int64_t)C + c,
+        make_float4(g.x * b.x * silu_gradf(p.x), g.y * b.y * silu_gradf(p.y), g.z * b.z * silu_gradf(p.z), g.w * b.w * silu_gradf(p.w)));
+  }
+}
+
 __global__ void k_sigmoid_rows(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int64_t M,
                                int C4) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -489,6 +508,19 @@ extern "C" int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_
   LCAO_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out),
                "lcao_sigmoid_rows: need C and strides multiples of 4, 16-byte aligned buffers");
   k_sigmoid_rows<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, M, C / 4);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
+                            const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream) {
+  if (E == 0) return LCAO_OK;
+  LCAO_REQUIRE(d_agg && src32 && h && bw && pre_h && d_bw && d_pre_h, "lcao_msg_bwd: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && aligned16(d_agg) && aligned16(h) && aligned16(bw) && aligned16(pre_h) &&
+                   aligned16(d_bw) && aligned16(d_pre_h),
+               "lcao_msg_bwd: need C, lda multiples of 4 and 16-byte aligned buffers");
+  k_msg_bwd<<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw,
+                                                                                                pre_h, E, C, d_bw, d_pre_h);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -223,23 +223,40 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   }
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
 
-  // ---- resident B operand (the layer's weight), split hi/lo once per CTA, by all threads
-  for (int idx = threadIdx.x; idx < g.Nb * (g.Kc / 4); idx += kRowsThreads) {
-    float4 w;
-    int n, kg;
-    if (!g.b_trans) {
-      n = idx / (g.Kc / 4); kg = idx - n * (g.Kc / 4);
-      w = ldg4(g.W + (int64_t)n * g.ldw + kg * 4);
-    } else {  // W is (Kc, Nb): contraction group kg = 4 rows of W, one output column n
-      kg = idx / g.Nb; n = idx - kg * g.Nb;
-      w = make_float4(__ldg(g.W + (int64_t)(kg * 4 + 0) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 1) * g.ldw + n),
-                      __ldg(g.W + (int64_t)(kg * 4 + 2) * g.ldw + n), __ldg(g.W + (int64_t)(kg * 4 + 3) * g.ldw + n));
+  // ---- resident B operand (the layer's weight), split hi/lo once per CTA, by all threads; 4 loads in flight per
+  //      thread (the weights come from L2 / HBM with ~1 us latency: a dependent loop would cost ~10 us per launch)
+  {
+    const int kq = g.Kc / 4, total = g.Nb * kq;
+    for (int base = 0; base < total; base += 4 * kRowsThreads) {
+      float4 w[4];
+      int n[4], kg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * kRowsThreads + (int)threadIdx.x;
+        w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        n[u] = -1;
+        if (idx < total) {
+          if (!g.b_trans) {
+            n[u] = idx / kq; kg[u] = idx - n[u] * kq;
+            w[u] = ldg4(g.W + (int64_t)n[u] * g.ldw + kg[u] * 4);
+          } else {  // W is (Kc, Nb): contraction group kg = 4 rows of W, one output column n
+            kg[u] = idx / g.Nb; n[u] = idx - kg[u] * g.Nb;
+            w[u] = make_float4(__ldg(g.W + (int64_t)(kg[u] * 4 + 0) * g.ldw + n[u]), __ldg(g.W + (int64_t)(kg[u] * 4 + 1) * g.ldw + n[u]),
+                               __ldg(g.W + (int64_t)(kg[u] * 4 + 2) * g.ldw + n[u]), __ldg(g.W + (int64_t)(kg[u] * 4 + 3) * g.ldw + n[u]));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (n[u] >= 0) {
+          float4 hi, lo;
+          split4(w[u], hi, lo);
+          const uint32_t off = (kg[u] >> 3) * blockB + sw128_off(n[u], kg[u] & 7);
+          *reinterpret_cast<float4*>(sB + off) = hi;
+          *reinterpret_cast<float4*>(sB + halfB + off) = lo;
+        }
+      }
     }
-    float4 hi, lo;
-    split4(w, hi, lo);
-    const uint32_t off = (kg >> 3) * blockB + sw128_off(n, kg & 7);
-    *reinterpret_cast<float4*>(sB + off) = hi;
-    *reinterpret_cast<float4*>(sB + halfB + off) = lo;
   }
   fence_proxy_async();
   tc_fence_before();

@@ -513,13 +513,11 @@ class _InteractionLayer(torch.autograd.Function):
         d_agg = torch.empty(N, C, device=dev)
         _lin_dgrad(d_out, H, N, w_o, d_agg, C, 0, st)
         # agg[s] = sum_{e in out(s)} bw[e] * h[e]
-        d_bw, d_h = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
-        _call("lcao_gather_rows", ptr(d_agg), C, ptr(gi.src32), 0, ptr(h), C, E, C, ptr(d_bw), C, st)
-        _call("lcao_gather_rows", ptr(d_agg), C, ptr(gi.src32), 0, ptr(bw), C, E, C, ptr(d_h), C, st)
+        d_bw, d_preh = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
+        _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), ptr(h), ptr(bw), ptr(pre_h), E, C, ptr(d_bw), ptr(d_preh), st)
         # h = silu(f_node.2(a1)) ; a1 = silu(u_a[s] + u_b[t] + b1)
-        d_preh = _act_bwd(d_h, pre_h, E, C, st)
         dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st)
-        d_a1 = d_h  # reuse
+        d_a1 = torch.empty(E, C, device=dev)
         _lin_dgrad(d_preh, C, E, w_2, d_a1, C, 0, st)
         d_prea = _act_bwd(d_a1, pre_a, E, C, st)
         d_u = torch.empty(N, 2 * C, device=dev)

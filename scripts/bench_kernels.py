@@ -34,6 +34,25 @@ def timeit(fn, reps=5, warm=2):
     return ts[len(ts) // 2]
 
 
+def gemm_small():
+    """latency of the dense-layer kernels at the node / table sized shapes of one step"""
+    P, st = ops.ptr, ops.stream_ptr
+    for M, K, N in ((128, 128, 128), (2048, 128, 128), (10952, 128, 128), (18470, 128, 128), (18470, 128, 256), (252798, 128, 128)):
+        x = torch.randn(M, K, device=DEV)
+        w = torch.randn(N, K, device=DEV) / K**0.5
+        dy = torch.randn(M, N, device=DEV)
+        y, dx = torch.empty(M, N, device=DEV), torch.empty(M, K, device=DEV)
+        dw = torch.zeros(N, K, device=DEV)
+        for mode in ("fp32", "tf32x3"):
+            m = ops.GEMM_MODES[mode]
+            n_scr = int(_lib.load().lcao_linear_bwd_scratch(P(dy), N, None, 0, 0, None, P(x), K, None, 0, M, K, N, m))
+            scr = torch.empty(max(n_scr, 1), device=DEV)
+            t_f = timeit(lambda: ops._call("lcao_linear_fwd", P(x), K, P(w), None, P(y), N, None, N, M, K, N, 0, m, st()), reps=9)
+            t_d = timeit(lambda: ops._call("lcao_linear_dgrad", P(dy), N, None, 0, 0, P(w), P(dx), K, M, K, N, 0, m, None, st()), reps=9)
+            t_w = timeit(lambda: ops._call("lcao_linear_wgrad", P(dy), N, None, 0, 0, P(x), K, P(dw), None, M, K, N, m, P(scr), st()), reps=9)
+            print(f"gemm {mode:7s} M={M:7d} K={K} N={N}: fwd {t_f*1e3:7.1f} us | dgrad {t_d*1e3:7.1f} us | wgrad {t_w*1e3:7.1f} us", flush=True)
+
+
 def gemm():
     M, K, N = 2_022_384, 128, 128
     x = torch.randn(M, K, device=DEV)
@@ -105,5 +124,7 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
         gemm()
+    if what in ("gemm_small", "all"):
+        gemm_small()
     if what in ("edge", "all"):
         edge()

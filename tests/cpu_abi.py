@@ -437,6 +437,15 @@ def lcao_segment_sum(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo, stream):
         O[r] = seg / max(int(p[r + 1] - p[r]), 1) if mean else seg
 
 
+def lcao_msg_bwd(d_agg, lda, src32, h, bw, pre_h, E, C, d_bw, d_pre_h, stream):
+    s = view(src32, E, dtype=I32).long()
+    g = view(d_agg, int(s.max()) + 1, C, ld=lda)[s]
+    p = view(pre_h, E, C)
+    sg = torch.sigmoid(p)
+    view(d_bw, E, C).copy_(g * view(h, E, C))
+    view(d_pre_h, E, C).copy_(g * view(bw, E, C) * (sg * (1 + p * (1 - sg))))
+
+
 def lcao_gather_rows(table, ldt, idx, is64, mul, ldm, n, W, out, ldo, stream):
     i = view(idx, n, dtype=I64 if is64 else I32).long()
     T = view(table, int(i.max()) + 1, W, ld=ldt)

@@ -69,7 +69,7 @@ def test_shard_range_partitions_everything():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gradient_allreduce_matches_single_process():
+def test_two_rank_gradient_allreduce_matches_single_process(monkeypatch):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -85,7 +85,8 @@ def test_two_rank_gradient_allreduce_matches_single_process():
     assert torch.equal(g0, g1)          # every rank holds the same averaged gradient
     # single-process reference: mean over ranks of the per-shard losses, rank 0's initial weights
     from lcaonet_b200 import LCAONet
-    _install_emulator()
+    from tests import cpu_abi
+    cpu_abi.install(monkeypatch)  # (undone at test exit; the workers patched their own processes)
     torch.manual_seed(0)
     model = LCAONet(**KW).train()
     loss = sum(_shard_loss(model, r, world) for r in range(world)) / world
