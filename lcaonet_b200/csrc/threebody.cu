@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
     float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
+  constexpr int RI = FORCES ? 1 : kRI;  // in-edges per warp at a time (the forces variant needs the registers)
   const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
   // per-warp scratch, pair (rr, jj) at slot rr*8 + jj: a_l = w Y_l | norm-path flag | (forces) w Y'_l
   __shared__ __align__(16) float s_a[kBwdWarps][16 * 4];
@@ -274,18 +275,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
   }
   float* sa = s_a[warp];
   float* sf = s_f[warp];
-  const int jj_mine = lane & 7, rr_mine = (lane >> 3) & 1;  // coefficient duty: pair (out j0+jj, in i0+rr); lanes >= 16 mirror
+  const int jj_mine = lane & 7, rr_mine = (lane >> 3) & (RI - 1);  // coefficient duty: pair (out j0+jj, in i0+rr); lanes >= 16 mirror
   const int jsub = bfly8_index(lane);
   bool okc[V4];
 #pragma unroll
   for (int v = 0; v < V4; ++v) okc[v] = (lane + 32 * v) * 4 < C;
 
-  for (int i0 = warp * kRI; i0 < dI; i0 += kBwdWarps * kRI) {
-    float4 gb[kRI][NL][V4], dacc[kRI][NL][V4], gt[kRI][V4];
-    float h[kRI][NP];
-    int ep[kRI];
+  for (int i0 = warp * RI; i0 < dI; i0 += kBwdWarps * RI) {
+    float4 gb[RI][NL][V4], dacc[RI][NL][V4], gt[RI][V4];
+    float h[RI][NP];
+    int ep[RI];
 #pragma unroll
-    for (int rr = 0; rr < kRI; ++rr) {
+    for (int rr = 0; rr < RI; ++rr) {
       const int pos = ib + min(i0 + rr, dI - 1);
       ep[rr] = in_edge[pos];
       const int k = in_src[pos];
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
       for (int p = 0; p < NP; ++p) h[rr][p] = 0.f;
     }
     // this lane's in-edge for the coefficient duty
-    const int epc = rr_mine == 0 ? ep[0] : ep[1];
+    const int epc = ep[rr_mine];
     const bool in_live = i0 + rr_mine < dI;
     const float vx = unit[3 * (int64_t)epc], vy = unit[3 * (int64_t)epc + 1], vz = unit[3 * (int64_t)epc + 2];
     double g[NP];
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
         const float fl = (live && nrm > kEps) ? 1.f : 0.f;
         const float4 a = make_float4(ww * Y[0], ww * Y[1], ww * Y[2], ww * Y[3]);
         __syncwarp();
-        if (lane < 16) {
+        if (lane < 8 * RI) {
           st4(sa + lane * 4, a);
           sf[lane] = fl;
           if constexpr (FORCES) {
@@ -345,11 +346,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
 #pragma unroll
           for (int v = 0; v < V4; ++v) gr[jj][v] = okc[v] ? ldg4(d_tbw + (int64_t)e * C + (lane + 32 * v) * 4) : zero4();
         }
-        float part[kRI][8], part2[FORCES ? kRI : 1][8];
+        float part[RI][8], part2[FORCES ? RI : 1][8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
-          for (int rr = 0; rr < kRI; ++rr) {
+          for (int rr = 0; rr < RI; ++rr) {
             const float4 ar = lds4(sa + (rr * 8 + jj) * 4);
             float4 ar2;
             if constexpr (FORCES) ar2 = lds4(s_a2[warp] + (rr * 8 + jj) * 4);
@@ -378,9 +379,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
           }
         }
         // ---- per pair scalars: the quad `jsub` of the warp finishes pair (j0 + jsub, i0 + rr)
-        float dotv[kRI], dot2v[FORCES ? kRI : 1];
+        float dotv[RI], dot2v[FORCES ? RI : 1];
 #pragma unroll
-        for (int rr = 0; rr < kRI; ++rr) {
+        for (int rr = 0; rr < RI; ++rr) {
           dotv[rr] = bfly8(part[rr], lane);
           if constexpr (FORCES) dot2v[rr] = bfly8(part2[rr], lane);
           const int slot = rr * 8 + jsub;
@@ -398,10 +399,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
           // butterfly element jj (lane bits 4,3,2 = bits 2,1,0 of jj).
           const int srcl = (((jj_mine >> 2) & 1) << 4) | (((jj_mine >> 1) & 1) << 3) | ((jj_mine & 1) << 2);
 #pragma unroll
-          for (int rr = 0; rr < kRI; ++rr) {
+          for (int rr = 0; rr < RI; ++rr) {
             const float dt = __shfl_sync(0xffffffffu, dotv[rr], srcl);
             const float dt2 = __shfl_sync(0xffffffffu, dot2v[rr], srcl);
-            if (lane < 16 && rr_mine == rr && live) {
+            if (lane < 8 * RI && rr_mine == rr && live) {
               float dY[4];
               sph_harm_grad<NL>(cc, dY);
               const float corr = (float)bilin_form<NL>(g, dY, Y);
@@ -432,12 +433,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
         ks_y += __shfl_xor_sync(0xffffffffu, ks_y, o);
         ks_z += __shfl_xor_sync(0xffffffffu, ks_z, o);
       }
-      if (lane < 16 && jj_mine == 0 && in_live) {
+      if (lane < 8 * RI && jj_mine == 0 && in_live) {
         du_ks[3 * (int64_t)epc] = ks_x; du_ks[3 * (int64_t)epc + 1] = ks_y; du_ks[3 * (int64_t)epc + 2] = ks_z;
       }
     }
 #pragma unroll
-    for (int rr = 0; rr < kRI; ++rr) {
+    for (int rr = 0; rr < RI; ++rr) {
       if (i0 + rr >= dI) continue;  // warp-uniform
 #pragma unroll
       for (int p = 0; p < NP; ++p) {  // h was accumulated by one lane quad per out-edge slot: add the 8 slots
