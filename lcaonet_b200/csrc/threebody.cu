@@ -33,7 +33,7 @@ namespace {
 constexpr int kFwdWarps = 2;   // forward CTA: 2 warps x 8 out-edges per pass
 constexpr int kBwdWarps = 4;   // backward CTA: 4 warps x 2 in-edges per pass
 constexpr int kR = 8;          // forward: out-edge accumulators per warp
-constexpr int kRI = 2;         // backward: in-edges per warp at a time
+constexpr int kRI = 1;         // backward: in-edges per warp at a time (1 measured faster than 2: 128 vs 168 registers)
 constexpr int kIB = 4;         // forward: in-edges per coefficient batch (kR * kIB = 32 pairs = one per lane)
 constexpr int kJS = 64;        // backward (forces): out-edges whose d_unit partials live in shared memory
 constexpr float kEps = 1e-12f; // F.normalize eps (lcaonet.py:184)
@@ -96,6 +96,8 @@ __device__ __forceinline__ float4 sigmoid4(float4 x) {
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float comp4(const float4& a, int l) { return l == 0 ? a.x : l == 1 ? a.y : l == 2 ? a.z : a.w; }
 
+// (Packed FP32 pairs — fma.rn.f32x2 / FFMA2 — were tried for the FMA blocks: same FP32 pipe rate (measured 36.8 vs
+// 36.2 TFMA/s, scripts/micro/ffma2.cu) and the forward kernel ran 2x SLOWER with them; see profiles/r01_notes.md.)
 // Sum 8 per-lane partials over the 32 lanes with 9 shuffles; every lane ends up with the total of
 // element  4*bit4(lane) + 2*bit3(lane) + bit2(lane).
 __device__ __forceinline__ float bfly8(const float (&p)[8], int lane) {
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
 //   FORCES: dc = Gt[j,:] . sum_l (w Y'_l) GB[i,l,:] - w^2 dot sum_l Y'_l (G Y)_l ;  d unit[e_j] += dc unit[e_i] and v.v.
 // Same clamping convention as the forward: dead slots read a valid row and carry zero coefficients.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int V4, bool FORCES>
+template <int NL, int V4, bool FORCES, int RI>
 __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
@@ -239,7 +241,6 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
     float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
-  constexpr int RI = FORCES ? 1 : kRI;  // in-edges per warp at a time (the forces variant needs the registers)
   const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
   // per-warp scratch, pair (rr, jj) at slot rr*8 + jj: a_l = w Y_l | norm-path flag | (forces) w Y'_l
   __shared__ __align__(16) float s_a[kBwdWarps][16 * 4];
@@ -493,6 +494,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
   }
 }
 
+// tuning knob read once from the environment (benchmark sweeps); falls back to the default when out of range
+int tile_in(const char* env, int dflt, int lo, int hi) {
+  const char* s = getenv(env);
+  const int v = s ? atoi(s) : dflt;
+  return (v < lo || v > hi) ? dflt : v;
+}
+
 }  // namespace
 
 #define TB_DISPATCH(NL, V4, CALL)   \
@@ -542,15 +550,20 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   cudaStream_t st = (cudaStream_t)stream;
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
+  static const int ri = tile_in("LCAO_TB_RI", kRI, 1, 2);  // in-edges per warp at a time (energy path; forces: 1)
 #define CALL(nl, v4)                                                                                                   \
   if (forces)                                                                                                          \
-    k_threebody_bwd<nl, v4, true><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
-                                                                          in_src, out_ptr, out_edge, C, d_tbw, dP, dB, \
-                                                                          q, d_unit_ks, d_unit_st);                    \
+    k_threebody_bwd<nl, v4, true, 1><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,     \
+                                                                             in_edge, in_src, out_ptr, out_edge, C,    \
+                                                                             d_tbw, dP, dB, q, d_unit_ks, d_unit_st);  \
+  else if (ri == 1)                                                                                                    \
+    k_threebody_bwd<nl, v4, false, 1><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,    \
+                                                                              in_edge, in_src, out_ptr, out_edge, C,   \
+                                                                              d_tbw, dP, dB, q, nullptr, nullptr);     \
   else                                                                                                                 \
-    k_threebody_bwd<nl, v4, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,       \
-                                                                           in_edge, in_src, out_ptr, out_edge, C,      \
-                                                                           d_tbw, dP, dB, q, nullptr, nullptr)
+    k_threebody_bwd<nl, v4, false, 2><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,    \
+                                                                              in_edge, in_src, out_ptr, out_edge, C,   \
+                                                                              d_tbw, dP, dB, q, nullptr, nullptr)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();
