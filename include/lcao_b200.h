@@ -87,6 +87,23 @@ int lcao_triplets_fill(const int32_t* src32, const int32_t* in_ptr, const int32_
 /* histogram of small integer keys (pair / species counts for the BatchNorm statistics) */
 int lcao_histogram(const int64_t* keys, int64_t n, int64_t nb, float* counts, void* stream);
 
+/* ---- neighbour list under PBC (data/convert.py:103-172 atoms2graphdata; ase.neighborlist.neighbor_list) -------- */
+/* Two phases because E is data dependent.  Atoms of one structure are contiguous: graph_ptr (B+1) int32, batch (N)
+ * int64 (PyG convention), lattice (B,3,3) rows = cell vectors, pbc (B,3) int32 flags.
+ * count[i] = number of (j, image) within `cutoff` of atom i (NOT truncated).  The caller clamps to max_neighbors,
+ * marks structures with no neighbour at all as `fallback` (fully linked graph, convert.py:154-157: count = n_atoms-1),
+ * and scans into out_ptr (N+1, int64). */
+int lcao_neighbor_count(const float* pos, const int64_t* batch, const int32_t* graph_ptr, const float* lattice,
+                        const int32_t* pbc, int64_t N, double cutoff, int32_t* count, void* stream);
+/* edge_index (2,E) int64 [centre, neighbour] grouped by centre ascending, each centre's neighbours ordered by
+ * (distance, neighbour id, image) ascending and truncated to max_neighbors; edge_shift (E,3) = integer image offsets
+ * as float32.  status (1 int32, zero-initialised by the caller) is set to 1 if a centre had more than 2048
+ * neighbours within the cutoff (not supported). */
+int lcao_neighbor_fill(const float* pos, const int64_t* batch, const int32_t* graph_ptr, const float* lattice,
+                       const int32_t* pbc, const int32_t* fallback, const int64_t* out_ptr, int64_t N, int64_t E,
+                       double cutoff, int32_t max_neighbors, int64_t* edge_index, float* edge_shift, int32_t* status,
+                       void* stream);
+
 /* ---- geometry + radial basis (base.py:27-43, rbf.py:92-103,129-142, cutoff.py:32-67) --------- */
 /* dist (E), unit (E,3), rb (E,O), optional drb (E,O) = d rb / d r (for autograd forces). */
 int lcao_geom_basis_fwd(const float* pos, const float* shift, const float* lattice, const int64_t* batch,

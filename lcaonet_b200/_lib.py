@@ -37,6 +37,8 @@ SIGNATURES = {
     "lcao_graph_index_build": [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "lcao_triplets_fill": [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p],
     "lcao_histogram": [_p, _i64, _i64, _p, _p],
+    "lcao_neighbor_count": [_p, _p, _p, _p, _p, _i64, C.c_double, _p, _p],
+    "lcao_neighbor_fill": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, C.c_double, _i32, _p, _p, _p, _p],
     "lcao_geom_basis_fwd": [_p, _p, _p, _p, _p, _p, _i64, C.POINTER(BasisSpec), _p, _p, _p, _p, _p],
     "lcao_geom_basis_bwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p],
     "lcao_coeff_contract_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p],

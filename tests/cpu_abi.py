@@ -121,6 +121,33 @@ def lcao_triplets_fill(src32, in_ptr, in_edge, tri_ptr, E, tri_k, e_ks, e_st, un
             view(cos_out, T).copy_((u[est] * u[eks]).sum(-1))
 
 
+def _nl_inputs(pos, batch, graph_ptr, lattice, pbc, N):
+    b = view(batch, N, dtype=I64)
+    B = int(b.max()) + 1
+    return (view(pos, N, 3).numpy(), view(graph_ptr, B + 1, dtype=I32).numpy(), view(lattice, B * 3, 3).reshape(B, 3, 3).numpy(),
+            view(pbc, B, 3, dtype=I32).numpy(), B)
+
+
+def lcao_neighbor_count(pos, batch, graph_ptr, lattice, pbc, N, cutoff, count, stream):
+    from oracle import neighbor_oracle as NO
+    P, gp, lat, pb, B = _nl_inputs(pos, batch, graph_ptr, lattice, pbc, N)
+    out = view(count, N, dtype=I32)
+    for g in range(B):
+        lo, hi = int(gp[g]), int(gp[g + 1])
+        out[lo:hi] = torch.from_numpy(NO.raw_counts(P[lo:hi], lat[g], [bool(x) for x in pb[g]], cutoff)).to(I32)
+
+
+def lcao_neighbor_fill(pos, batch, graph_ptr, lattice, pbc, fallback, out_ptr, N, E, cutoff, max_nb, edge_index, edge_shift,
+                       status, stream):
+    from oracle import neighbor_oracle as NO
+    P, gp, lat, pb, B = _nl_inputs(pos, batch, graph_ptr, lattice, pbc, N)
+    s, t, sh, _ = NO.batch_neighbor_list(P, gp, lat, pb, cutoff, max_nb)
+    assert len(s) == E
+    ei = view(edge_index, 2, E, dtype=I64)
+    ei[0], ei[1] = torch.from_numpy(s), torch.from_numpy(t)
+    view(edge_shift, E, 3).copy_(torch.from_numpy(sh))
+
+
 def lcao_histogram(keys, n, nb, counts, stream):
     k = view(keys, n, dtype=I64)
     view(counts, nb).copy_(torch.bincount(k, minlength=nb).float() if n else torch.zeros(nb))
