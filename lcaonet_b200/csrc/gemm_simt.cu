@@ -158,10 +158,80 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dY, in
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---------------------------------------------------------------------------------------------
+// Tiny row counts (species / pair tables: M = 37 ... 512).  The tiled kernel above runs them as one or two
+// CTAs stepping through K with a barrier per 16 columns (~30 us of pure latency); here the OUTPUT columns are
+// spread over the grid (8 per CTA, their operand columns staged in shared memory), one thread per row, all
+// loads of a row in flight at once.  FP32 FMA, same summation order over k as a plain dot product.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTinyCols = 8, kTinyMaxK = 256;
+
+// Y[m, n0..n0+7] = act(sum_k X[m,k] * Wt(n,k) + bias) ; TRANS: Wt(n,k) = W[k*ldw + n] (dgrad) else W[n*ldw + k]
+template <bool TRANS>
+__global__ void __launch_bounds__(128) k_tiny_rows(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W,
+                                                   int64_t ldw, const float* __restrict__ bias, float* __restrict__ Y,
+                                                   int64_t ldy, float* __restrict__ pre, int64_t ldp, int M, int K, int N,
+                                                   int act, int accumulate) {
+  __shared__ float s_w[kTinyCols][kTinyMaxK];
+  const int n0 = blockIdx.x * kTinyCols;
+  for (int i = threadIdx.x; i < kTinyCols * K; i += 128) {
+    const int j = TRANS ? i % kTinyCols : i / K, k = TRANS ? i / kTinyCols : i % K;
+    float w = 0.f;
+    if (n0 + j < N) w = TRANS ? __ldg(W + (int64_t)k * ldw + n0 + j) : __ldg(W + (int64_t)(n0 + j) * ldw + k);
+    s_w[j][k] = w;
+  }
+  __syncthreads();
+  for (int m = blockIdx.y * 128 + threadIdx.x; m < M; m += gridDim.y * 128) {
+    float acc[kTinyCols];
+#pragma unroll
+    for (int j = 0; j < kTinyCols; ++j) acc[j] = 0.f;
+    const float* xr = X + (int64_t)m * ldx;
+    for (int k = 0; k < K; ++k) {
+      const float x = __ldg(xr + k);
+#pragma unroll
+      for (int j = 0; j < kTinyCols; ++j) acc[j] = fmaf(x, s_w[j][k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kTinyCols; ++j) {
+      const int n = n0 + j;
+      if (n >= N) continue;
+      float v = acc[j];
+      if (bias) v += __ldg(bias + n);
+      if (accumulate) v += Y[(int64_t)m * ldy + n];
+      if (pre) pre[(int64_t)m * ldp + n] = v;
+      Y[(int64_t)m * ldy + n] = (act == LCAO_ACT_SILU) ? siluf(v) : v;
+    }
+  }
+}
+
+// dW[n, k] += sum_m dY[m,n] X[m,k] ; db[n] += sum_m dY[m,n].  CTA = one output row n, thread = column k.
+__global__ void __launch_bounds__(128) k_tiny_wgrad(const float* __restrict__ dY, int64_t ldy, const float* __restrict__ X,
+                                                    int64_t ldx, float* __restrict__ dW, float* __restrict__ db, int M, int K) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc = fmaf(__ldg(dY + (int64_t)m * ldy + n), __ldg(X + (int64_t)m * ldx + k), acc);
+    dW[(int64_t)n * K + k] += acc;
+  }
+  if (db && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += __ldg(dY + (int64_t)m * ldy + n);
+    db[n] += s;
+  }
+}
+
+inline bool tiny_ok(int64_t M, int K) { return M <= 512 && K <= kTinyMaxK; }
+
 }  // namespace
 
 int lcao_simt_linear_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy,
                          float* pre, int64_t ldp, int64_t M, int32_t K, int32_t Nout, int32_t act, cudaStream_t st) {
+  if (tiny_ok(M, K)) {
+    dim3 grid((unsigned)ceil_div64(Nout, kTinyCols), (unsigned)ceil_div64(M, 128));
+    k_tiny_rows<false><<<grid, 128, 0, st>>>(X, ldx, W, K, bias, Y, ldy, pre, ldp, (int)M, K, Nout, act, 0);
+    LCAO_LAUNCH_CHECK();
+    return LCAO_OK;
+  }
   GemmArgs g{};
   g.A = X; g.lda = ldx; g.B = W; g.ldb = K; g.C = Y; g.ldc = ldy; g.pre = pre; g.ldp = ldp; g.bias = bias;
   g.M = M; g.N = Nout; g.K = K; g.k_chunk = K; g.act = act;
@@ -176,6 +246,12 @@ int lcao_simt_linear_fwd(const float* X, int64_t ldx, const float* W, const floa
 
 int lcao_simt_linear_dgrad(const float* dY, int64_t ldy, const float* W, float* dX, int64_t ldx, int64_t M, int32_t K,
                            int32_t Nout, int32_t accumulate, cudaStream_t st) {
+  if (tiny_ok(M, Nout)) {  // dX[m, k] = sum_n dY[m,n] W[n,k]: contraction over Nout, "weight" read transposed
+    dim3 grid((unsigned)ceil_div64(K, kTinyCols), (unsigned)ceil_div64(M, 128));
+    k_tiny_rows<true><<<grid, 128, 0, st>>>(dY, ldy, W, K, nullptr, dX, ldx, nullptr, 0, (int)M, Nout, K, LCAO_ACT_NONE, accumulate);
+    LCAO_LAUNCH_CHECK();
+    return LCAO_OK;
+  }
   GemmArgs g{};
   g.A = dY; g.lda = ldy; g.B = W; g.ldb = K; g.C = dX; g.ldc = ldx;
   g.M = M; g.N = K; g.K = Nout; g.k_chunk = Nout; g.accumulate = accumulate;
@@ -190,6 +266,11 @@ int lcao_simt_linear_dgrad(const float* dY, int64_t ldy, const float* W, float* 
 
 int lcao_simt_linear_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int64_t M,
                            int32_t K, int32_t Nout, cudaStream_t st) {
+  if (M <= 64) {  // (longer row loops are better served by the split-K tiled kernel below)
+    k_tiny_wgrad<<<(unsigned)Nout, 128, 0, st>>>(dY, ldy, X, ldx, dW, db, (int)M, K);
+    LCAO_LAUNCH_CHECK();
+    return LCAO_OK;
+  }
   GemmArgs g{};
   g.A = dY; g.lda = ldy; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = K;
   g.M = Nout; g.N = K; g.K = M; g.atomic_out = 1;

@@ -17,6 +17,8 @@
 // Pipelines: smem stages full/empty (producer <-> MMA), TMEM accumulator full/empty (MMA <-> epilogue),
 // persistent loop over 128-row blocks (grid = #SMs).  All mbarrier waits are bounded (trap on timeout)
 // so a protocol bug aborts the kernel instead of hanging the GPU.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -165,6 +167,7 @@ struct RowsArgs {
   float* pre; int64_t ldp;
   int64_t M; int Kc; int Nb;
   int b_trans, act, accumulate, x3, stages, lo_stages;
+  int debug;  // ablation bits for tuning runs (LCAO_TC_DEBUG): 1 = no output stores, 2 = no input copies, 4 = no MMAs
 };
 
 constexpr int kLoadWarps = 4;
@@ -182,6 +185,7 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 
 __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (g.debug & 32) return;  // (ablation: launch cost only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t blockB = g.Nb * 128;                 // bytes of one 32-k column block of the weight
   const uint32_t halfB = (g.Kc / kChunkK) * blockB;   // bytes of one of {W_hi, W_lo}
@@ -263,6 +267,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (g.debug & 64) {  // (ablation: launch + prologue only)
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
 
   if (warp >= 9) {
     // ============================== loader warps ==============================
@@ -278,10 +287,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
         mbar_wait(&hi_empty[s], ((it / R) & 1) ^ 1);
         const uint32_t dst = hi_base + s * kStageBytes;
         const float* src = g.A + mrow * g.lda + kc * kChunkK + c * 4;
+        if (!(g.debug & 2)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool ok = mrow + 4 * j < g.M;
-          cp_async16(dst + sw128_off(32 * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = mrow + 4 * j < g.M;
+            cp_async16(dst + sw128_off(32 * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+          }
         }
         cp_async_arrive(&raw_full[s]);
       }
@@ -296,6 +307,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
         mbar_wait(&raw_full[s], (it / R) & 1);
         if (g.x3) {
           mbar_wait(&lo_empty[l], ((it / L) & 1) ^ 1);
+        }
+        if (g.x3 && !(g.debug & 16)) {
           uint8_t* ph = sHi + (size_t)s * kStageBytes + t * 16;
           uint8_t* pl = sLo + (size_t)l * kStageBytes + t * 16;
 #pragma unroll
@@ -327,13 +340,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
           tc_fence_after();
           const uint32_t a_hi = hiBase + s * kStageBytes, a_lo = loBase + l * kStageBytes;
           const uint32_t b_hi = bBase + kc * blockB, b_lo = b_hi + halfB;
+          if (!(g.debug & 4)) {
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / 8; ++kk) {
-            const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
-            umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
-            if (g.x3) {
-              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, (kc | kk) != 0);
-              umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+            for (int kk = 0; kk < kChunkK / 8; ++kk) {
+              const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
+              umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
+              if (g.x3) {
+                umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, (kc | kk) != 0);
+                umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+              }
             }
           }
           umma_commit(&hi_empty[s]);
@@ -356,7 +371,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
       const int64_t mw = mb * kBlockM + warp * 32;
-      for (int c0 = 0; c0 < g.Nb; c0 += 32) {
+      for (int c0 = 0; c0 < ((g.debug & 8) ? 0 : g.Nb); c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
         if (g.x3) {
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
               if (g.pre) st4(g.pre + m * g.ldp + col, o);
               if (g.act == LCAO_ACT_SILU) o = make_float4(silu_fast(o.x), silu_fast(o.y), silu_fast(o.z), silu_fast(o.w));
               if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + col));
-              st4(g.Y + m * g.ldy + col, o);
+              if (!(g.debug & 1)) st4(g.Y + m * g.ldy + col, o);
             }
           }
         }
@@ -704,6 +719,8 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.G = G; g.ldg = ldg; g.Y = Y; g.ldy = ldy;
   g.pre = pre; g.ldp = ldp; g.M = M; g.Kc = Kc; g.Nb = Nb; g.b_trans = b_trans; g.act = act; g.accumulate = accumulate;
   g.x3 = x3;
+  static const int dbg = getenv("LCAO_TC_DEBUG") ? atoi(getenv("LCAO_TC_DEBUG")) : 0;
+  g.debug = dbg;
   const int lo_stages = x3 ? 2 : 0;
   int stages = 8;
   while (stages > 2 && rows_smem(Kc, Nb, stages, lo_stages) > kMaxSmem) --stages;

@@ -92,7 +92,9 @@ def _both(fn, monkeypatch, *cpu_args):
 
 
 @pytest.mark.parametrize("M,K,N,silu,bias", [(1000, 128, 128, True, False), (777, 256, 128, True, True), (64, 128, 256, False, True),
-                                             (333, 64, 1, False, False), (5, 20, 12, True, True), (40000, 128, 128, True, False)])
+                                             (333, 64, 1, False, False), (5, 20, 12, True, True), (40000, 128, 128, True, False),
+                                             (37, 256, 128, False, False), (296, 128, 128, True, False), (512, 128, 128, True, True),
+                                             (513, 128, 128, True, True)])
 def test_linear_fwd_bwd(M, K, N, silu, bias, monkeypatch):
     torch.manual_seed(M)
     x = torch.randn(M, K, requires_grad=True)
