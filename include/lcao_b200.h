@@ -71,11 +71,16 @@ int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t
  *   in_ptr (N+1), in_edge (E)  in-CSR;   in_src (E) = src32[in_edge]
  *   out_ptr (N+1), out_edge (E) out-CSR
  *   tri_ptr (E+1)  exclusive scan of the triplet count per edge, tri_ptr[E] = T
- *                  (T = sum_e indeg(s_e) - [s_e == t_e]; reference lcaonet.py:464-473)
+ *                  (T = sum_e indeg(s_e) - [s_e == t_e]; reference lcaonet.py:464-473); may be NULL (skipped:
+ *                  only the reference's triplet LISTS need it, see lcao_triplet_offsets)
  * scratch: (2*N + 2*E + 8) int32. */
 int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,
                            int32_t* in_ptr, int32_t* in_edge, int32_t* in_src, int32_t* out_ptr,
                            int32_t* out_edge, int32_t* tri_ptr, int32_t* scratch, void* stream);
+
+/* tri_ptr (E+1) alone, from an existing index; scratch: E int32. */
+int lcao_triplet_offsets(const int32_t* src32, const int32_t* dst32, const int32_t* in_ptr, int64_t E, int32_t* tri_ptr,
+                         int32_t* scratch, void* stream);
 
 /* Materialise the reference's triplet lists (lcaonet.py:468-485) and, if unit != NULL, the triplet
  * cosines (lcaonet.py:431-435): for edge e, for e' in in(s_e) with e' != e:

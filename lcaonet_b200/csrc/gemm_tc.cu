@@ -668,18 +668,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
   }
 }
 
-// stage 2 of the weight gradient: dW[n, j] += sum_cta part[cta][j][n] ; db[n] += sum_cta part_db[cta][n]  (fixed order)
-__global__ void __launch_bounds__(128) k_wgrad_reduce(const float* __restrict__ part, int ncta, int Kx, float* __restrict__ dW,
-                                                      int64_t ldw, float* __restrict__ db) {
-  const int j = blockIdx.x, n = threadIdx.x;
-  if (j < Kx) {
-    float acc = 0.f;
-    for (int c = 0; c < ncta; ++c) acc += part[((size_t)c * Kx + j) * 128 + n];
-    dW[(int64_t)n * ldw + j] += acc;
-  } else if (db) {
-    float acc = 0.f;
-    for (int c = 0; c < ncta; ++c) acc += part[(size_t)ncta * Kx * 128 + (size_t)c * 128 + n];
-    db[n] += acc;
+// stage 2 of the weight gradient: dW[n, j] += sum_cta part[cta][j][n] ; db[n] += sum_cta part_db[cta][n].
+// CTA = one column j (or the bias row), 8 thread rows split the CTA range, fixed-order tree over the 8 partial sums.
+__global__ void __launch_bounds__(1024) k_wgrad_reduce(const float* __restrict__ part, int ncta, int Kx, float* __restrict__ dW,
+                                                       int64_t ldw, float* __restrict__ db) {
+  __shared__ float s_p[8][128];
+  const int j = blockIdx.x, n = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const bool bias_row = j >= Kx;
+  const float* src = bias_row ? part + (size_t)ncta * Kx * 128 + n : part + (size_t)j * 128 + n;
+  const size_t stride = bias_row ? 128 : (size_t)Kx * 128;
+  float acc = 0.f;
+  for (int c = ty; c < ncta; c += 8) acc += src[(size_t)c * stride];
+  s_p[ty][n] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    const float t = ((s_p[0][n] + s_p[1][n]) + (s_p[2][n] + s_p[3][n])) + ((s_p[4][n] + s_p[5][n]) + (s_p[6][n] + s_p[7][n]));
+    if (bias_row) db[n] += t;
+    else dW[(int64_t)n * ldw + j] += t;
   }
 }
 
@@ -776,7 +781,7 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
   const unsigned grid = wgrad_grid(M);
   k_tc_wgrad<<<grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st>>>(g);
   LCAO_LAUNCH_CHECK();
-  k_wgrad_reduce<<<Kx + (db ? 1 : 0), 128, 0, st>>>(part, (int)grid, Kx, dW, ldw, db);
+  k_wgrad_reduce<<<Kx + (db ? 1 : 0), 1024, 0, st>>>(part, (int)grid, Kx, dW, ldw, db);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

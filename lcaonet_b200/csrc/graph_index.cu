@@ -22,12 +22,14 @@ __global__ void k_hist64(const int64_t* __restrict__ keys, int64_t n, int32_t* _
   grouped_atomic_add(cnt, i < n ? keys[i] : 0, i < n);
 }
 
+// few hot keys (species / pair tables): lanes holding the same key elect a leader that issues ONE atomic for the group
 __global__ void k_hist_f(const int64_t* __restrict__ keys, int64_t n, int64_t nb, float* __restrict__ cnt) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) {
-    int64_t k = keys[i];
-    if (k >= 0 && k < nb) atomicAdd(&cnt[k], 1.0f);  // integer-valued float adds are exact below 2^24
-  }
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t k = i < n ? keys[i] : -1;
+  const bool valid = k >= 0 && k < nb;
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? k : (int64_t)-1 - lane);
+  if (valid && (int)lane == __ffs(peers) - 1) atomicAdd(&cnt[k], (float)__popc(peers));  // integer-valued: exact below 2^24
 }
 
 // single-CTA exclusive scan; out has n+1 entries (out[n] = total).  in may alias out.
@@ -186,7 +188,7 @@ extern "C" int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t
 extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,
                                       int32_t* in_ptr, int32_t* in_edge, int32_t* in_src, int32_t* out_ptr,
                                       int32_t* out_edge, int32_t* tri_ptr, int32_t* scratch, void* stream) {
-  LCAO_REQUIRE(E >= 0 && N >= 0 && in_ptr && out_ptr && tri_ptr && scratch, "lcao_graph_index_build: null buffer");
+  LCAO_REQUIRE(E >= 0 && N >= 0 && in_ptr && out_ptr && scratch, "lcao_graph_index_build: null buffer");
   LCAO_REQUIRE(E == 0 || (edge_index && src32 && dst32 && in_edge && in_src && out_edge),
                "lcao_graph_index_build: null edge buffer");
   LCAO_REQUIRE(E < (1ll << 31) && N < (1ll << 31), "lcao_graph_index_build: sizes must fit int32");
@@ -201,14 +203,32 @@ extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int6
   if (E > 0) {
     k_edge_prep<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(edge_index, E, src32, dst32);
     LCAO_LAUNCH_CHECK();
-    int32_t* cnt = scr_out;  // E entries, free after the out sort
-    k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, cnt);
-    LCAO_LAUNCH_CHECK();
-    k_exscan<<<1, 1024, 0, st>>>(cnt, E, tri_ptr);
-    LCAO_LAUNCH_CHECK();
-  } else {
+    if (tri_ptr) {  // only the reference's triplet LISTS need these offsets; the fused kernels work from the CSRs
+      int32_t* cnt = scr_out;  // E entries, free after the out sort
+      k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, cnt);
+      LCAO_LAUNCH_CHECK();
+      k_exscan<<<1, 1024, 0, st>>>(cnt, E, tri_ptr);
+      LCAO_LAUNCH_CHECK();
+    }
+  } else if (tri_ptr) {
     LCAO_CUDA(cudaMemsetAsync(tri_ptr, 0, sizeof(int32_t), st));
   }
+  return LCAO_OK;
+}
+
+// triplet offsets alone, from an existing index (for callers that asked lcao_graph_index_build to skip them)
+extern "C" int lcao_triplet_offsets(const int32_t* src32, const int32_t* dst32, const int32_t* in_ptr, int64_t E,
+                                    int32_t* tri_ptr, int32_t* scratch, void* stream) {
+  LCAO_REQUIRE(tri_ptr && (E == 0 || (src32 && dst32 && in_ptr && scratch)), "lcao_triplet_offsets: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E == 0) {
+    LCAO_CUDA(cudaMemsetAsync(tri_ptr, 0, sizeof(int32_t), st));
+    return LCAO_OK;
+  }
+  k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, scratch);
+  LCAO_LAUNCH_CHECK();
+  k_exscan<<<1, 1024, 0, st>>>(scratch, E, tri_ptr);
+  LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
 

@@ -71,11 +71,20 @@ class GraphIndex:
         self.src32, self.dst32 = torch.empty(E, **i32), torch.empty(E, **i32)
         self.in_ptr, self.out_ptr = torch.empty(N + 1, **i32), torch.empty(N + 1, **i32)
         self.in_edge, self.in_src, self.out_edge = torch.empty(E, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
-        self.tri_ptr = torch.empty(E + 1, **i32)
+        self._tri_ptr = None  # triplet offsets: only the reference's triplet LISTS need them -> built on demand
         scratch = torch.empty(2 * N + 2 * E + 8, **i32)
         _call("lcao_graph_index_build", ptr(ei), E, N, ptr(self.src32), ptr(self.dst32), ptr(self.in_ptr),
-              ptr(self.in_edge), ptr(self.in_src), ptr(self.out_ptr), ptr(self.out_edge), ptr(self.tri_ptr),
-              ptr(scratch), stream_ptr())
+              ptr(self.in_edge), ptr(self.in_src), ptr(self.out_ptr), ptr(self.out_edge), None, ptr(scratch), stream_ptr())
+
+    @property
+    def tri_ptr(self) -> Tensor:
+        if self._tri_ptr is None:
+            i32 = dict(dtype=torch.int32, device=self.src32.device)
+            self._tri_ptr = torch.empty(self.E + 1, **i32)
+            scratch = torch.empty(max(self.E, 1), **i32)
+            _call("lcao_triplet_offsets", ptr(self.src32), ptr(self.dst32), ptr(self.in_ptr), self.E, ptr(self._tri_ptr),
+                  ptr(scratch), stream_ptr())
+        return self._tri_ptr
 
     def num_triplets(self) -> int:
         return int(self.tri_ptr[-1].item())  # host sync: T is data dependent

@@ -75,6 +75,17 @@ def lcao_graph_index_build(ei, E, N, src32, dst32, in_ptr, in_edge, in_src, out_
         view(out_edge, E, dtype=I32).copy_(oe)
         indeg = (ip[1:] - ip[:-1]).long()
         tp[1:] = (indeg[s] - (s == t).long()).cumsum(0)
+    if tri_ptr:
+        view(tri_ptr, E + 1, dtype=I32).copy_(tp.to(I32))
+
+
+def lcao_triplet_offsets(src32, dst32, in_ptr, E, tri_ptr, scratch, stream):
+    tp = torch.zeros(E + 1, dtype=I64)
+    if E:
+        s, t = view(src32, E, dtype=I32).long(), view(dst32, E, dtype=I32).long()
+        N = int(max(s.max(), t.max())) + 1
+        ip = view(in_ptr, N + 1, dtype=I32).long()
+        tp[1:] = ((ip[1:] - ip[:-1])[s] - (s == t).long()).cumsum(0)
     view(tri_ptr, E + 1, dtype=I32).copy_(tp.to(I32))
 
 
