@@ -144,6 +144,18 @@ __device__ __forceinline__ float4 silu_grad4(float4 g, float4 h) {
   return make_float4(g.x * silu_grad_fast(h.x), g.y * silu_grad_fast(h.y), g.z * silu_grad_fast(h.z), g.w * silu_grad_fast(h.w));
 }
 
+// 8 consecutive floats: one 256-bit store (a full 32-byte sector) when the address allows it, else two 128-bit ones
+__device__ __forceinline__ void store8(float* p, const float* v, bool wide) {
+  if (wide) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  } else {
+    st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
 // =================================================================================================
 // Kernel 1: row-streaming GEMM   Y[M, Nb] = epi( A[M, Kc] * Bop[Kc, Nb] )
 //   forward : Bop(n, k) = W[n*ldw + k]  (b_trans = 0, W is (Nb, Kc) row-major)
@@ -167,6 +179,7 @@ struct RowsArgs {
   float* pre; int64_t ldp;
   int64_t M; int Kc; int Nb;
   int b_trans, act, accumulate, x3, stages, lo_stages;
+  int wide_store;  // Y / pre rows are 32-byte aligned: 256-bit stores
   int debug;  // ablation bits for tuning runs (LCAO_TC_DEBUG): 1 = no output stores, 2 = no input copies, 4 = no MMAs
 };
 
@@ -193,8 +206,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   uint8_t* sB = smem_raw;
   uint8_t* sHi = sB + 2 * halfB;
   uint8_t* sLo = sHi + (size_t)R * kStageBytes;
-  uint8_t* sEpi = sLo + (size_t)(g.x3 ? L : 0) * kStageBytes;  // no lo ring in 1x mode
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * kEpiWarpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)(g.x3 ? L : 0) * kStageBytes);  // no lo ring in 1x mode
   uint64_t* raw_full = bars;            // [R] loaders (cp.async completion) -> split warps
   uint64_t* full = raw_full + R;        // [R] split warps -> MMA
   uint64_t* hi_empty = full + R;        // [R] MMA -> loaders
@@ -360,17 +372,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     __syncwarp();
   } else {
     // ============================== epilogue warps ==============================
-    // TMEM gives every thread one ROW (32 columns per load); storing that directly would touch 32
-    // different 128-byte lines per instruction.  Each warp therefore transposes its 32x32 chunk through
-    // a private padded smem tile so that every global store instruction writes 4 full 128-byte rows.
-    uint8_t* stg = sEpi + warp * kEpiWarpBytes;
-    const int rl = lane >> 3, cl = (lane & 7) * 4;   // read-back mapping: 4 rows x 8 float4 per instruction
+    // TMEM gives every thread one ROW (32 consecutive columns = 128 contiguous bytes of the output row per load).
+    // The row segment is finished in registers (bias, accumulate, pre-activation, SiLU, SiLU' factor) and written
+    // with 256-bit stores: every store instruction of a thread fills one whole 32-byte sector, so no shared-memory
+    // transpose is needed (and its 18 KB go to the operand ring).
+    const bool wide = g.wide_store != 0;
     uint32_t tile = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
       const int acc = tile & 1;
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
-      const int64_t mw = mb * kBlockM + warp * 32;
+      const int64_t m = mb * kBlockM + warp * 32 + lane;
       for (int c0 = 0; c0 < ((g.debug & 8) ? 0 : g.Nb); c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
@@ -380,32 +392,32 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
         }
-        __syncwarp();  // previous chunk fully read back
+        if (m < g.M) {
+          const int nc = min(32, g.Nb - c0);  // multiple of 16
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        const int nc = min(32, g.Nb - c0);
-        if (cl < nc) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rl + 4 * i;
-            const int64_t m = mw + r;
-            if (m < g.M) {
-              float4 o = *reinterpret_cast<const float4*>(stg + r * kEpiPitch + cl * 4);
-              const int64_t col = c0 + cl;
+          for (int j = 0; j < 32; j += 8) {
+            if (j < nc) {
+              float* o = v + j;
               if (g.bias) {
-                const float4 b = ldg4(g.bias + col);
-                o = make_float4(o.x + b.x, o.y + b.y, o.z + b.z, o.w + b.w);
+                const float4 b0 = ldg4(g.bias + c0 + j), b1 = ldg4(g.bias + c0 + j + 4);
+                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
               }
               if (g.accumulate) {
-                const float4 p = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + col);
-                o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+                const float4 p0 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
+                const float4 p1 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j + 4);
+                o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w; o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
               }
-              if (g.pre) st4(g.pre + m * g.ldp + col, o);
-              if (g.act == LCAO_ACT_SILU) o = make_float4(silu_fast(o.x), silu_fast(o.y), silu_fast(o.z), silu_fast(o.w));
-              if (g.G) o = silu_grad4(o, ldg4(g.G + m * g.ldg + col));
-              if (!(g.debug & 1)) st4(g.Y + m * g.ldy + col, o);
+              if (g.pre) store8(g.pre + m * g.ldp + c0 + j, o, wide);
+              if (g.act == LCAO_ACT_SILU) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
+              }
+              if (g.G) {
+                const float4 h0 = ldg4(g.G + m * g.ldg + c0 + j), h1 = ldg4(g.G + m * g.ldg + c0 + j + 4);
+                o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
+                o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
+              }
+              if (!(g.debug & 1)) store8(g.Y + m * g.ldy + c0 + j, o, wide);
             }
           }
         }
@@ -709,7 +721,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 // rows kernel: contraction Kc % 32 == 0, output columns Nb % 16 == 0 and <= 128 per launch, weights resident.
 static size_t rows_smem(int Kc, int Nb, int stages, int lo_stages) {
   const size_t halfB = (size_t)(Kc / kChunkK) * Nb * 128;
-  return 2 * halfB + (size_t)(stages + lo_stages) * kStageBytes + kEpiWarps * kEpiWarpBytes + 512 + 1024;
+  return 2 * halfB + (size_t)(stages + lo_stages) * kStageBytes + 512 + 1024;
 }
 
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y) {
@@ -724,11 +736,19 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.G = G; g.ldg = ldg; g.Y = Y; g.ldy = ldy;
   g.pre = pre; g.ldp = ldp; g.M = M; g.Kc = Kc; g.Nb = Nb; g.b_trans = b_trans; g.act = act; g.accumulate = accumulate;
   g.x3 = x3;
+  g.wide_store = ((reinterpret_cast<uintptr_t>(Y) | (uintptr_t)(ldy * 4)) & 31u) == 0 &&
+                 (!pre || ((reinterpret_cast<uintptr_t>(pre) | (uintptr_t)(ldp * 4)) & 31u) == 0);
   static const int dbg = getenv("LCAO_TC_DEBUG") ? atoi(getenv("LCAO_TC_DEBUG")) : 0;
   g.debug = dbg;
-  const int lo_stages = x3 ? 2 : 0;
+  // the 3xTF32 weight (hi + lo) takes 128 KB at K = N = 128: 6 operand stages of 16 KB remain -> 3 hi + 3 lo
+  int lo_stages = x3 ? 3 : 0;
   int stages = 8;
   while (stages > 2 && rows_smem(Kc, Nb, stages, lo_stages) > kMaxSmem) --stages;
+  if (x3 && stages < 3 && lo_stages > 2) {  // keep the two rings balanced
+    lo_stages = 2;
+    stages = 8;
+    while (stages > 2 && rows_smem(Kc, Nb, stages, lo_stages) > kMaxSmem) --stages;
+  }
   g.stages = stages;
   g.lo_stages = x3 ? lo_stages : 1;  // (modulo operand only; no buffer is touched in 1x mode)
   const size_t smem = rows_smem(Kc, Nb, stages, lo_stages);
