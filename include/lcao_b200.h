@@ -195,7 +195,8 @@ int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, int64_t ldb,
                        const int32_t* src32, const int32_t* dst32, int64_t E, int32_t C, int32_t act,
                        float* out, float* pre, void* stream);
 /* out[r,:] = sum_{j in [ptr[r],ptr[r+1])} x[perm[j],:] * (y ? y[perm[j],:] : 1) * scale_r
- * scale_r = 1 (mean=0) or 1/max(count,1) (mean=1).  Deterministic, no atomics. */
+ * scale_r = 1 (mean=0) or 1/max(count,1) (mean=1).  Deterministic, no atomics.  x may be NULL when no segment
+ * has any item (edge-less batch): out is zero-filled. */
 int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int64_t ldy, const int32_t* ptr,
                      const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo, void* stream);
 /* backward of the message sum  agg[s] = sum_{e in out(s)} bw[e] * h[e],  h = SiLU(pre_h)  (lcaonet.py:207-214):

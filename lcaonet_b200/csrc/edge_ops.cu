@@ -450,7 +450,8 @@ extern "C" int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int
                                 const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo,
                                 void* stream) {
   if (R == 0 || C == 0) return LCAO_OK;
-  LCAO_REQUIRE(x && ptr && out, "lcao_segment_sum: null buffer");
+  // x may be NULL when there are no items at all (an edge-less batch): every segment is empty and out is zero-filled
+  LCAO_REQUIRE(ptr && out, "lcao_segment_sum: null buffer");
   const bool vec = C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && (!y || ldy % 4 == 0) && aligned16(x) &&
                    aligned16(out) && (!y || aligned16(y));
   const unsigned grid = (unsigned)ceil_div64(R, kWarpsPerCta);

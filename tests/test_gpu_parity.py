@@ -289,6 +289,44 @@ def test_autograd_forces_match_reference_golden():
     _check_autograd_forces(gold, model, out, 1e-5, 5e-5)
 
 
+def test_degenerate_graphs_match_oracle():
+    """isolated atoms (no edges at all for some nodes), a batch without any edge, and batch=None"""
+    kwargs = dict(emb_size=32, emb_size_coeff=32, emb_size_conv=32, cutoff=5.0, cutoff_net="polynomial")
+    torch.manual_seed(5)
+    model = LCAONet(**kwargs)
+    p = O.cast_params(model.state_dict(), torch.float64)
+    model = model.to(DEV).train()
+    g = qm9_like_batch(3, seed=12, margin=0.05)
+    n0 = g["z"].shape[0]
+    # append two isolated atoms as a 4th "molecule"
+    g2 = GraphBatch(z=torch.cat([g["z"], torch.tensor([1, 8])]), pos=torch.cat([g["pos"], torch.tensor([[0.0, 0, 0], [30.0, 0, 0]])]),
+                    edge_index=g["edge_index"], edge_shift=g["edge_shift"], lattice=torch.cat([g["lattice"], g["lattice"][:1]]),
+                    batch=torch.cat([g["batch"], torch.tensor([3, 3])]))
+    assert g2["z"].shape[0] == n0 + 2
+    out = model(g2.to(DEV))
+    ref = O.forward(p, full_cfg(kwargs), graph_as(g2, torch.float64), training=True)
+    assert rel_l2(out, ref) < 1e-5
+    (out**2).mean().backward()
+    assert all(torch.isfinite(q.grad).all() for q in model.parameters() if q.grad is not None)
+    # no edges at all
+    g3 = GraphBatch(z=torch.tensor([1, 6, 8]), pos=torch.tensor([[0.0, 0, 0], [20.0, 0, 0], [0, 20.0, 0]]),
+                    edge_index=torch.zeros(2, 0, dtype=torch.long), edge_shift=torch.zeros(0, 3), lattice=50 * torch.eye(3).unsqueeze(0),
+                    batch=torch.zeros(3, dtype=torch.long))
+    model.eval()
+    with torch.no_grad():
+        out3 = model(g3.to(DEV))  # (the reference itself cannot run this case: it reshapes a 0-row tensor with -1)
+        assert out3.shape == (1, 1) and torch.isfinite(out3).all()
+        singles = [GraphBatch(z=g3["z"][i:i + 1], pos=g3["pos"][i:i + 1], edge_index=g3["edge_index"], edge_shift=g3["edge_shift"],
+                              lattice=g3["lattice"], batch=torch.zeros(1, dtype=torch.long)) for i in range(3)]
+        assert rel_l2(sum(model(s.to(DEV)) for s in singles), out3) < 1e-6  # no edges: atoms contribute independently
+        # batch = None: a single graph
+        g1 = qm9_like_batch(1, seed=13, margin=0.05)
+        p_now = O.cast_params({k: v.cpu() for k, v in model.state_dict().items()}, torch.float64)  # BN stats moved above
+        ref1 = O.forward(p_now, full_cfg(kwargs), graph_as(g1, torch.float64), training=False)
+        g1n = GraphBatch({k: v for k, v in g1.items() if k != "batch"})
+        assert rel_l2(model(g1n.to(DEV)), ref1) < 1e-5
+
+
 def test_node_features_match_oracle_layer_by_layer():
     kwargs = dict(cutoff=5.0, cutoff_net="polynomial")
     torch.manual_seed(3)
