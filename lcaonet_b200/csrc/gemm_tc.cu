@@ -238,17 +238,28 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();  // barriers initialised, TMEM address published
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (g.debug & 64) {  // (ablation: launch + TMEM/barrier set-up only)
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
 
-  // ---- resident B operand (the layer's weight), split hi/lo once per CTA, by all threads; 4 loads in flight per
-  //      thread (the weights come from L2 / HBM with ~1 us latency: a dependent loop would cost ~10 us per launch)
-  {
+  // ---- resident B operand (the layer's weight), split hi/lo once per CTA by the 9 non-loader warps while the
+  //      loader warps already stream the first A stages; 4 loads in flight per thread (the weights come from L2 /
+  //      HBM with ~1 us latency: a dependent loop would cost ~10 us per launch)
+  constexpr int kStageThreads = (4 + 4 + 1) * 32;  // 288
+  if (warp < 9) {
     const int kq = g.Kc / 4, total = g.Nb * kq;
-    for (int base = 0; base < total; base += 4 * kRowsThreads) {
+    for (int base = 0; base < total; base += 4 * kStageThreads) {
       float4 w[4];
       int n[4], kg[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * kRowsThreads + (int)threadIdx.x;
+        const int idx = base + u * kStageThreads + (int)threadIdx.x;
         w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         n[u] = -1;
         if (idx < total) {
@@ -273,16 +284,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
         }
       }
     }
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (g.debug & 64) {  // (ablation: launch + prologue only)
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
-    return;
+    fence_proxy_async();
+    asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");  // weights complete (non-loader warps only)
   }
 
   if (warp >= 9) {

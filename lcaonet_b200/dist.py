@@ -21,6 +21,10 @@ class FlatGradBucket:
         for p in self.params:
             p.grad = self.flat[off: off + p.numel()].view_as(p)
             off += p.numel()
+        # the interaction blocks may now write their weight gradients straight into these views
+        for m in module.modules():
+            if hasattr(m, "grads_in_place"):
+                m.grads_in_place = True
 
     def zero(self) -> None:
         self.flat.zero_()

@@ -251,6 +251,9 @@ class LCAOInteraction(nn.Module):
         self.out_weight = Dense(C, emb_size, False, weight_init)
         # run the block as ONE autograd node (ops.interaction_layer); False = one node per kernel (same arithmetic)
         self.fused_node = True
+        # accumulate parameter gradients straight into existing `.grad` buffers (see ops.interaction_layer); switched
+        # on by dist.FlatGradBucket, whose flat buffer backs every .grad
+        self.grads_in_place = False
 
     def forward(self, x, cst, vmask, rb, unit, gi, lgrp, NL) -> Tensor:
         if self.add_valence and vmask is None:
@@ -258,10 +261,14 @@ class LCAOInteraction(nn.Module):
         C = self.emb_size_conv
         if isinstance(cst, PairCoeffs) and self.fused_node and x.shape[1] % 4 == 0:
             fc, fn = self.f_coeffs, self.f_node
-            return ops.interaction_layer(x, cst.table, rb, unit, self.node_weight.weight, self.node_weight.bias, fc[0].weight,
-                                         fc[2].weight, self.f_three[0].weight, self.basis_weight.weight, fn[0].weight,
-                                         fn[0].bias, fn[2].weight, fn[2].bias, self.out_weight.weight, cst.pair, cst.kptr,
-                                         cst.kperm, vmask, lgrp, gi, NL, C)
+            params = (self.node_weight.weight, self.node_weight.bias, fc[0].weight, fc[2].weight, self.f_three[0].weight,
+                      self.basis_weight.weight, fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias, self.out_weight.weight)
+            sinks = None
+            if self.grads_in_place and torch.is_grad_enabled():
+                sinks = tuple(p.grad if (p.requires_grad and p.grad is not None and p.grad.is_contiguous()) else None
+                              for p in params)
+            return ops.interaction_layer(x, cst.table, rb, unit, *params, cst.pair, cst.kptr, cst.kperm, vmask, lgrp, gi, NL, C,
+                                         sinks)
         nw = self.node_weight(x)  # (N, 2C): [:, :C] feeds f_node, [:, C:] is the three-body gate
         xc, xk = nw[:, :C], nw[:, C:]
         if isinstance(cst, PairCoeffs):  # f_coeffs on the species-pair table, contracted per edge

@@ -424,16 +424,18 @@ def _lin_dgrad(dy, ldy, M, w, dx, ldx, accumulate, st):
     _call("lcao_linear_dgrad", ptr(dy), ldy, None, 0, ACT_NONE, ptr(w), ptr(dx), ldx, M, K, Nout, accumulate, _gemm_mode, None, st)
 
 
-def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st):
+def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
+    """dW (+ db) of one layer.  With sinks (the parameters' .grad buffers) the kernels accumulate straight into them
+    — the C ABI's `dW +=` contract — and (None, None) is returned: no zero-fill, no separate accumulation pass."""
     Nout, K = w.shape
-    dw = torch.zeros(Nout, K, device=w.device)
-    db = torch.zeros(Nout, device=w.device) if has_bias else None
+    dw = dw_sink if dw_sink is not None else torch.zeros(Nout, K, device=w.device)
+    db = (db_sink if db_sink is not None else torch.zeros(Nout, device=w.device)) if has_bias else None
     n_scr = int(_lib.load().lcao_linear_bwd_scratch(ptr(dy), ldy, None, 0, ACT_NONE, None, ptr(x), ldx, None, 0, M, K, Nout,
                                                     _gemm_mode))
     scr = torch.empty(n_scr, device=w.device) if n_scr else None
     _call("lcao_linear_wgrad", ptr(dy), ldy, None, 0, ACT_NONE, ptr(x), ldx, ptr(dw), ptr(db), M, K, Nout, _gemm_mode,
           ptr(scr), st)
-    return dw, db
+    return (None if dw_sink is not None else dw), (None if (db_sink is not None or not has_bias) else db)
 
 
 def _act_bwd(dy, pre, M, C, st):
@@ -454,7 +456,7 @@ class _InteractionLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, aux):
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C = aux
+        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = aux
         require_cuda(x, table, rb, unit)
         st = stream_ptr()
         dev = x.device
@@ -507,7 +509,9 @@ class _InteractionLayer(torch.autograd.Function):
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
          lw, bw, a1, pre_a, h, pre_h, agg) = ctx.saved_tensors
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C = ctx.aux
+        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = ctx.aux
+        # gradient sinks: the parameters' own .grad buffers (order: w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o)
+        s_wn, s_bn, s_wc0, s_wc2, s_w3, s_wb, s_w1, s_b1, s_w2, s_b2, s_wo = sinks if sinks is not None else (None,) * 11
         st = stream_ptr()
         dev = x.device
         N, H = x.shape
@@ -518,14 +522,14 @@ class _InteractionLayer(torch.autograd.Function):
         need_rb, need_unit = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
         d_out = d_out.contiguous()
         # x_out = x + out_weight(agg)
-        dw_o, _ = _lin_wgrad(d_out, H, agg, C, N, w_o, False, st)
+        dw_o, _ = _lin_wgrad(d_out, H, agg, C, N, w_o, False, st, s_wo)
         d_agg = torch.empty(N, C, device=dev)
         _lin_dgrad(d_out, H, N, w_o, d_agg, C, 0, st)
         # agg[s] = sum_{e in out(s)} bw[e] * h[e]
         d_bw, d_preh = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
         _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), ptr(h), ptr(bw), ptr(pre_h), E, C, ptr(d_bw), ptr(d_preh), st)
         # h = silu(f_node.2(a1)) ; a1 = silu(u_a[s] + u_b[t] + b1)
-        dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st)
+        dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st, s_w2, s_b2)
         d_a1 = torch.empty(E, C, device=dev)
         _lin_dgrad(d_preh, C, E, w_2, d_a1, C, 0, st)
         d_prea = _act_bwd(d_a1, pre_a, E, C, st)
@@ -533,19 +537,25 @@ class _InteractionLayer(torch.autograd.Function):
         _call("lcao_segment_sum", ptr(d_prea), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 0, ptr(d_u), 2 * C, st)
         _call("lcao_segment_sum", ptr(d_prea), C, None, 0, ptr(gi.in_ptr), ptr(gi.in_edge), N, C, 0, d_u.data_ptr() + 4 * C,
               2 * C, st)
-        db_1 = d_u[:, :C].sum(0)
         d_nw = torch.empty(N, 2 * C, device=dev)
         _lin_dgrad(d_u, 2 * C, N, w_1cat, d_nw, 2 * C, 0, st)  # writes d_xc = d_nw[:, :C]
-        dw_1cat, _ = _lin_wgrad(d_u, 2 * C, nw, 2 * C, N, w_1cat, False, st)
-        dw_1 = torch.cat([dw_1cat[:C], dw_1cat[C:]], dim=1)
+        # the bias b_1 enters once per edge through the u_a half: d b_1 = column sums of d_u[:, :C]
+        dw_1cat, db_cat = _lin_wgrad(d_u, 2 * C, nw, 2 * C, N, w_1cat, True, st)
+        dw_1, db_1 = torch.cat([dw_1cat[:C], dw_1cat[C:]], dim=1), db_cat[:C]
+        if s_w1 is not None:
+            s_w1.add_(dw_1)
+            dw_1 = None
+        if s_b1 is not None:
+            s_b1.add_(db_1)
+            db_1 = None
         # bw = basis_weight(lw) ; lw = twobody(B, g) ; g = f_three(tbw) ; tbw = threebody(B, ...)
-        dw_b, _ = _lin_wgrad(d_bw, C, lw, C, E, w_b, False, st)
+        dw_b, _ = _lin_wgrad(d_bw, C, lw, C, E, w_b, False, st, s_wb)
         d_lw = d_preh  # reuse
         _lin_dgrad(d_bw, C, E, w_b, d_lw, C, 0, st)
         dP = torch.empty(E, 1 + valence, C, device=dev)
         d_g = torch.empty(E, Cp, device=dev)
         _call("lcao_twobody_bwd", ptr(B), NG, ptr(g), ptr(d_lw), E, C, NL, valence, 1, ptr(dP), ptr(d_g), st)
-        dw_3, _ = _lin_wgrad(d_g, Cp, tbw, C, E, w_3, False, st)
+        dw_3, _ = _lin_wgrad(d_g, Cp, tbw, C, E, w_3, False, st, s_w3)
         d_tbw = d_bw  # reuse
         _lin_dgrad(d_g, Cp, E, w_3, d_tbw, C, 0, st)
         dB = torch.empty(E, NG, C, device=dev)
@@ -567,15 +577,15 @@ class _InteractionLayer(torch.autograd.Function):
         _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB), E,
               P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), st)
         d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st)
-        dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st)
+        dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st, s_wc2)
         d_t1 = torch.empty(P * O, C, device=dev)
         _lin_dgrad(d_pre2, Cp, P * O, w_c2, d_t1, C, 0, st)
         d_pre1 = _act_bwd(d_t1, pre1, P * O, C, st)
-        dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st)
+        dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st, s_wc0)
         d_table = torch.empty(P, O, K, device=dev)
         _lin_dgrad(d_pre1, C, P * O, w_c0, d_table, K, 0, st)
         # nw = node_weight(x) ; residual
-        dw_n, db_n = _lin_wgrad(d_nw, 2 * C, x, H, N, w_n, True, st)
+        dw_n, db_n = _lin_wgrad(d_nw, 2 * C, x, H, N, w_n, True, st, s_wn, s_bn)
         dx = d_out.clone()
         _lin_dgrad(d_nw, 2 * C, N, w_n, dx, H, 1, st)
         d_unit = (du_ks + du_st) if need_unit else None
@@ -583,9 +593,13 @@ class _InteractionLayer(torch.autograd.Function):
 
 
 def interaction_layer(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, pair, kptr, kperm, vmask,
-                      lgrp, gi, NL, C):
+                      lgrp, gi, NL, C, grad_sinks=None):
+    """grad_sinks: optional 11-tuple of the weights' / biases' `.grad` buffers (contiguous, same shapes; None entries
+    allowed).  The backward pass then ACCUMULATES those gradients in place and returns None for them to autograd —
+    what AccumulateGrad would do, without the zero-fills and the per-parameter add kernels.  Opt-in
+    (`LCAOInteraction.grads_in_place`, set by `dist.FlatGradBucket`): parameter hooks do not fire for them."""
     return _InteractionLayer.apply(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o,
-                                   (pair, kptr, kperm, vmask, lgrp, gi, NL, C))
+                                   (pair, kptr, kperm, vmask, lgrp, gi, NL, C, grad_sinks))
 
 
 # ------------------------------------------------------------------------------------------------
