@@ -87,11 +87,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
   __shared__ int s_l[LCAO_MAX_ORB];
   if (threadIdx.x < O) s_l[threadIdx.x] = lgrp[threadIdx.x];
   __syncthreads();
-  const int64_t e = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
-  if (e >= E) return;
   const int lane = threadIdx.x & 31;
   constexpr int NG = NL + (VAL ? 1 : 0), NP = NL * (NL + 1) / 2;
   const int Cp = VAL ? 2 * C : C;
+  // grid-stride over edges: the per-CTA set-up above is paid once, and a warp's next pair id is already in flight
+  for (int64_t e = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); e < E; e += (int64_t)gridDim.x * kWarps) {
   const float* row = tab + pair[e] * (int64_t)O * Cp;
   double g[NP];
 #pragma unroll
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     }
   }
   if (gram) store_gram<NP>(g, lane, gram + e * NP);
+  }
 }
 
 // Gram matrix of an existing B (E,NG,C): upper triangle over the first NL groups, FP64
@@ -299,7 +300,8 @@ extern "C" int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, con
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && O > 0 && O <= LCAO_MAX_ORB && NL >= 1 && NL <= 4,
                "lcao_pair_contract_fwd: need C %% 4 == 0, O <= %d, 1 <= NL <= 4 (got C=%d O=%d NL=%d)", LCAO_MAX_ORB, C, O, NL);
   LCAO_REQUIRE(al16(tab) && al16(B), "lcao_pair_contract_fwd: buffers must be 16-byte aligned");
-  const unsigned grid = (unsigned)ceil_div64(E, kWarps);
+  const int64_t want = ceil_div64(E, kWarps);
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
 #define PC_CALL(nl, val) k_pair_contract_fwd<nl, val><<<grid, kWarps * 32, 0, st>>>(tab, pair, rb, vmask, lgrp, E, O, C, B, gram)
   if (valence) {
