@@ -134,11 +134,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int C, float* __restrict__ tbw) {
+    const int32_t* __restrict__ out_edge, int N, int C, float* __restrict__ tbw) {
   constexpr int NP = NL * (NL + 1) / 2;
   __shared__ __align__(16) float s_a[kFwdWarps][32 * 4];  // per-warp coefficient scratch: pair (t, r) at slot t*8 + r
-  const int s = blockIdx.x;
-  const int ib = in_ptr[s], dI = in_ptr[s + 1] - ib, ob = out_ptr[s], dO = out_ptr[s + 1] - ob;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_mine = lane & 7, t_mine = lane >> 3;
   float* sa = s_a[warp];
@@ -146,6 +144,17 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
 #pragma unroll
   for (int v = 0; v < V4; ++v) okc[v] = FULL || (lane + 32 * v) * 4 < C;
 
+  // grid-stride over the centre nodes; the CSR row of the NEXT node is fetched while this one is processed, which
+  // takes one of the three dependent latencies (row pointers -> edge ids -> rows) off every node's critical path
+  int s = blockIdx.x;
+  if (s >= N) return;
+  int n_ib = in_ptr[s], n_ie = in_ptr[s + 1], n_ob = out_ptr[s], n_oe = out_ptr[s + 1];
+  for (; s < N; s += gridDim.x) {
+  const int ib = n_ib, dI = n_ie - n_ib, ob = n_ob, dO = n_oe - n_ob;
+  if (s + (int)gridDim.x < N) {
+    const int sn = s + gridDim.x;
+    n_ib = in_ptr[sn]; n_ie = in_ptr[sn + 1]; n_ob = out_ptr[sn]; n_oe = out_ptr[sn + 1];
+  }
   for (int jb = warp * kR; jb < dO; jb += kFwdWarps * kR) {
     const int nr = min(kR, dO - jb);
     // lane (r, t) keeps out-edge r of this block: id and direction
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
       }
     }
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
+    const int32_t* __restrict__ out_edge, int N, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
     float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
   const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
@@ -248,13 +258,22 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
   __shared__ __align__(16) float s_a2[FORCES ? kBwdWarps : 1][16 * 4];
   __shared__ float s_st[FORCES ? kBwdWarps : 1][FORCES ? kJS * 3 : 1];  // per-warp partials of d unit[e_j] (s->t role)
 
-  const int s = blockIdx.x;
-  const int ib = in_ptr[s], dI = in_ptr[s + 1] - ib, ob = out_ptr[s], dO = out_ptr[s + 1] - ob;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // grid-stride over the centre nodes with the next node's CSR row in flight (see the forward kernel)
+  int s = blockIdx.x;
+  if (s >= N) return;
+  int n_ib = in_ptr[s], n_ie = in_ptr[s + 1], n_ob = out_ptr[s], n_oe = out_ptr[s + 1];
+  for (; s < N; s += gridDim.x) {
+  const int ib = n_ib, dI = n_ie - n_ib, ob = n_ob, dO = n_oe - n_ob;
+  if (s + (int)gridDim.x < N) {
+    const int sn = s + gridDim.x;
+    n_ib = in_ptr[sn]; n_ie = in_ptr[sn + 1]; n_ob = out_ptr[sn]; n_oe = out_ptr[sn + 1];
+  }
+  if (FORCES) __syncthreads();  // the previous node's d_unit partials have been consumed
   if (dI == 0) {  // no in-edges: only the s->t role gradients of the out-edges exist, and they are zero
     if (FORCES)
       for (int t = threadIdx.x; t < dO * 3; t += kBwdWarps * 32) du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = 0.f;
-    return;
+    continue;
   }
   if (dO == 0) {  // in-edges that feed no triplet: zero gradients
     for (int i = warp; i < dI; i += kBwdWarps) {
@@ -266,7 +285,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
       }
       if (FORCES && lane < 3) du_ks[3 * (int64_t)ep + lane] = 0.f;
     }
-    return;
+    continue;
   }
   if constexpr (FORCES) {
     for (int t = lane; t < kJS * 3; t += 32) s_st[warp][t] = 0.f;
@@ -492,6 +511,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
       du_st[3 * (int64_t)out_edge[ob + t / 3] + t % 3] = x;
     }
   }
+  }
 }
 
 // tuning knob read once from the environment (benchmark sweeps); falls back to the default when out of range
@@ -527,13 +547,15 @@ extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram
   cudaStream_t st = (cudaStream_t)stream;
   const int V4 = C <= 128 ? 1 : 2;
   const bool full = false;  // (the predicate-free specialisation measured SLOWER in the forward: 0.291 vs 0.260 ms)
+  static const int per_sm_f = tile_in("LCAO_TB_GRID_FWD", 48, 1, 64);
+  const unsigned grid = (unsigned)(N < 148ll * per_sm_f ? N : 148ll * per_sm_f);
 #define CALL(nl, v4)                                                                                                    \
   if (full)                                                                                                             \
-    k_threebody_fwd<nl, v4, true><<<(unsigned)N, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
-                                                                          in_src, out_ptr, out_edge, C, tbw);           \
+    k_threebody_fwd<nl, v4, true><<<grid, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
+                                                                          in_src, out_ptr, out_edge, (int)N, C, tbw);           \
   else                                                                                                                  \
-    k_threebody_fwd<nl, v4, false><<<(unsigned)N, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,        \
-                                                                           in_edge, in_src, out_ptr, out_edge, C, tbw)
+    k_threebody_fwd<nl, v4, false><<<grid, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,        \
+                                                                           in_edge, in_src, out_ptr, out_edge, (int)N, C, tbw)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();
@@ -556,26 +578,29 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
   static const int ri = tile_in("LCAO_TB_RI", kRI, 1, 2);
-  const bool full = C == 128 * V4;  // in-edges per warp at a time (energy path; forces: 1)
+  const bool full = C == 128 * V4;
+  static const int per_sm_b = tile_in("LCAO_TB_GRID_BWD", 24, 1, 64);
+  const unsigned grid = (unsigned)(N < 148ll * per_sm_b ? N : 148ll * per_sm_b);
 #define CALL(nl, v4)                                                                                                   \
   if (forces)                                                                                                          \
-    k_threebody_bwd<nl, v4, true, 1, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,     \
-                                                                             in_edge, in_src, out_ptr, out_edge, C,    \
-                                                                             d_tbw, dP, dB, q, d_unit_ks, d_unit_st);  \
+    k_threebody_bwd<nl, v4, true, 1, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,     \
+                                                                             in_edge, in_src, out_ptr, out_edge,       \
+                                                                             (int)N, C, d_tbw, dP, dB, q, d_unit_ks,   \
+                                                                             d_unit_st);                               \
   else if (ri == 1 && full)                                                                                            \
-    k_threebody_bwd<nl, v4, false, 1, true><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,      \
+    k_threebody_bwd<nl, v4, false, 1, true><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,      \
                                                                                     in_ptr, in_edge, in_src, out_ptr,  \
-                                                                                    out_edge, C, d_tbw, dP, dB, q,     \
+                                                                                    out_edge, (int)N, C, d_tbw, dP, dB, q,     \
                                                                                     nullptr, nullptr);                 \
   else if (ri == 1)                                                                                                    \
-    k_threebody_bwd<nl, v4, false, 1, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
+    k_threebody_bwd<nl, v4, false, 1, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
                                                                                      in_ptr, in_edge, in_src, out_ptr, \
-                                                                                     out_edge, C, d_tbw, dP, dB, q,    \
+                                                                                     out_edge, (int)N, C, d_tbw, dP, dB, q,    \
                                                                                      nullptr, nullptr);                \
   else                                                                                                                 \
-    k_threebody_bwd<nl, v4, false, 2, false><<<(unsigned)N, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
+    k_threebody_bwd<nl, v4, false, 2, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
                                                                                      in_ptr, in_edge, in_src, out_ptr, \
-                                                                                     out_edge, C, d_tbw, dP, dB, q,    \
+                                                                                     out_edge, (int)N, C, d_tbw, dP, dB, q,    \
                                                                                      nullptr, nullptr)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
