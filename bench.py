@@ -81,6 +81,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _ncu_traffic(call: str):
+    """DRAM bytes (read + write) of one launch of `call`'s kernel from the committed ncu --set full capture of this
+    round (profiles/ncu_traffic.json, written from gpurun_out/*.ncu-rep by hand; same shapes as the bench workload)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(call, {}).get("dram_bytes_per_launch")
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -191,18 +200,18 @@ def algorithmic_bytes(name, shp):
         return E * (4 * NL * C + 8 * NP + 12 + 8 + 4 * C) + N * (4 * C + 8)
     if name == "lcao_threebody_bwd":  # read B, Gram, d_tbw, unit, CSR, xk; write dB (E,NL,C), q (E,C)
         return E * (4 * NL * C + 8 * NP + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
-    if name == "lcao_pair_contract_fwd":  # read rb + pair id (table is L2 resident); write B + Gram
-        return E * (4 * O + 8 + 4 * NL * C + 8 * NP)
+    if name == "lcao_pair_contract_fwd":  # read rb + pair id (table is L2 resident); write B + Gram + two-body sums
+        return E * (4 * O + 8 + 4 * NL * C + 8 * NP + 4 * C)
     if name == "lcao_pair_contract_bwd":  # read dB + rb + perm; the (P,O,C) result is L2 sized
         return E * (4 * NL * C + 4 * O + 4)
     if name == "lcao_coeff_contract_fwd":  # read cst' (E,O,C) + rb; write B
         return E * (4 * O * C + 4 * O + 4 * NL * C)
     if name == "lcao_coeff_contract_bwd":  # read dB + rb; write d_cst' (E,O,C)
         return E * (4 * NL * C + 4 * O + 4 * O * C)
-    if name == "lcao_twobody_fwd":
-        return E * (4 * NL * C + 4 * C + 4 * C)
-    if name == "lcao_twobody_bwd":
-        return E * (4 * NL * C + 4 * C + 4 * C + 4 * NL * C + 4 * C)
+    if name == "lcao_twobody_fwd":  # read sum_l B_l and g; write lw
+        return E * 3 * 4 * C
+    if name == "lcao_twobody_bwd":  # read sum_l B_l, g, d_lw; write the compact dP and d_g
+        return E * 5 * 4 * C
     return None
 
 
@@ -355,7 +364,8 @@ def run_ours(args):
         if dom is not None:
             per_launch = dom.get("bytes_per_launch", dom.get("bytes_per_step", 0) / max(dom["calls_per_step"], 1))
             roofline = {"kernel": dom["call"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+                        "frac": dom["frac"], "traffic": _ncu_traffic(dom["call"]) if args.workload == "qm9" and args.mol_per_gpu == 1024 else None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
                         "share_of_step": dom["share"]}
         cpu = None
         if world == 1 or True:

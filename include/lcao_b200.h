@@ -139,10 +139,12 @@ int lcao_coeff_contract_bwd(const float* cst1, const float* rb, const float* vma
  *   B[e,l,:]  = sum_{o: l(o)=l} rb[e,o] * (tabA[pair[e],o,:] + m[e,o] tabV[pair[e],o,:])      l = 0..NL-1
  *   B[e,NL,:] = sum_o rb[e,o] m[e,o] tabV[pair[e],o,:]                                        (only if valence)
  * with tab (P,O,Cp) = [A | V].  gram (nullable): (E, NL(NL+1)/2) FP64 upper triangle of B[e,l,:].B[e,l',:]
- * over the first NL groups (consumed by lcao_threebody_*). */
+ * over the first NL groups (consumed by lcao_threebody_*).  psum (nullable): (E, 1 + valence, C) =
+ * [sum_{l<NL} B[e,l,:] | B[e,NL,:]] — the only part of B the two-body weight needs; lcao_twobody_fwd/bwd accept it
+ * in place of B with NG = 1 + valence, NL = 1 (a third of the bytes). */
 int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, const float* rb, const float* vmask,
                            const int32_t* lgrp, int64_t E, int32_t O, int32_t C, int32_t NL, int32_t valence,
-                           float* B, double* gram, void* stream);
+                           float* B, double* gram, float* psum, void* stream);
 /* d_tab (P,O,Cp) = keyed reduction of rb[e,o] dB[e,l(o),:] over the edges of each pair, deterministic
  * (two stages, no atomics); (kptr (P+1), kperm (E)) = edges grouped by pair (lcao_bucket_sort).
  * d_rb (E,O) written if non-NULL (autograd forces).  scratch: lcao_pair_contract_bwd_scratch() BYTES. */

@@ -44,7 +44,7 @@ SIGNATURES = {
     "lcao_geom_basis_bwd": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p],
     "lcao_coeff_contract_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "lcao_coeff_contract_bwd": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
-    "lcao_pair_contract_fwd": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
+    "lcao_pair_contract_fwd": [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "lcao_pair_contract_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "lcao_coeff_gram": [_p, _i32, _i64, _i32, _i32, _p, _p],
     "lcao_sigmoid_rows": [_p, _i64, _p, _i64, _i64, _i32, _p],

@@ -83,7 +83,7 @@ template <int NL, bool VAL>
 __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     const float* __restrict__ tab, const int64_t* __restrict__ pair, const float* __restrict__ rb,
     const float* __restrict__ vmask, const int32_t* __restrict__ lgrp, int64_t E, int O, int C, float* __restrict__ B,
-    double* __restrict__ gram) {
+    double* __restrict__ gram, float* __restrict__ psum) {
   __shared__ int s_l[LCAO_MAX_ORB];
   if (threadIdx.x < O) s_l[threadIdx.x] = lgrp[threadIdx.x];
   __syncthreads();
@@ -121,6 +121,13 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     }
 #pragma unroll
     for (int l = 0; l < NG; ++l) st4(B + (e * NG + l) * (int64_t)C + c, acc[l]);
+    if (psum) {  // [sum_{l<NL} B_l | B_NL]: all the two-body weight needs (lcao_twobody_* with NG = 1 + valence, NL = 1)
+      float4 t = acc[0];
+#pragma unroll
+      for (int l = 1; l < NL; ++l) t = f4add(t, acc[l]);
+      st4(psum + e * (int64_t)(VAL ? 2 : 1) * C + c, t);
+      if (VAL) st4(psum + (e * 2 + 1) * (int64_t)C + c, acc[NL]);
+    }
     if (gram) {
       int i = 0;
 #pragma unroll
@@ -294,7 +301,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 extern "C" int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, const float* rb, const float* vmask,
                                       const int32_t* lgrp, int64_t E, int32_t O, int32_t C, int32_t NL,
-                                      int32_t valence, float* B, double* gram, void* stream) {
+                                      int32_t valence, float* B, double* gram, float* psum, void* stream) {
   if (E == 0) return LCAO_OK;
   LCAO_REQUIRE(tab && pair && rb && lgrp && B && (!valence || vmask), "lcao_pair_contract_fwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && O > 0 && O <= LCAO_MAX_ORB && NL >= 1 && NL <= 4,
@@ -303,7 +310,7 @@ extern "C" int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, con
   const int64_t want = ceil_div64(E, kWarps);
   const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
-#define PC_CALL(nl, val) k_pair_contract_fwd<nl, val><<<grid, kWarps * 32, 0, st>>>(tab, pair, rb, vmask, lgrp, E, O, C, B, gram)
+#define PC_CALL(nl, val) k_pair_contract_fwd<nl, val><<<grid, kWarps * 32, 0, st>>>(tab, pair, rb, vmask, lgrp, E, O, C, B, gram, psum)
   if (valence) {
     switch (NL) { case 1: PC_CALL(1, true); break; case 2: PC_CALL(2, true); break; case 3: PC_CALL(3, true); break; default: PC_CALL(4, true); }
   } else {

@@ -271,7 +271,7 @@ class _PairContract(torch.autograd.Function):
         B = torch.empty(E, NG, C, device=tab.device)
         gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=tab.device)
         _call("lcao_pair_contract_fwd", ptr(tab), ptr(pair), ptr(rb), ptr(vmask), ptr(lgrp), E, O, C, NL, valence, ptr(B),
-              ptr(gram), stream_ptr())
+              ptr(gram), None, stream_ptr())
         ctx.dims = (E, P, O, C, NL, valence)
         ctx.save_for_backward(tab, pair, kptr, kperm, rb, vmask, lgrp)
         ctx.mark_non_differentiable(gram)
@@ -474,8 +474,9 @@ class _InteractionLayer(torch.autograd.Function):
         tab, pre2 = _lin_fwd(t1, C, P * O, w_c2, None, ACT_SILU, st, grad)
         B = torch.empty(E, NG, C, device=dev)
         gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=dev)
+        psum = torch.empty(E, 1 + valence, C, device=dev)  # [sum_l B_l | valence slot]: the two-body weight's view of B
         _call("lcao_pair_contract_fwd", ptr(tab), ptr(pair), ptr(rb), ptr(vmask), ptr(lgrp), E, O, C, NL, valence, ptr(B),
-              ptr(gram), st)
+              ptr(gram), ptr(psum), st)
         # three-body
         gate = torch.empty(N, C, device=dev)
         _call("lcao_sigmoid_rows", nw.data_ptr() + 4 * C, 2 * C, ptr(gate), C, N, C, st)
@@ -485,7 +486,7 @@ class _InteractionLayer(torch.autograd.Function):
         g, _ = _lin_fwd(tbw, C, E, w_3, None, ACT_NONE, st, False)
         # two-body weight and message
         lw = torch.empty(E, C, device=dev)
-        _call("lcao_twobody_fwd", ptr(B), NG, ptr(g), E, C, NL, valence, ptr(lw), st)
+        _call("lcao_twobody_fwd", ptr(psum), 1 + valence, ptr(g), E, C, 1, valence, ptr(lw), st)
         bw, _ = _lin_fwd(lw, C, E, w_b, None, ACT_NONE, st, False)
         w_1cat = torch.cat([w_1[:, :C], w_1[:, C:]], dim=0)  # (2C, C): [W1a ; W1b] acting on x_s / x_t per NODE
         u, _ = _lin_fwd(nw, 2 * C, N, w_1cat, None, ACT_NONE, st, False)  # reads xc = nw[:, :C]
@@ -501,14 +502,14 @@ class _InteractionLayer(torch.autograd.Function):
         if grad:
             ctx.aux = aux
             ctx.save_for_backward(x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2,
-                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, h, pre_h, agg)
+                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, h, pre_h, agg, psum)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
-         lw, bw, a1, pre_a, h, pre_h, agg) = ctx.saved_tensors
+         lw, bw, a1, pre_a, h, pre_h, agg, psum) = ctx.saved_tensors
         pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = ctx.aux
         # gradient sinks: the parameters' own .grad buffers (order: w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o)
         s_wn, s_bn, s_wc0, s_wc2, s_w3, s_wb, s_w1, s_b1, s_w2, s_b2, s_wo = sinks if sinks is not None else (None,) * 11
@@ -554,7 +555,7 @@ class _InteractionLayer(torch.autograd.Function):
         _lin_dgrad(d_bw, C, E, w_b, d_lw, C, 0, st)
         dP = torch.empty(E, 1 + valence, C, device=dev)
         d_g = torch.empty(E, Cp, device=dev)
-        _call("lcao_twobody_bwd", ptr(B), NG, ptr(g), ptr(d_lw), E, C, NL, valence, 1, ptr(dP), ptr(d_g), st)
+        _call("lcao_twobody_bwd", ptr(psum), 1 + valence, ptr(g), ptr(d_lw), E, C, 1, valence, 1, ptr(dP), ptr(d_g), st)
         dw_3, _ = _lin_wgrad(d_g, Cp, tbw, C, E, w_3, False, st, s_w3)
         d_tbw = d_bw  # reuse
         _lin_dgrad(d_g, Cp, E, w_3, d_tbw, C, 0, st)

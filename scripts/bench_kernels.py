@@ -88,7 +88,7 @@ def edge():
     lgrp = torch.tensor([0, 0, 1, 0, 1, 0, 2, 1], dtype=torch.int32, device=DEV)
     B = torch.empty(E, NL, C, device=DEV)
     gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=DEV)
-    t_pf = timeit(lambda: ops._call("lcao_pair_contract_fwd", P(tab), P(pair), P(rb), None, P(lgrp), E, O, C, NL, 0, P(B), P(gram), st()))
+    t_pf = timeit(lambda: ops._call("lcao_pair_contract_fwd", P(tab), P(pair), P(rb), None, P(lgrp), E, O, C, NL, 0, P(B), P(gram), None, st()))
     kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
     dBr = torch.randn(E, NL, C, device=DEV)
     d_tab = torch.empty_like(tab)

@@ -294,7 +294,7 @@ def _gram(Bt, NL):
     return torch.stack(cols, 1)
 
 
-def lcao_pair_contract_fwd(tab, pair, rb, vmask, lgrp, E, O, C, NL, valence, B, gram, stream):
+def lcao_pair_contract_fwd(tab, pair, rb, vmask, lgrp, E, O, C, NL, valence, B, gram, psum, stream):
     Cp = C * (1 + valence)
     pr = view(pair, E, dtype=I64)
     T = view(tab, int(pr.max()) + 1, O * Cp).reshape(-1, O, Cp)
@@ -311,6 +311,11 @@ def lcao_pair_contract_fwd(tab, pair, rb, vmask, lgrp, E, O, C, NL, valence, B, 
     out[:, :NL] = torch.einsum("eoc,ol->elc", t, G)
     if gram:
         view(gram, E, NL * (NL + 1) // 2, dtype=torch.float64).copy_(_gram(out, NL))
+    if psum:
+        ps = view(psum, E, (1 + valence) * C).reshape(E, 1 + valence, C)
+        ps[:, 0] = out[:, :NL].sum(1)
+        if valence:
+            ps[:, 1] = out[:, NL]
 
 
 def lcao_coeff_gram(B, NG, E, C, NL, gram, stream):
