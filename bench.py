@@ -117,7 +117,7 @@ def cpu_oracle_step_time(n_mol: int, reps: int, threads: int | None = None):
     g = qm9_like_batch(n_mol, seed=0, cutoff=5.0)
     y = g["y"]
     times = []
-    for _ in range(reps + 1):  # first one is the warm-up
+    for _ in range(max(reps, 1) + 1):  # first one is the warm-up
         for v in p.values():
             if v.grad is not None:
                 v.grad = None

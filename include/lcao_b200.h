@@ -197,12 +197,15 @@ int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, int64_t ldb,
                        const int32_t* src32, const int32_t* dst32, int64_t E, int32_t C, int32_t act,
                        float* out, float* pre, void* stream);
 /* out[r,:] = sum_{j in [ptr[r],ptr[r+1])} x[perm[j],:] * (y ? y[perm[j],:] : 1) * scale_r
- * scale_r = 1 (mean=0) or 1/max(count,1) (mean=1).  Deterministic, no atomics.  x may be NULL when no segment
+ * `mean` is a flag word: bit 0: scale_r = 1/max(count,1) instead of 1; bit 1: y holds a pre-activation and the
+ * factor is SiLU(y) (the message sum then needs no stored copy of h = SiLU(pre_h)); bit 2: the factor is SiLU'(y)
+ * (backward through an activation folded into the reduction that follows it).  Deterministic, no atomics.  x may be NULL when no segment
  * has any item (edge-less batch): out is zero-filled. */
 int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int64_t ldy, const int32_t* ptr,
                      const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo, void* stream);
 /* backward of the message sum  agg[s] = sum_{e in out(s)} bw[e] * h[e],  h = SiLU(pre_h)  (lcaonet.py:207-214):
- *   d_bw[e,:] = d_agg[src[e],:] * h[e,:] ;  d_pre_h[e,:] = d_agg[src[e],:] * bw[e,:] * SiLU'(pre_h[e,:]) */
+ *   d_bw[e,:] = d_agg[src[e],:] * h[e,:] ;  d_pre_h[e,:] = d_agg[src[e],:] * bw[e,:] * SiLU'(pre_h[e,:])
+ * h may be NULL: it is then recomputed from pre_h. */
 int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
                  const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream);
 /* out[i,:] = table[idx[i],:] * (mul ? mul[i,:] : 1)   (idx int64 or int32 chosen by idx_is64) */
@@ -223,6 +226,11 @@ int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, const float* bi
 int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W, float* dX,
                       int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t accumulate, int32_t mode, float* scratch,
                       void* stream);
+/* dX = (dY W) * act'(G): lcao_linear_dgrad of a layer whose INPUT is act(G), G (M,K) ldg being that activation's
+ * pre-activation (nn.Sequential(Dense, act, Dense) chains: lcaonet.py:108-113,122-127,254-269).  Fuses the
+ * lcao_act_bwd pass that would otherwise follow into the GEMM epilogue. */
+int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* W, const float* G, int64_t ldg, int32_t act,
+                          float* dX, int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t mode, void* stream);
 /* dW (Nout,K) += (dY * act'(H))^T X ; db (Nout) += its column sums (db nullable).  dW/db zeroed by the caller. */
 int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
                       float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode, float* scratch, void* stream);

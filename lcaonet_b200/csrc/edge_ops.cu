@@ -231,14 +231,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
   const int32_t lo = ptr[r], hi = ptr[r + 1];
-  const float scale = mean ? 1.0f / (float)max(hi - lo, 1) : 1.0f;
+  const float scale = (mean & 1) ? 1.0f / (float)max(hi - lo, 1) : 1.0f;
+  const bool ysilu = (mean & 2) != 0;   // y holds a pre-activation: the factor is SiLU(y)
+  const bool ygrad = (mean & 4) != 0;   // ... or SiLU'(y) (backward through an activation, folded into the reduction)
   if (VEC) {
     for (int c = lane * 4; c < C; c += 128) {
       float4 acc = f4_zero();
       for (int32_t j = lo; j < hi; ++j) {
         const int64_t i = perm ? perm[j] : j;
         float4 v = ldg4(x + i * ldx + c);
-        if (y) v = f4_mul(v, ldg4(y + i * ldy + c));
+        if (y) {
+          float4 w = ldg4(y + i * ldy + c);
+          if (ysilu) w = make_float4(siluf(w.x), siluf(w.y), siluf(w.z), siluf(w.w));
+          if (ygrad) w = make_float4(silu_gradf(w.x), silu_gradf(w.y), silu_gradf(w.z), silu_gradf(w.w));
+          v = f4_mul(v, w);
+        }
         acc = f4_add(acc, v);
       }
       st4(out + r * ldo + c, f4_scale(scale, acc));
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
       for (int32_t j = lo; j < hi; ++j) {
         const int64_t i = perm ? perm[j] : j;
         float v = x[i * ldx + c];
-        if (y) v *= y[i * ldy + c];
+        if (y) v *= ysilu ? siluf(y[i * ldy + c]) : ygrad ? silu_gradf(y[i * ldy + c]) : y[i * ldy + c];
         acc += v;
       }
       out[r * ldo + c] = scale * acc;
@@ -334,8 +341,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
   const int lane = threadIdx.x & 31;
   const float* pa = d_agg + src32[e] * lda;
   for (int c = lane * 4; c < C; c += 128) {
-    const float4 g = ldg4(pa + c), hv = ldg4(h + e * (int64_t)C + c), b = ldg4(bw + e * (int64_t)C + c);
+    const float4 g = ldg4(pa + c), b = ldg4(bw + e * (int64_t)C + c);
     const float4 p = ldg4(pre_h + e * (int64_t)C + c);
+    const float4 hv = h ? ldg4(h + e * (int64_t)C + c) : make_float4(siluf(p.x), siluf(p.y), siluf(p.z), siluf(p.w));
     st4(d_bw + e * (int64_t)C + c, f4_mul(g, hv));
     st4(d_pre_h + e * (int64_t)C + c,
         make_float4(g.x * b.x * silu_gradf(p.x), g.y * b.y * silu_gradf(p.y), g.z * b.z * silu_gradf(p.z), g.w * b.w * silu_gradf(p.w)));
@@ -516,8 +524,8 @@ extern "C" int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_
 extern "C" int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
                             const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream) {
   if (E == 0) return LCAO_OK;
-  LCAO_REQUIRE(d_agg && src32 && h && bw && pre_h && d_bw && d_pre_h, "lcao_msg_bwd: null buffer");
-  LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && aligned16(d_agg) && aligned16(h) && aligned16(bw) && aligned16(pre_h) &&
+  LCAO_REQUIRE(d_agg && src32 && bw && pre_h && d_bw && d_pre_h, "lcao_msg_bwd: null buffer");
+  LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && aligned16(d_agg) && (!h || aligned16(h)) && aligned16(bw) && aligned16(pre_h) &&
                    aligned16(d_bw) && aligned16(d_pre_h),
                "lcao_msg_bwd: need C, lda multiples of 4 and 16-byte aligned buffers");
   k_msg_bwd<<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw,

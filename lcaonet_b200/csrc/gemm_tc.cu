@@ -383,10 +383,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     uint32_t tile = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
       const int acc = tile & 1;
+      const int64_t m = mb * kBlockM + warp * 32 + lane;
+      // The SiLU' factor rows (G) are fetched one 32-column chunk AHEAD of their use — the first chunk while the
+      // tile's MMAs are still running — so that the epilogue never waits on HBM between a TMEM load and its stores.
+      float4 gq[8];
+      if (g.G && m < g.M) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gq[q] = (4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
-      const int64_t m = mb * kBlockM + warp * 32 + lane;
       for (int c0 = 0; c0 < ((g.debug & 8) ? 0 : g.Nb); c0 += 32) {
+        float4 gn[8];
+        if (g.G && m < g.M && c0 + 32 < g.Nb) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            gn[q] = (c0 + 32 + 4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + c0 + 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
         if (g.x3) {
@@ -416,13 +429,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
                 for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
               }
               if (g.G) {
-                const float4 h0 = ldg4(g.G + m * g.ldg + c0 + j), h1 = ldg4(g.G + m * g.ldg + c0 + j + 4);
+                const float4 h0 = gq[j / 4], h1 = gq[j / 4 + 1];
                 o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
                 o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
               }
               if (!(g.debug & 1)) store8(g.Y + m * g.ldy + c0 + j, o, wide);
             }
           }
+        }
+        if (g.G) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) gq[q] = gn[q];
         }
       }
       tc_fence_before();

@@ -98,6 +98,37 @@ extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, i
   return LCAO_OK;
 }
 
+extern "C" int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
+                            int32_t C, int32_t act, void* stream);
+
+// dX = (dY W) * act'(G): the data gradient of a layer whose INPUT came out of an activation with pre-activation G.
+// The tcgen05 kernel applies the factor in its epilogue (last contraction chunk), which saves the separate
+// lcao_act_bwd pass (one read + one write of M x K) that would follow lcao_linear_dgrad.
+extern "C" int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* W, const float* G, int64_t ldg, int32_t act,
+                                     float* dX, int64_t ldx, int64_t M, int32_t K, int32_t Nout, int32_t mode,
+                                     void* stream) {
+  if (M == 0 || K == 0) return LCAO_OK;
+  LCAO_REQUIRE(dY && W && dX && G && Nout > 0, "lcao_linear_dgrad_act: null buffer");
+  LCAO_REQUIRE(act == LCAO_ACT_SILU, "lcao_linear_dgrad_act: unsupported activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dgrad_tc(dY, ldy, W, dX, ldx, M, K, Nout, mode) || ldg % 4 != 0 || ((uintptr_t)G & 15)) {
+    int rc = lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, 0, st);
+    if (rc) return rc;
+    return lcao_act_bwd(dX, ldx, G, ldg, dX, ldx, M, K, act, stream);  // elementwise, in place
+  }
+  for (int n0 = 0; n0 < K; n0 += 128) {          // output columns
+    const int nb = imin(128, K - n0);
+    for (int c0 = 0; c0 < Nout; c0 += 128) {     // contraction chunks; the factor goes on the last one
+      const int kc = imin(128, Nout - c0);
+      const bool last = c0 + 128 >= Nout;
+      int rc = lcao_tc_rows(dY + c0, ldy, W + (int64_t)c0 * K + n0, K, 1, nullptr, last ? G + n0 : nullptr, ldg, dX + n0, ldx,
+                            nullptr, 0, M, kc, nb, LCAO_ACT_NONE, c0 > 0, mode == LCAO_GEMM_TF32X3, st);
+      if (rc) return rc;
+    }
+  }
+  return LCAO_OK;
+}
+
 extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X,
                                  int64_t ldx, float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode,
                                  float* scratch, void* stream) {

@@ -15,7 +15,7 @@
 // are recomputed per (e,e') pair by one thread and broadcast through shared memory.
 //
 // Thread mapping: lane <-> float4 channel column (C = 128 -> 32 lanes), warp <-> 8 out-edges of a node
-// (forward: 8 register accumulators) or 2 in-edges (backward).  Warps are independent: B / gate / d_tbw
+// (forward: 8 register accumulators) or one in-edge (backward).  Warps are independent: B / gate / d_tbw
 // rows are read straight from global memory (L1/L2 serve the re-reads by the sibling warps of the same
 // node), the per-pair coefficients are computed by the lanes of the warp itself (one pair per lane)
 // and broadcast through a 512-byte per-warp scratch.  There is no block-level staging and no
@@ -31,9 +31,8 @@
 namespace {
 
 constexpr int kFwdWarps = 2;   // forward CTA: 2 warps x 8 out-edges per pass
-constexpr int kBwdWarps = 4;   // backward CTA: 4 warps x 2 in-edges per pass
+constexpr int kBwdWarps = 4;   // backward CTA: 4 warps, one in-edge per warp at a time (2 measured slower: 168 vs 128 registers)
 constexpr int kR = 8;          // forward: out-edge accumulators per warp
-constexpr int kRI = 1;         // backward: in-edges per warp at a time (1 measured faster than 2: 128 vs 168 registers)
 constexpr int kIB = 4;         // forward: in-edges per coefficient batch (kR * kIB = 32 pairs = one per lane)
 constexpr int kJS = 64;        // backward (forces): out-edges whose d_unit partials live in shared memory
 constexpr float kEps = 1e-12f; // F.normalize eps (lcaonet.py:184)
@@ -128,71 +127,60 @@ __device__ __forceinline__ int bfly8_index(int lane) { return ((lane >> 4) & 1) 
 // ---------------------------------------------------------------------------------------------
 // Out-of-range slots (out-edge r >= nr, in-edge beyond the node's list) are handled by CLAMPING the
 // index to a valid row and zeroing the pair's coefficient, so the row loads and the FMA block are
-// branch- and predicate-free.
-template <int NL, int V4, bool FULL>
-__global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
-    const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
-    const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
-    const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
-    const int32_t* __restrict__ out_edge, int N, int C, float* __restrict__ tbw) {
+// branch- and predicate-free.  (Fitting the slot grid to the node — R = 8 / 6 / 4 accumulator rows, skipping the
+// FMA block of in-edges beyond the tail, per-row guards — removed up to 30 % of the issued FMAs and did not make the
+// kernel faster: it is bound by the latency of each warp's dependent chain, not by issue slots; profiles/r01_notes.md.)
+
+// One block of nr <= R out-edges (positions ob + jb ..) of a node against all its dI in-edges.
+template <int NL, int V4, bool FULL, int R, bool TGUARD, int HB>
+__device__ __forceinline__ void tb_fwd_block(const float* __restrict__ B, int NG, const double* __restrict__ gram,
+                                             const float* __restrict__ unit, const float* __restrict__ gate, int64_t ldg,
+                                             const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src,
+                                             const int32_t* __restrict__ out_edge, int C, float* __restrict__ tbw,
+                                             float* sa, int lane, const bool (&okc)[V4], int ib, int dI, int ob, int jb,
+                                             int nr) {
   constexpr int NP = NL * (NL + 1) / 2;
-  __shared__ __align__(16) float s_a[kFwdWarps][32 * 4];  // per-warp coefficient scratch: pair (t, r) at slot t*8 + r
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r_mine = lane & 7, t_mine = lane >> 3;
-  float* sa = s_a[warp];
-  bool okc[V4];
+  const int r_mine = lane % R, t_mine = lane / R;  // coefficient duty: pair (in-edge t, out-edge r); lanes with t >= kIB idle
+  // lane (r, t) keeps out-edge r of this block: id and direction
+  const int e_mine = out_edge[ob + jb + min(r_mine, nr - 1)];
+  const float ux = unit[3 * (int64_t)e_mine], uy = unit[3 * (int64_t)e_mine + 1], uz = unit[3 * (int64_t)e_mine + 2];
+  float4 acc[R][V4];
 #pragma unroll
-  for (int v = 0; v < V4; ++v) okc[v] = FULL || (lane + 32 * v) * 4 < C;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int v = 0; v < V4; ++v) acc[r][v] = zero4();
 
-  // grid-stride over the centre nodes; the CSR row of the NEXT node is fetched while this one is processed, which
-  // takes one of the three dependent latencies (row pointers -> edge ids -> rows) off every node's critical path
-  int s = blockIdx.x;
-  if (s >= N) return;
-  int n_ib = in_ptr[s], n_ie = in_ptr[s + 1], n_ob = out_ptr[s], n_oe = out_ptr[s + 1];
-  for (; s < N; s += gridDim.x) {
-  const int ib = n_ib, dI = n_ie - n_ib, ob = n_ob, dO = n_oe - n_ob;
-  if (s + (int)gridDim.x < N) {
-    const int sn = s + gridDim.x;
-    n_ib = in_ptr[sn]; n_ie = in_ptr[sn + 1]; n_ob = out_ptr[sn]; n_oe = out_ptr[sn + 1];
-  }
-  for (int jb = warp * kR; jb < dO; jb += kFwdWarps * kR) {
-    const int nr = min(kR, dO - jb);
-    // lane (r, t) keeps out-edge r of this block: id and direction
-    const int e_mine = out_edge[ob + jb + min(r_mine, nr - 1)];
-    const float ux = unit[3 * (int64_t)e_mine], uy = unit[3 * (int64_t)e_mine + 1], uz = unit[3 * (int64_t)e_mine + 2];
-    float4 acc[kR][V4];
+  for (int ic = 0; ic < dI; ic += 32) {  // the node's in-edge ids, 32 at a time, one per lane
+    const int nI = min(32, dI - ic);
+    const int my_ep = in_edge[ib + ic + min(lane, nI - 1)];
+    const int my_k = in_src[ib + ic + min(lane, nI - 1)];
+    for (int i0 = 0; i0 < nI; i0 += kIB) {
+      // ---- coefficients of the R x 4 pairs of this batch, one per lane
+      const int ep_c = __shfl_sync(0xffffffffu, my_ep, min(i0 + t_mine, nI - 1));
+      float4 a = zero4();
+      {
+        const float c = fmaf(ux, unit[3 * (int64_t)ep_c], fmaf(uy, unit[3 * (int64_t)ep_c + 1], uz * unit[3 * (int64_t)ep_c + 2]));
+        float Y[4];
+        sph_harm<NL>(c, Y);
+        double g[NP];
 #pragma unroll
-    for (int r = 0; r < kR; ++r)
+        for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)ep_c * NP + p];
+        float w = 1.0f / fmaxf(sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f)), kEps);
+        if (r_mine >= nr || i0 + t_mine >= nI || ep_c == e_mine) w = 0.f;
+        a = make_float4(w * Y[0], w * Y[1], w * Y[2], w * Y[3]);
+      }
+      __syncwarp();  // previous batch's readers are done
+      if (R == 8 || t_mine < kIB) st4(sa + (t_mine * 8 + r_mine) * 4, a);
+      __syncwarp();
+      // ---- rows of the batch: issue every load first, then the FMAs (HB in-edges at a time: HB = 2 halves the row
+      //      registers, which buys resident warps)
+#pragma unroll 1
+      for (int h0 = 0; h0 < kIB; h0 += HB) {
+        if (TGUARD && h0 > 0 && i0 + h0 >= nI) break;  // warp-uniform
+        float4 gb[HB][NL][V4];
 #pragma unroll
-      for (int v = 0; v < V4; ++v) acc[r][v] = zero4();
-
-    for (int ic = 0; ic < dI; ic += 32) {  // the node's in-edge ids, 32 at a time, one per lane
-      const int nI = min(32, dI - ic);
-      const int my_ep = in_edge[ib + ic + min(lane, nI - 1)];
-      const int my_k = in_src[ib + ic + min(lane, nI - 1)];
-      for (int i0 = 0; i0 < nI; i0 += kIB) {
-        // ---- coefficients of the 8 x 4 pairs of this batch, one per lane
-        const int ep_c = __shfl_sync(0xffffffffu, my_ep, min(i0 + t_mine, nI - 1));
-        float4 a = zero4();
-        {
-          const float c = fmaf(ux, unit[3 * (int64_t)ep_c], fmaf(uy, unit[3 * (int64_t)ep_c + 1], uz * unit[3 * (int64_t)ep_c + 2]));
-          float Y[4];
-          sph_harm<NL>(c, Y);
-          double g[NP];
-#pragma unroll
-          for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)ep_c * NP + p];
-          float w = 1.0f / fmaxf(sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f)), kEps);
-          if (r_mine >= nr || i0 + t_mine >= nI || ep_c == e_mine) w = 0.f;
-          a = make_float4(w * Y[0], w * Y[1], w * Y[2], w * Y[3]);
-        }
-        __syncwarp();  // previous batch's readers are done
-        st4(sa + lane * 4, a);
-        __syncwarp();
-        // ---- rows of the batch: issue every load first, then the FMAs
-        float4 gb[kIB][NL][V4];
-#pragma unroll
-        for (int t = 0; t < kIB; ++t) {
-          const int src = min(i0 + t, nI - 1);
+        for (int t = 0; t < HB; ++t) {
+          const int src = min(i0 + h0 + t, nI - 1);
           const int ep = __shfl_sync(0xffffffffu, my_ep, src);
           const int k = __shfl_sync(0xffffffffu, my_k, src);
 #pragma unroll
@@ -204,33 +192,97 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
           }
         }
 #pragma unroll
-        for (int t = 0; t < kIB; ++t) {
+        for (int t = 0; t < HB; ++t) {
+          if (!TGUARD || t == 0 || i0 + h0 + t < nI) {  // warp-uniform
 #pragma unroll
-          for (int r = 0; r < kR; ++r) {
-            const float4 ar = lds4(sa + (t * 8 + r) * 4);
+            for (int r = 0; r < R; ++r) {
+              const float4 ar = lds4(sa + ((h0 + t) * 8 + r) * 4);
 #pragma unroll
-            for (int v = 0; v < V4; ++v) {
-              acc[r][v] = fma4(ar.x, gb[t][0][v], acc[r][v]);
-              if (NL > 1) acc[r][v] = fma4(ar.y, gb[t][1][v], acc[r][v]);
-              if (NL > 2) acc[r][v] = fma4(ar.z, gb[t][2][v], acc[r][v]);
-              if (NL > 3) acc[r][v] = fma4(ar.w, gb[t][3][v], acc[r][v]);
+              for (int v = 0; v < V4; ++v) {
+                acc[r][v] = fma4(ar.x, gb[t][0][v], acc[r][v]);
+                if (NL > 1) acc[r][v] = fma4(ar.y, gb[t][1][v], acc[r][v]);
+                if (NL > 2) acc[r][v] = fma4(ar.z, gb[t][2][v], acc[r][v]);
+                if (NL > 3) acc[r][v] = fma4(ar.w, gb[t][3][v], acc[r][v]);
+              }
             }
           }
         }
       }
     }
+  }
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      const int e = __shfl_sync(0xffffffffu, e_mine, r);
-      if (r < nr) {
+  for (int r = 0; r < R; ++r) {
+    const int e = __shfl_sync(0xffffffffu, e_mine, r % R);
+    if (r < nr) {
 #pragma unroll
-        for (int v = 0; v < V4; ++v) {
-          const int c = (lane + 32 * v) * 4;
-          if (okc[v]) st4(tbw + (int64_t)e * C + c, acc[r][v]);
-        }
+      for (int v = 0; v < V4; ++v) {
+        const int c = (lane + 32 * v) * 4;
+        if (okc[v]) st4(tbw + (int64_t)e * C + c, acc[r][v]);
       }
     }
   }
+}
+
+// L2 prefetch of `bytes` (multiple of 16) starting at the 16-byte aligned global address p: one instruction per row group
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int NL, int V4, bool FULL>
+__global__ void __launch_bounds__(kFwdWarps * 32, 8) k_threebody_fwd(
+    const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
+    const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
+    const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
+    const int32_t* __restrict__ out_edge, int N, int C, float* __restrict__ tbw) {
+  __shared__ __align__(16) float s_a[kFwdWarps][32 * 4];  // per-warp coefficient scratch: pair (t, r) at slot t*8 + r
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sa = s_a[warp];
+  bool okc[V4];
+#pragma unroll
+  for (int v = 0; v < V4; ++v) okc[v] = FULL || (lane + 32 * v) * 4 < C;
+  constexpr bool TG = false, PF = false;  // measured without effect (profiles/r01_notes.md): dead in-edge FMA blocks skipped, L2 prefetch of the next node's rows
+
+  // Grid-stride over the centre nodes as a three-deep software pipeline that takes the dependent latencies
+  // (row pointers -> edge ids -> rows) off every node's critical path: while node s is processed, the CSR row
+  // pointers of node s + 2G are fetched, and (PF) the in-edge ids of node s + G are read and its B / gate rows
+  // are pulled into L2 by bulk prefetches (one instruction per in-edge: its NL rows of B are contiguous).
+  const int G = gridDim.x;
+  int s = blockIdx.x;
+  if (s >= N) return;
+  int c_ib = in_ptr[s], c_ie = in_ptr[s + 1], c_ob = out_ptr[s], c_oe = out_ptr[s + 1];
+  int n_ib = 0, n_ie = 0, n_ob = 0, n_oe = 0;
+  if (s + G < N) { n_ib = in_ptr[s + G]; n_ie = in_ptr[s + G + 1]; n_ob = out_ptr[s + G]; n_oe = out_ptr[s + G + 1]; }
+  for (; s < N; s += G) {
+    const int ib = c_ib, dI = c_ie - c_ib, ob = c_ob, dO = c_oe - c_ob;
+    int f_ib = 0, f_ie = 0, f_ob = 0, f_oe = 0;
+    if ((int64_t)s + 2 * G < N) {
+      const int sn = s + 2 * G;
+      f_ib = in_ptr[sn]; f_ie = in_ptr[sn + 1]; f_ob = out_ptr[sn]; f_oe = out_ptr[sn + 1];
+    }
+    int pf_ep = -1, pf_k = 0;  // next node: in-edge lane * kFwdWarps + warp is this lane's to prefetch
+    if (PF) {
+      const int i = lane * kFwdWarps + warp;
+      if (i < n_ie - n_ib && n_oe > n_ob) { pf_ep = in_edge[n_ib + i]; pf_k = in_src[n_ib + i]; }
+    }
+    // the node's out-edges are split into ceil(dO / 8) blocks of (almost) equal size <= 8, one block per warp and pass
+    const int nblk = (dO + kR - 1) / kR, per = nblk ? (dO + nblk - 1) / nblk : 0;
+    for (int blk = warp; blk < nblk; blk += kFwdWarps) {
+      const int jb = blk * per, nr = min(per, dO - jb);
+#define TB_BLOCK(R) \
+  tb_fwd_block<NL, V4, FULL, R, TG, kIB>(B, NG, gram, unit, gate, ldg, in_edge, in_src, out_edge, C, tbw, sa, lane, okc, ib, dI, ob, jb, nr)
+      TB_BLOCK(8);
+#undef TB_BLOCK
+      if (PF && blk == warp && pf_ep >= 0) {
+        prefetch_l2(B + (int64_t)pf_ep * NG * C, (uint32_t)(NL * C * 4));
+        prefetch_l2(gate + (int64_t)pf_k * ldg, (uint32_t)(C * 4));
+      }
+    }
+    if (PF && warp >= nblk && pf_ep >= 0) {  // this warp had no block of the node
+      prefetch_l2(B + (int64_t)pf_ep * NG * C, (uint32_t)(NL * C * 4));
+      prefetch_l2(gate + (int64_t)pf_k * ldg, (uint32_t)(C * 4));
+    }
+    c_ib = n_ib; c_ie = n_ie; c_ob = n_ob; c_oe = n_oe;
+    n_ib = f_ib; n_ie = f_ie; n_ob = f_ob; n_oe = f_oe;
   }
 }
 
@@ -243,7 +295,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_threebody_fwd(
 //   FORCES: dc = Gt[j,:] . sum_l (w Y'_l) GB[i,l,:] - w^2 dot sum_l Y'_l (G Y)_l ;  d unit[e_j] += dc unit[e_i] and v.v.
 // Same clamping convention as the forward: dead slots read a valid row and carry zero coefficients.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int V4, bool FORCES, int RI, bool FULL>
+template <int NL, int V4, bool FORCES, bool FULL, bool GUARD>
 __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
@@ -252,10 +304,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
   constexpr int NP = NL * (NL + 1) / 2;
   const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
-  // per-warp scratch, pair (rr, jj) at slot rr*8 + jj: a_l = w Y_l | norm-path flag | (forces) w Y'_l
-  __shared__ __align__(16) float s_a[kBwdWarps][16 * 4];
-  __shared__ float s_f[kBwdWarps][16];
-  __shared__ __align__(16) float s_a2[FORCES ? kBwdWarps : 1][16 * 4];
+  // per-warp scratch, one slot per out-edge of the current chunk of 32: a_l = w Y_l | norm-path flag | (forces) w Y'_l
+  __shared__ __align__(16) float s_a[kBwdWarps][33 * 4];  // (+1: the coefficient prefetch reads one slot ahead)
+  __shared__ float s_f[kBwdWarps][32];
+  __shared__ __align__(16) float s_a2[FORCES ? kBwdWarps : 1][FORCES ? 33 * 4 : 4];
   __shared__ float s_st[FORCES ? kBwdWarps : 1][FORCES ? kJS * 3 : 1];  // per-warp partials of d unit[e_j] (s->t role)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -295,210 +347,197 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
   }
   float* sa = s_a[warp];
   float* sf = s_f[warp];
-  const int jj_mine = lane & 7, rr_mine = (lane >> 3) & (RI - 1);  // coefficient duty: pair (out j0+jj, in i0+rr); lanes >= 16 mirror
   const int jsub = bfly8_index(lane);
   bool okc[V4];
 #pragma unroll
   for (int v = 0; v < V4; ++v) okc[v] = FULL || (lane + 32 * v) * 4 < C;
 
-  for (int i0 = warp * RI; i0 < dI; i0 += kBwdWarps * RI) {
-    float4 gb[RI][NL][V4], dacc[RI][NL][V4], gt[RI][V4];
-    float h[RI][NP];
-    int ep[RI];
+  for (int i = warp; i < dI; i += kBwdWarps) {  // one in-edge per warp at a time
+    const int ep = in_edge[ib + i], k = in_src[ib + i];
+    float4 gb[NL][V4], dacc[NL][V4], gt[V4];
+    float h[NP];
 #pragma unroll
-    for (int rr = 0; rr < RI; ++rr) {
-      const int pos = ib + min(i0 + rr, dI - 1);
-      ep[rr] = in_edge[pos];
-      const int k = in_src[pos];
+    for (int v = 0; v < V4; ++v) {
+      const int c = (lane + 32 * v) * 4;
+      gt[v] = okc[v] ? ldg4(gate + (int64_t)k * ldg + c) : zero4();
 #pragma unroll
-      for (int v = 0; v < V4; ++v) {
-        const int c = (lane + 32 * v) * 4;
-        gt[rr][v] = okc[v] ? ldg4(gate + (int64_t)k * ldg + c) : zero4();
-#pragma unroll
-        for (int l = 0; l < NL; ++l) {
-          gb[rr][l][v] = okc[v] ? mul4(gt[rr][v], ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c)) : zero4();
-          dacc[rr][l][v] = zero4();
-        }
+      for (int l = 0; l < NL; ++l) {
+        gb[l][v] = okc[v] ? mul4(gt[v], ldg4(B + ((int64_t)ep * NG + l) * C + c)) : zero4();
+        dacc[l][v] = zero4();
       }
-#pragma unroll
-      for (int p = 0; p < NP; ++p) h[rr][p] = 0.f;
     }
-    // this lane's in-edge for the coefficient duty
-    const int epc = ep[rr_mine];
-    const bool in_live = i0 + rr_mine < dI;
-    const float vx = unit[3 * (int64_t)epc], vy = unit[3 * (int64_t)epc + 1], vz = unit[3 * (int64_t)epc + 2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) h[p] = 0.f;
+    const float vx = unit[3 * (int64_t)ep], vy = unit[3 * (int64_t)ep + 1], vz = unit[3 * (int64_t)ep + 2];
     double g[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)epc * NP + p];
+    for (int p = 0; p < NP; ++p) g[p] = gram[(int64_t)ep * NP + p];
     float ks_x = 0.f, ks_y = 0.f, ks_z = 0.f;  // FORCES: d unit[e_i] partial of this lane (k->s role)
 
-    for (int oc = 0; oc < dO; oc += 32) {  // the node's out-edge ids, 32 at a time, one per lane
+    for (int oc = 0; oc < dO; oc += 32) {  // the node's out-edges, 32 at a time: lane <-> out-edge oc + lane
       const int nO = min(32, dO - oc);
       const int my_ej = out_edge[ob + oc + min(lane, nO - 1)];
+      // ---- coefficients of the pairs (out-edge oc + lane, this in-edge): one pair per lane, once per chunk
+      const float ox = unit[3 * (int64_t)my_ej], oy = unit[3 * (int64_t)my_ej + 1], oz = unit[3 * (int64_t)my_ej + 2];
+      const float cc = fmaf(ox, vx, fmaf(oy, vy, oz * vz));
+      float Y[4];
+      sph_harm<NL>(cc, Y);
+      const float nrm = sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f));
+      const bool live = lane < nO && my_ej != ep;
+      const float ww = live ? 1.0f / fmaxf(nrm, kEps) : 0.f;
+      const float fl = (live && nrm > kEps) ? 1.f : 0.f;
+      __syncwarp();  // the previous chunk's readers are done
+      st4(sa + lane * 4, make_float4(ww * Y[0], ww * Y[1], ww * Y[2], ww * Y[3]));
+      sf[lane] = fl;
+      if constexpr (FORCES) {
+        float dY[4];
+        sph_harm_grad<NL>(cc, dY);
+        st4(s_a2[warp] + lane * 4, make_float4(ww * dY[0], ww * dY[1], ww * dY[2], ww * dY[3]));
+      }
+      __syncwarp();
       for (int j0 = 0; j0 < nO; j0 += 8) {
-        // ---- coefficients of the 2 x 8 pairs of this batch
-        const int ej = __shfl_sync(0xffffffffu, my_ej, min(j0 + jj_mine, nO - 1));
-        const float ox = unit[3 * (int64_t)ej], oy = unit[3 * (int64_t)ej + 1], oz = unit[3 * (int64_t)ej + 2];
-        const float cc = fmaf(ox, vx, fmaf(oy, vy, oz * vz));
-        float Y[4];
-        sph_harm<NL>(cc, Y);
-        const float nrm = sqrtf(fmaxf((float)quad_form<NL>(g, Y), 0.f));
-        const bool live = in_live && j0 + jj_mine < nO && ej != epc;
-        const float ww = live ? 1.0f / fmaxf(nrm, kEps) : 0.f;
-        const float fl = (live && nrm > kEps) ? 1.f : 0.f;
-        const float4 a = make_float4(ww * Y[0], ww * Y[1], ww * Y[2], ww * Y[3]);
-        __syncwarp();
-        if (lane < 8 * RI) {
-          st4(sa + lane * 4, a);
-          sf[lane] = fl;
-          if constexpr (FORCES) {
-            float dY[4];
-            sph_harm_grad<NL>(cc, dY);
-            st4(s_a2[warp] + lane * 4, make_float4(ww * dY[0], ww * dY[1], ww * dY[2], ww * dY[3]));
-          }
-        }
-        __syncwarp();
-        // ---- d_tbw rows of the batch (all loads first)
+        const int nj = min(8, nO - j0);
+        // ---- d_tbw rows of the batch (all loads first).  GUARD: dead slots (jj >= nj) are SKIPPED by warp-uniform
+        //      branches (a clamped slot costs as many issue slots as a live one) and the coefficients are fetched one
+        //      slot ahead, so that no block starts by waiting on shared memory; !GUARD: dead slots read a clamped row
+        //      and carry zero coefficients (branch-free)
         float4 gr[8][V4];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const int e = __shfl_sync(0xffffffffu, my_ej, min(j0 + jj, nO - 1));
+          if (!GUARD || jj < nj) {
+            const int e = __shfl_sync(0xffffffffu, my_ej, GUARD ? j0 + jj : min(j0 + jj, nO - 1));
 #pragma unroll
-          for (int v = 0; v < V4; ++v) gr[jj][v] = okc[v] ? ldg4(d_tbw + (int64_t)e * C + (lane + 32 * v) * 4) : zero4();
+            for (int v = 0; v < V4; ++v) gr[jj][v] = okc[v] ? ldg4(d_tbw + (int64_t)e * C + (lane + 32 * v) * 4) : zero4();
+          }
         }
-        float part[RI][8], part2[FORCES ? RI : 1][8];
+        float part[8], part2[FORCES ? 8 : 1];
+        float4 ar = lds4(sa + j0 * 4), ar2;
+        if constexpr (FORCES) ar2 = lds4(s_a2[warp] + j0 * 4);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-#pragma unroll
-          for (int rr = 0; rr < RI; ++rr) {
-            const float4 ar = lds4(sa + (rr * 8 + jj) * 4);
-            float4 ar2;
-            if constexpr (FORCES) ar2 = lds4(s_a2[warp] + (rr * 8 + jj) * 4);
+          part[jj] = 0.f;
+          if constexpr (FORCES) part2[jj] = 0.f;
+          if (!GUARD || jj < nj) {
+            const float4 ar_next = lds4(sa + (j0 + jj + 1) * 4);
+            float4 ar2_next;
+            if constexpr (FORCES) ar2_next = lds4(s_a2[warp] + (j0 + jj + 1) * 4);
             float d = 0.f, d2 = 0.f;
 #pragma unroll
             for (int v = 0; v < V4; ++v) {
-              float4 t = scale4(ar.x, gb[rr][0][v]);
-              if (NL > 1) t = fma4(ar.y, gb[rr][1][v], t);
-              if (NL > 2) t = fma4(ar.z, gb[rr][2][v], t);
-              if (NL > 3) t = fma4(ar.w, gb[rr][3][v], t);
+              float4 t = scale4(ar.x, gb[0][v]);
+              if (NL > 1) t = fma4(ar.y, gb[1][v], t);
+              if (NL > 2) t = fma4(ar.z, gb[2][v], t);
+              if (NL > 3) t = fma4(ar.w, gb[3][v], t);
               d += dot4(t, gr[jj][v]);
               if constexpr (FORCES) {
-                float4 t2 = scale4(ar2.x, gb[rr][0][v]);
-                if (NL > 1) t2 = fma4(ar2.y, gb[rr][1][v], t2);
-                if (NL > 2) t2 = fma4(ar2.z, gb[rr][2][v], t2);
-                if (NL > 3) t2 = fma4(ar2.w, gb[rr][3][v], t2);
+                float4 t2 = scale4(ar2.x, gb[0][v]);
+                if (NL > 1) t2 = fma4(ar2.y, gb[1][v], t2);
+                if (NL > 2) t2 = fma4(ar2.z, gb[2][v], t2);
+                if (NL > 3) t2 = fma4(ar2.w, gb[3][v], t2);
                 d2 += dot4(t2, gr[jj][v]);
               }
-              dacc[rr][0][v] = fma4(ar.x, gr[jj][v], dacc[rr][0][v]);
-              if (NL > 1) dacc[rr][1][v] = fma4(ar.y, gr[jj][v], dacc[rr][1][v]);
-              if (NL > 2) dacc[rr][2][v] = fma4(ar.z, gr[jj][v], dacc[rr][2][v]);
-              if (NL > 3) dacc[rr][3][v] = fma4(ar.w, gr[jj][v], dacc[rr][3][v]);
+              dacc[0][v] = fma4(ar.x, gr[jj][v], dacc[0][v]);
+              if (NL > 1) dacc[1][v] = fma4(ar.y, gr[jj][v], dacc[1][v]);
+              if (NL > 2) dacc[2][v] = fma4(ar.z, gr[jj][v], dacc[2][v]);
+              if (NL > 3) dacc[3][v] = fma4(ar.w, gr[jj][v], dacc[3][v]);
             }
-            part[rr][jj] = d;
-            if constexpr (FORCES) part2[rr][jj] = d2;
+            part[jj] = d;
+            if constexpr (FORCES) part2[jj] = d2;
+            ar = ar_next;
+            if constexpr (FORCES) ar2 = ar2_next;
           }
         }
-        // ---- per pair scalars: the quad `jsub` of the warp finishes pair (j0 + jsub, i0 + rr)
-        float dotv[RI], dot2v[FORCES ? RI : 1];
-#pragma unroll
-        for (int rr = 0; rr < RI; ++rr) {
-          dotv[rr] = bfly8(part[rr], lane);
-          if constexpr (FORCES) dot2v[rr] = bfly8(part2[rr], lane);
-          const int slot = rr * 8 + jsub;
+        // ---- per pair scalars: the quad `jsub` of the warp finishes pair (out j0 + jsub, this in-edge)
+        const float dotv = bfly8(part, lane);
+        {
+          const int slot = j0 + jsub;  // dead slots carry a = 0, flag = 0 and a zero dot
           const float4 ar = lds4(sa + slot * 4);
-          const float sc = -sf[slot] * dotv[rr];  // 0 for dead / clamped pairs
+          const float sc = -sf[slot] * dotv;
           int p = 0;
 #pragma unroll
           for (int x = 0; x < NL; ++x)
 #pragma unroll
-            for (int y = x; y < NL; ++y) h[rr][p++] += sc * comp4(ar, x) * comp4(ar, y);
+            for (int y = x; y < NL; ++y) h[p++] += sc * comp4(ar, x) * comp4(ar, y);
         }
         if constexpr (FORCES) {
-          // dL/dcos of pair (j0 + jj, i0 + rr) is finished on its coefficient lane rr*8 + jj, which still holds the
-          // pair's cos / w / flag, both directions and the Gram matrix; the two dots come from the quad that owns
-          // butterfly element jj (lane bits 4,3,2 = bits 2,1,0 of jj).
-          const int srcl = (((jj_mine >> 2) & 1) << 4) | (((jj_mine >> 1) & 1) << 3) | ((jj_mine & 1) << 2);
-#pragma unroll
-          for (int rr = 0; rr < RI; ++rr) {
-            const float dt = __shfl_sync(0xffffffffu, dotv[rr], srcl);
-            const float dt2 = __shfl_sync(0xffffffffu, dot2v[rr], srcl);
-            if (lane < 8 * RI && rr_mine == rr && live) {
-              float dY[4];
-              sph_harm_grad<NL>(cc, dY);
-              const float corr = (float)bilin_form<NL>(g, dY, Y);
-              const float dc = dt2 - fl * ww * ww * dt * corr;
-              ks_x = fmaf(dc, ox, ks_x); ks_y = fmaf(dc, oy, ks_y); ks_z = fmaf(dc, oz, ks_z);
-              const int j = oc + j0 + jj_mine;
-              if (j < kJS) {
-                s_st[warp][3 * j] = fmaf(dc, vx, s_st[warp][3 * j]);
-                s_st[warp][3 * j + 1] = fmaf(dc, vy, s_st[warp][3 * j + 1]);
-                s_st[warp][3 * j + 2] = fmaf(dc, vz, s_st[warp][3 * j + 2]);
-              } else {
-                atomicAdd(du_st + 3 * (int64_t)ej, dc * vx);
-                atomicAdd(du_st + 3 * (int64_t)ej + 1, dc * vy);
-                atomicAdd(du_st + 3 * (int64_t)ej + 2, dc * vz);
-              }
+          // dL/dcos of pair (j0 + jl) is finished on its coefficient lane j0 + jl, which still holds the pair's cos /
+          // w / flag and both directions; the two dots come from the quad that owns butterfly element jl (lane bits
+          // 4,3,2 = bits 2,1,0 of jl).
+          const float dot2v = bfly8(part2, lane);
+          const int jl = (lane - j0) & 7;
+          const int srcl = (((jl >> 2) & 1) << 4) | (((jl >> 1) & 1) << 3) | ((jl & 1) << 2);
+          const float dt = __shfl_sync(0xffffffffu, dotv, srcl);
+          const float dt2 = __shfl_sync(0xffffffffu, dot2v, srcl);
+          if (lane >= j0 && lane < j0 + nj && live) {
+            float dY[4];
+            sph_harm_grad<NL>(cc, dY);
+            const float corr = (float)bilin_form<NL>(g, dY, Y);
+            const float dc = dt2 - fl * ww * ww * dt * corr;
+            ks_x = fmaf(dc, ox, ks_x); ks_y = fmaf(dc, oy, ks_y); ks_z = fmaf(dc, oz, ks_z);
+            const int j = oc + lane;
+            if (j < kJS) {  // slot j of this warp's partials is only ever touched by this lane
+              s_st[warp][3 * j] = fmaf(dc, vx, s_st[warp][3 * j]);
+              s_st[warp][3 * j + 1] = fmaf(dc, vy, s_st[warp][3 * j + 1]);
+              s_st[warp][3 * j + 2] = fmaf(dc, vz, s_st[warp][3 * j + 2]);
+            } else {
+              atomicAdd(du_st + 3 * (int64_t)my_ej, dc * vx);
+              atomicAdd(du_st + 3 * (int64_t)my_ej + 1, dc * vy);
+              atomicAdd(du_st + 3 * (int64_t)my_ej + 2, dc * vz);
             }
-            __syncwarp();  // the two rr passes update the same s_st rows
           }
         }
       }
     }
-    // ---- finish the in-edges of this warp
+    // ---- finish this in-edge
     if constexpr (FORCES) {
-      // lanes 0-7 hold in-edge i0, lanes 8-15 in-edge i0+1: sum the 8 out-edge slots of each
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 32; o <<= 1) {
         ks_x += __shfl_xor_sync(0xffffffffu, ks_x, o);
         ks_y += __shfl_xor_sync(0xffffffffu, ks_y, o);
         ks_z += __shfl_xor_sync(0xffffffffu, ks_z, o);
       }
-      if (lane < 8 * RI && jj_mine == 0 && in_live) {
-        du_ks[3 * (int64_t)epc] = ks_x; du_ks[3 * (int64_t)epc + 1] = ks_y; du_ks[3 * (int64_t)epc + 2] = ks_z;
+      if (lane == 0) {
+        du_ks[3 * (int64_t)ep] = ks_x; du_ks[3 * (int64_t)ep + 1] = ks_y; du_ks[3 * (int64_t)ep + 2] = ks_z;
       }
     }
 #pragma unroll
-    for (int rr = 0; rr < RI; ++rr) {
-      if (i0 + rr >= dI) continue;  // warp-uniform
+    for (int p = 0; p < NP; ++p) {  // h was accumulated by one lane quad per out-edge slot: add the 8 slots
+      float x = h[p];
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      h[p] = x;
+    }
+    float H[NL][NL];
+    {
+      int p = 0;
 #pragma unroll
-      for (int p = 0; p < NP; ++p) {  // h was accumulated by one lane quad per out-edge slot: add the 8 slots
-        float x = h[rr][p];
-        x += __shfl_xor_sync(0xffffffffu, x, 4);
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
-        h[rr][p] = x;
-      }
-      float H[NL][NL];
-      {
-        int p = 0;
+      for (int x = 0; x < NL; ++x)
 #pragma unroll
-        for (int x = 0; x < NL; ++x)
+        for (int y = x; y < NL; ++y) { H[x][y] = h[p]; H[y][x] = h[p]; ++p; }
+    }
 #pragma unroll
-          for (int y = x; y < NL; ++y) { H[x][y] = h[rr][p]; H[y][x] = h[rr][p]; ++p; }
-      }
+    for (int v = 0; v < V4; ++v) {
+      const int c = (lane + 32 * v) * 4;
+      if (okc[v]) {
+        float4 b[NL];
 #pragma unroll
-      for (int v = 0; v < V4; ++v) {
-        const int c = (lane + 32 * v) * 4;
-        if (okc[v]) {
-          float4 b[NL];
+        for (int l = 0; l < NL; ++l) b[l] = ldg4(B + ((int64_t)ep * NG + l) * C + c);
+        float4 qq = zero4();
+        const float4 two_body = dP ? ldg4(dP + (int64_t)ep * NGP * C + c) : zero4();  // same for every l < NL
 #pragma unroll
-          for (int l = 0; l < NL; ++l) b[l] = ldg4(B + ((int64_t)ep[rr] * NG + l) * C + c);
-          float4 qq = zero4();
-          const float4 two_body = dP ? ldg4(dP + (int64_t)ep[rr] * NGP * C + c) : zero4();  // same for every l < NL
+        for (int l = 0; l < NL; ++l) {
+          float4 o4 = fma4(1.0f, mul4(gt[v], dacc[l][v]), two_body);
 #pragma unroll
-          for (int l = 0; l < NL; ++l) {
-            float4 o4 = fma4(1.0f, mul4(gt[rr][v], dacc[rr][l][v]), two_body);
-#pragma unroll
-            for (int l2 = 0; l2 < NL; ++l2) o4 = fma4(H[l][l2], b[l2], o4);
-            st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, o4);
-            qq = add4(qq, mul4(b[l], dacc[rr][l][v]));
-          }
-          const float4 sg = gt[rr][v];
-          qq = mul4(qq, make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w)));
-          st4(q + (int64_t)ep[rr] * C + c, qq);
-          for (int l = NL; l < NG; ++l)
-            st4(dB + ((int64_t)ep[rr] * NG + l) * C + c, dP ? ldg4(dP + ((int64_t)ep[rr] * NGP + 1) * C + c) : zero4());
+          for (int l2 = 0; l2 < NL; ++l2) o4 = fma4(H[l][l2], b[l2], o4);
+          st4(dB + ((int64_t)ep * NG + l) * C + c, o4);
+          qq = add4(qq, mul4(b[l], dacc[l][v]));
         }
+        const float4 sg = gt[v];
+        qq = mul4(qq, make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w)));
+        st4(q + (int64_t)ep * C + c, qq);
+        for (int l = NL; l < NG; ++l)
+          st4(dB + ((int64_t)ep * NG + l) * C + c, dP ? ldg4(dP + ((int64_t)ep * NGP + 1) * C + c) : zero4());
       }
     }
   }
@@ -546,16 +585,11 @@ extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram
                "lcao_threebody_fwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL (C=%d NL=%d NG=%d)", C, NL, NG);
   cudaStream_t st = (cudaStream_t)stream;
   const int V4 = C <= 128 ? 1 : 2;
-  const bool full = false;  // (the predicate-free specialisation measured SLOWER in the forward: 0.291 vs 0.260 ms)
   static const int per_sm_f = tile_in("LCAO_TB_GRID_FWD", 48, 1, 64);
   const unsigned grid = (unsigned)(N < 148ll * per_sm_f ? N : 148ll * per_sm_f);
-#define CALL(nl, v4)                                                                                                    \
-  if (full)                                                                                                             \
-    k_threebody_fwd<nl, v4, true><<<grid, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, \
-                                                                          in_src, out_ptr, out_edge, (int)N, C, tbw);           \
-  else                                                                                                                  \
-    k_threebody_fwd<nl, v4, false><<<grid, kFwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,        \
-                                                                           in_edge, in_src, out_ptr, out_edge, (int)N, C, tbw)
+  // (the predicate-free specialisation FULL measured SLOWER in the forward: 0.291 vs 0.260 ms)
+#define TB_FWD_ARGS B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, (int)N, C, tbw
+#define CALL(nl, v4) k_threebody_fwd<nl, v4, false><<<grid, kFwdWarps * 32, 0, st>>>(TB_FWD_ARGS)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();
@@ -577,31 +611,22 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   cudaStream_t st = (cudaStream_t)stream;
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
-  static const int ri = tile_in("LCAO_TB_RI", kRI, 1, 2);
   const bool full = C == 128 * V4;
   static const int per_sm_b = tile_in("LCAO_TB_GRID_BWD", 24, 1, 64);
+  static const bool guard = tile_in("LCAO_TB_BWD_GUARD", 0, 0, 1) != 0;
   const unsigned grid = (unsigned)(N < 148ll * per_sm_b ? N : 148ll * per_sm_b);
-#define CALL(nl, v4)                                                                                                   \
-  if (forces)                                                                                                          \
-    k_threebody_bwd<nl, v4, true, 1, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg, in_ptr,     \
-                                                                             in_edge, in_src, out_ptr, out_edge,       \
-                                                                             (int)N, C, d_tbw, dP, dB, q, d_unit_ks,   \
-                                                                             d_unit_st);                               \
-  else if (ri == 1 && full)                                                                                            \
-    k_threebody_bwd<nl, v4, false, 1, true><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,      \
-                                                                                    in_ptr, in_edge, in_src, out_ptr,  \
-                                                                                    out_edge, (int)N, C, d_tbw, dP, dB, q,     \
-                                                                                    nullptr, nullptr);                 \
-  else if (ri == 1)                                                                                                    \
-    k_threebody_bwd<nl, v4, false, 1, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
-                                                                                     in_ptr, in_edge, in_src, out_ptr, \
-                                                                                     out_edge, (int)N, C, d_tbw, dP, dB, q,    \
-                                                                                     nullptr, nullptr);                \
-  else                                                                                                                 \
-    k_threebody_bwd<nl, v4, false, 2, false><<<grid, kBwdWarps * 32, 0, st>>>(B, NG, gram, unit, gate, ldg,     \
-                                                                                     in_ptr, in_edge, in_src, out_ptr, \
-                                                                                     out_edge, (int)N, C, d_tbw, dP, dB, q,    \
-                                                                                     nullptr, nullptr)
+#define TB_BWD_ARGS B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, (int)N, C, d_tbw, dP, dB, q
+#define CALL(nl, v4)                                                                                              \
+  if (forces && guard)                                                                                            \
+    k_threebody_bwd<nl, v4, true, false, true><<<grid, kBwdWarps * 32, 0, st>>>(TB_BWD_ARGS, d_unit_ks, d_unit_st);  \
+  else if (forces)                                                                                                \
+    k_threebody_bwd<nl, v4, true, false, false><<<grid, kBwdWarps * 32, 0, st>>>(TB_BWD_ARGS, d_unit_ks, d_unit_st); \
+  else if (full && guard)                                                                                         \
+    k_threebody_bwd<nl, v4, false, true, true><<<grid, kBwdWarps * 32, 0, st>>>(TB_BWD_ARGS, nullptr, nullptr);   \
+  else if (full)                                                                                                  \
+    k_threebody_bwd<nl, v4, false, true, false><<<grid, kBwdWarps * 32, 0, st>>>(TB_BWD_ARGS, nullptr, nullptr);  \
+  else                                                                                                            \
+    k_threebody_bwd<nl, v4, false, false, false><<<grid, kBwdWarps * 32, 0, st>>>(TB_BWD_ARGS, nullptr, nullptr)
   TB_DISPATCH(NL, V4, CALL)
 #undef CALL
   LCAO_LAUNCH_CHECK();

@@ -424,6 +424,12 @@ def _lin_dgrad(dy, ldy, M, w, dx, ldx, accumulate, st):
     _call("lcao_linear_dgrad", ptr(dy), ldy, None, 0, ACT_NONE, ptr(w), ptr(dx), ldx, M, K, Nout, accumulate, _gemm_mode, None, st)
 
 
+def _lin_dgrad_act(dy, ldy, M, w, pre_in, dx, ldx, st):
+    """dx = (dy W) * SiLU'(pre_in): data gradient chained through the activation that produced the layer's input."""
+    Nout, K = w.shape
+    _call("lcao_linear_dgrad_act", ptr(dy), ldy, ptr(w), ptr(pre_in), K, ACT_SILU, ptr(dx), ldx, M, K, Nout, _gemm_mode, st)
+
+
 def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
     """dW (+ db) of one layer.  With sinks (the parameters' .grad buffers) the kernels accumulate straight into them
     — the C ABI's `dW +=` contract — and (None, None) is returned: no zero-fill, no separate accumulation pass."""
@@ -494,22 +500,24 @@ class _InteractionLayer(torch.autograd.Function):
         pre_a = torch.empty(E, C, device=dev) if grad else None
         _call("lcao_edge_pair_fwd", ptr(u), 2 * C, u.data_ptr() + 4 * C, 2 * C, ptr(b_1), ptr(gi.src32), ptr(gi.dst32), E, C,
               ACT_SILU, ptr(a1), ptr(pre_a), st)
-        h, pre_h = _lin_fwd(a1, C, E, w_2, b_2, ACT_SILU, st, grad)
+        # h = SiLU(pre_h) is never stored: the message sum and its backward apply the activation on the fly, which takes
+        # one E x C write off the f_node GEMM and one E x C read off each consumer
+        pre_h, _ = _lin_fwd(a1, C, E, w_2, b_2, ACT_NONE, st, False)
         agg = torch.empty(N, C, device=dev)
-        _call("lcao_segment_sum", ptr(bw), C, ptr(h), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 0, ptr(agg), C, st)
+        _call("lcao_segment_sum", ptr(bw), C, ptr(pre_h), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 2, ptr(agg), C, st)
         y, _ = _lin_fwd(agg, C, N, w_o, None, ACT_NONE, st, False)
         out = x + y
         if grad:
             ctx.aux = aux
             ctx.save_for_backward(x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2,
-                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, h, pre_h, agg, psum)
+                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, pre_h, agg, psum)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
-         lw, bw, a1, pre_a, h, pre_h, agg, psum) = ctx.saved_tensors
+         lw, bw, a1, pre_a, pre_h, agg, psum) = ctx.saved_tensors
         pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = ctx.aux
         # gradient sinks: the parameters' own .grad buffers (order: w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o)
         s_wn, s_bn, s_wc0, s_wc2, s_w3, s_wb, s_w1, s_b1, s_w2, s_b2, s_wo = sinks if sinks is not None else (None,) * 11
@@ -528,16 +536,16 @@ class _InteractionLayer(torch.autograd.Function):
         _lin_dgrad(d_out, H, N, w_o, d_agg, C, 0, st)
         # agg[s] = sum_{e in out(s)} bw[e] * h[e]
         d_bw, d_preh = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
-        _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), ptr(h), ptr(bw), ptr(pre_h), E, C, ptr(d_bw), ptr(d_preh), st)
+        _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), None, ptr(bw), ptr(pre_h), E, C, ptr(d_bw), ptr(d_preh), st)
         # h = silu(f_node.2(a1)) ; a1 = silu(u_a[s] + u_b[t] + b1)
         dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st, s_w2, s_b2)
+        # d_prea = d_a1 * SiLU'(pre_a) is never materialised: the two segment sums over it apply the factor on the fly
         d_a1 = torch.empty(E, C, device=dev)
         _lin_dgrad(d_preh, C, E, w_2, d_a1, C, 0, st)
-        d_prea = _act_bwd(d_a1, pre_a, E, C, st)
         d_u = torch.empty(N, 2 * C, device=dev)
-        _call("lcao_segment_sum", ptr(d_prea), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 0, ptr(d_u), 2 * C, st)
-        _call("lcao_segment_sum", ptr(d_prea), C, None, 0, ptr(gi.in_ptr), ptr(gi.in_edge), N, C, 0, d_u.data_ptr() + 4 * C,
-              2 * C, st)
+        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 4, ptr(d_u), 2 * C, st)
+        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.in_ptr), ptr(gi.in_edge), N, C, 4,
+              d_u.data_ptr() + 4 * C, 2 * C, st)
         d_nw = torch.empty(N, 2 * C, device=dev)
         _lin_dgrad(d_u, 2 * C, N, w_1cat, d_nw, 2 * C, 0, st)  # writes d_xc = d_nw[:, :C]
         # the bias b_1 enters once per edge through the u_a half: d b_1 = column sums of d_u[:, :C]
@@ -560,7 +568,7 @@ class _InteractionLayer(torch.autograd.Function):
         d_tbw = d_bw  # reuse
         _lin_dgrad(d_g, Cp, E, w_3, d_tbw, C, 0, st)
         dB = torch.empty(E, NG, C, device=dev)
-        q = d_prea  # reuse
+        q = d_a1  # reuse
         du_ks = torch.empty(E, 3, device=dev) if need_unit else None
         du_st = torch.empty(E, 3, device=dev) if need_unit else None
         _call("lcao_threebody_bwd", ptr(B), NG, ptr(gram), ptr(unit), ptr(gate), C, ptr(gi.in_ptr), ptr(gi.in_edge),
@@ -579,9 +587,8 @@ class _InteractionLayer(torch.autograd.Function):
               P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), st)
         d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st)
         dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st, s_wc2)
-        d_t1 = torch.empty(P * O, C, device=dev)
-        _lin_dgrad(d_pre2, Cp, P * O, w_c2, d_t1, C, 0, st)
-        d_pre1 = _act_bwd(d_t1, pre1, P * O, C, st)
+        d_pre1 = torch.empty(P * O, C, device=dev)
+        _lin_dgrad_act(d_pre2, Cp, P * O, w_c2, pre1, d_pre1, C, st)
         dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st, s_wc0)
         d_table = torch.empty(P, O, K, device=dev)
         _lin_dgrad(d_pre1, C, P * O, w_c0, d_table, K, 0, st)

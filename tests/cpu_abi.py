@@ -473,11 +473,15 @@ def lcao_segment_sum(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo, stream):
     n_src = (int(pm.max()) + 1) if n else 0
     X = view(x, n_src, C, ld=ldx)
     if y:
-        X = X * view(y, n_src, C, ld=ldy)
+        Y = view(y, n_src, C, ld=ldy)
+        if mean & 4:
+            sg = torch.sigmoid(Y)
+            Y = sg * (1 + Y * (1 - sg))
+        X = X * (torch.nn.functional.silu(Y) if (mean & 2) else Y)
     O = view(out, R, C, ld=ldo)
     for r in range(R):
         seg = X[pm[p[r]:p[r + 1]]].sum(0)
-        O[r] = seg / max(int(p[r + 1] - p[r]), 1) if mean else seg
+        O[r] = seg / max(int(p[r + 1] - p[r]), 1) if (mean & 1) else seg
 
 
 def lcao_msg_bwd(d_agg, lda, src32, h, bw, pre_h, E, C, d_bw, d_pre_h, stream):
@@ -485,7 +489,7 @@ def lcao_msg_bwd(d_agg, lda, src32, h, bw, pre_h, E, C, d_bw, d_pre_h, stream):
     g = view(d_agg, int(s.max()) + 1, C, ld=lda)[s]
     p = view(pre_h, E, C)
     sg = torch.sigmoid(p)
-    view(d_bw, E, C).copy_(g * view(h, E, C))
+    view(d_bw, E, C).copy_(g * (view(h, E, C) if h else p * sg))
     view(d_pre_h, E, C).copy_(g * view(bw, E, C) * (sg * (1 + p * (1 - sg))))
 
 
@@ -529,6 +533,13 @@ def lcao_linear_dgrad(dY, ldy, H, ldh, act, W, dX, ldx, M, K, Nout, accumulate, 
     v = _dy_eff(dY, ldy, H, ldh, act, M, Nout) @ view(W, Nout, K)
     o = view(dX, M, K, ld=ldx)
     o.copy_(o + v if accumulate else v)
+
+
+def lcao_linear_dgrad_act(dY, ldy, W, G, ldg, act, dX, ldx, M, K, Nout, mode, stream):
+    v = view(dY, M, Nout, ld=ldy) @ view(W, Nout, K)
+    h = view(G, M, K, ld=ldg)
+    sg = torch.sigmoid(h)
+    view(dX, M, K, ld=ldx).copy_(v * (sg * (1 + h * (1 - sg))))
 
 
 def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, scratch, stream):

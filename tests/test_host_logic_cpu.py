@@ -81,8 +81,9 @@ def test_autograd_forces_match_reference(monkeypatch):
 
 @pytest.mark.parametrize("name", ["qm9_valence_ext_2perorb", "crystal_autograd_forces"])
 def test_op_by_op_path_equals_single_node_path(name, monkeypatch):
-    """LCAOInteraction as one autograd node (ops.interaction_layer) vs one node per kernel: same kernels, same
-    order -> identical energies and gradients."""
+    """LCAOInteraction as one autograd node (ops.interaction_layer) vs one node per kernel: the same arithmetic up to
+    the single-node path's fusions (h = SiLU(pre_h) recomputed by its consumers, SiLU' folded into the dgrad epilogue),
+    so energies, forces and gradients agree to FP32 rounding."""
     res = []
     for fused in (True, False):
         cpu_abi.install(monkeypatch)
@@ -97,7 +98,7 @@ def test_op_by_op_path_equals_single_node_path(name, monkeypatch):
         res.append((out, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
     (o1, g1), (o2, g2) = res
     if isinstance(o1, tuple):
-        assert rel_l2(o1[1], o2[1]) < 1e-6
+        assert rel_l2(o1[1], o2[1]) < 1e-5
         o1, o2 = o1[0], o2[0]
     assert rel_l2(o1, o2) < 1e-6 and g1.keys() == g2.keys()
     for n in g1:
