@@ -78,7 +78,7 @@ int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int3
                            int32_t* in_ptr, int32_t* in_edge, int32_t* in_src, int32_t* out_ptr,
                            int32_t* out_edge, int32_t* tri_ptr, int32_t* scratch, void* stream);
 
-/* tri_ptr (E+1) alone, from an existing index; scratch: E int32. */
+/* tri_ptr (E+1) alone, from an existing index; scratch: E + ceil(E / 4096) int32. */
 int lcao_triplet_offsets(const int32_t* src32, const int32_t* dst32, const int32_t* in_ptr, int64_t E, int32_t* tri_ptr,
                          int32_t* scratch, void* stream);
 

@@ -32,23 +32,20 @@ __global__ void k_hist_f(const int64_t* __restrict__ keys, int64_t n, int64_t nb
   if (valid && (int)lane == __ffs(peers) - 1) atomicAdd(&cnt[k], (float)__popc(peers));  // integer-valued: exact below 2^24
 }
 
-// single-CTA exclusive scan; out has n+1 entries (out[n] = total).  in may alias out.  Every pass costs three block
-// barriers plus one global round trip (~2 us), so a thread takes IPT consecutive items per pass: 16 for the edge-sized
-// scans (E = 253 k: 124 us with 4 items per pass -> 16 passes instead of 62), 4 for the short ones.
-template <int IPT>
+// exclusive scan; out has n+1 entries (out[n] = total).  in may alias out.
+// One CTA scans 4096 items per pass; a single CTA walking an edge-sized array pays three block barriers plus a global
+// round trip per pass (124 us at E = 253 k), so arrays beyond one pass use the two-launch form below.
 __global__ void __launch_bounds__(1024) k_exscan(const int32_t* in, int64_t n, int32_t* out) {
   __shared__ int32_t wsum[32];
   __shared__ int32_t total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int32_t carry = 0;
-  for (int64_t base = 0; base < n; base += 1024 * IPT) {
-    int64_t idx = base + (int64_t)threadIdx.x * IPT;
-    int32_t v[IPT];
+  for (int64_t base = 0; base < n; base += 4096) {
+    int64_t idx = base + (int64_t)threadIdx.x * 4;
+    int32_t v[4];
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
-    int32_t tsum = 0;
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) tsum += v[j];
+    for (int j = 0; j < 4; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
+    int32_t tsum = v[0] + v[1] + v[2] + v[3];
     int32_t incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -70,7 +67,7 @@ __global__ void __launch_bounds__(1024) k_exscan(const int32_t* in, int64_t n, i
     __syncthreads();
     int32_t run = carry + wsum[w] + incl - tsum;
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
+    for (int j = 0; j < 4; ++j) {
       if (idx + j < n) out[idx + j] = run;
       run += v[j];
     }
@@ -79,9 +76,82 @@ __global__ void __launch_bounds__(1024) k_exscan(const int32_t* in, int64_t n, i
   }
   if (threadIdx.x == 0) out[n] = carry;
 }
-inline void launch_exscan(const int32_t* in, int64_t n, int32_t* out, cudaStream_t st) {
-  if (n > 16384) k_exscan<16><<<1, 1024, 0, st>>>(in, n, out);
-  else k_exscan<4><<<1, 1024, 0, st>>>(in, n, out);
+
+// Two-launch scan for long arrays: (1) every CTA sums its 4096-item block into bsum[b]; (2) every CTA adds up the
+// sums of the blocks before it (a few hundred at most: one strided pass + a block reduction), then scans its own
+// block from that carry.  bsum (ceil(n / 4096) entries) is caller-owned scratch.
+constexpr int kScanBlock = 4096;
+
+__device__ __forceinline__ int32_t block_sum_1024(int32_t v, int32_t* wsum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  int32_t t = wsum[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;  // every thread holds the block total
+}
+
+__global__ void __launch_bounds__(1024) k_scan_block_sums(const int32_t* in, int64_t n, int32_t* bsum) {
+  __shared__ int32_t wsum[32];
+  const int64_t idx = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * 4;
+  int32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s += (idx + j < n) ? in[idx + j] : 0;
+  s = block_sum_1024(s, wsum);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t* in, int64_t n, const int32_t* bsum, int32_t* out) {
+  __shared__ int32_t wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t c = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) c += bsum[b];
+  const int32_t carry = block_sum_1024(c, wsum);
+  const int64_t idx = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * 4;
+  int32_t v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = (idx + j < n) ? in[idx + j] : 0;
+  const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+  int32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int32_t s = wsum[lane], inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    wsum[lane] = inc - s;
+  }
+  __syncthreads();
+  int32_t run = carry + wsum[w] + incl - tsum;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (idx + j < n) out[idx + j] = run;
+    run += v[j];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) out[n] = run;  // the last thread's running sum is the total
+}
+
+// bsum: scratch of ceil(n / 4096) int32 (distinct from in / out), or nullptr for the single-CTA form
+inline void launch_exscan(const int32_t* in, int64_t n, int32_t* out, int32_t* bsum, cudaStream_t st) {
+  const int64_t nblk = (n + kScanBlock - 1) / kScanBlock;
+  if (nblk <= 2 || !bsum) {
+    k_exscan<<<1, 1024, 0, st>>>(in, n, out);
+  } else {
+    k_scan_block_sums<<<(unsigned)nblk, 1024, 0, st>>>(in, n, bsum);
+    k_scan_blocks<<<(unsigned)nblk, 1024, 0, st>>>(in, n, bsum, out);
+  }
 }
 
 __global__ void k_fill64(const int64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ ptr,
@@ -171,7 +241,7 @@ int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t
     k_hist64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, cursor);
     LCAO_LAUNCH_CHECK();
   }
-  launch_exscan(cursor, nb, ptr, st);
+  launch_exscan(cursor, nb, ptr, n >= (nb + kScanBlock - 1) / kScanBlock ? tmp : nullptr, st);  // tmp is free until the fill
   LCAO_LAUNCH_CHECK();
   if (n > 0) {
     LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
@@ -216,7 +286,7 @@ extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int6
       int32_t* cnt = scr_out;  // E entries, free after the out sort
       k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, cnt);
       LCAO_LAUNCH_CHECK();
-      launch_exscan(cnt, E, tri_ptr, st);
+      launch_exscan(cnt, E, tri_ptr, scr_in, st);  // scr_in (N + E entries) is free after the sorts
       LCAO_LAUNCH_CHECK();
     }
   } else if (tri_ptr) {
@@ -236,7 +306,7 @@ extern "C" int lcao_triplet_offsets(const int32_t* src32, const int32_t* dst32, 
   }
   k_tri_count<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src32, dst32, in_ptr, E, scratch);
   LCAO_LAUNCH_CHECK();
-  launch_exscan(scratch, E, tri_ptr, st);
+  launch_exscan(scratch, E, tri_ptr, scratch + E, st);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

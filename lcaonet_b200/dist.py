@@ -25,6 +25,9 @@ class FlatGradBucket:
         for m in module.modules():
             if hasattr(m, "grads_in_place"):
                 m.grads_in_place = True
+            # ... and the embedding block may replay its static-shape table arithmetic as CUDA graphs
+            if hasattr(m, "graph_tables") and self.flat.is_cuda:
+                m.graph_tables = True
 
     def zero(self) -> None:
         self.flat.zero_()

@@ -195,8 +195,14 @@ class LCAOEmbedding(nn.Module):
         self.node_embed = EmbedNode(emb_size, emb_size, use_elec, self.emb_size_node_e, activation, weight_init)
         self.coeff_embed = EmbedCoeffs(emb_size_coeff, emb_size_coeff, emb_size_coeff, elec_info.n_orb, activation,
                                        weight_init)
+        # training steps replay the static-shape table arithmetic (`_tables`) as CUDA graphs: ~220 launches of a few
+        # microseconds each become two graph launches (1.35 ms -> see profiles/r01_notes.md).  Opt-in.
+        self.graph_tables = False
 
-    def forward(self, z: Tensor, idx_s: Tensor, idx_t: Tensor) -> tuple[Tensor, Tensor]:
+    def _tables(self, cnt_z: Tensor, cnt_pair: Tensor) -> tuple[Tensor, Tensor]:
+        """The static-shape part of the block: parameters + species / species-pair counts -> the normalised node table
+        (Zd, H) and coefficient table (Zd^2, O*K).  Its ~80 forward and ~140 backward launches work on rows of a few
+        hundred floats; `graph_tables` replays them as two CUDA graphs."""
         H, K, Zd = self.emb_size, self.emb_size_coeff, self.max_z + 1
         ztab = self.z_embed.table()  # (Zd, H+K)
         etab = self.e_embed.table()  # (Zd, O, He+K)
@@ -207,28 +213,67 @@ class LCAOEmbedding(nn.Module):
             enc_in = torch.cat([node_z, node_e.sum(1) / math.sqrt(O)], dim=-1)
         else:
             coeff_e, enc_in = etab, node_z
-        # node embedding: species table -> BN with species counts -> gather
+        # node embedding: species table -> BN with species counts
         xtab = _mlp(self.node_embed.f_enc, enc_in.contiguous())
-        xtab = _weighted_batch_norm(self.node_embed.bn, xtab, ops.histogram(z, Zd), self.training)
-        need_bwd = torch.is_grad_enabled() and xtab.requires_grad
-        if H % 4 == 0:
-            x = ops.gather_rows(xtab.contiguous(), z, *(ops.bucket_sort(z, Zd, stable=False) if need_bwd else (None, None)))
-        else:
-            x = xtab[z]
-        # coefficient embedding: pair table (z_s, z_t) -> BN with pair counts -> row gather
+        xtab = _weighted_batch_norm(self.node_embed.bn, xtab, cnt_z, self.training)
+        # coefficient embedding: pair table (z_s, z_t) -> BN with pair counts
         wz = self.coeff_embed.f_z[0].weight  # (K, 2K) acting on [z_s ; z_t]
         za = ops.linear(coeff_z.contiguous(), wz[:, :K].contiguous())
         zb = ops.linear(coeff_z.contiguous(), wz[:, K:].contiguous())
         fe = _mlp(self.coeff_embed.f_e, coeff_e.contiguous())  # (Zd, O, K), orbitals of the TARGET element
         pre = fe.unsqueeze(0) * (1.0 + za[:, None, None, :] + zb[None, :, None, :])  # (Zd_s, Zd_t, O, K)
+        ctab = _weighted_batch_norm(self.coeff_embed.bn, pre.reshape(Zd * Zd, O * K), cnt_pair, self.training)
+        return xtab.contiguous(), ctab
+
+    def _graphed_tables(self, cnt_z: Tensor, cnt_pair: Tensor):
+        """`_tables` captured (forward and backward) by torch.cuda.make_graphed_callables, built on first use per
+        device.  Capture runs the function a few times, so the BatchNorm buffers are restored afterwards."""
+        key = (cnt_z.device, cnt_z.shape, cnt_pair.shape)
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        if key not in cache:
+            bufs = [b for bn in (self.node_embed.bn, self.coeff_embed.bn)
+                    for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if b is not None]
+            saved = [b.clone() for b in bufs]
+            holder = _EmbedTables(self)
+            cache[key] = torch.cuda.make_graphed_callables(holder, (cnt_z.clone(), cnt_pair.clone()),
+                                                           allow_unused_input=True)
+            with torch.no_grad():
+                for b, v in zip(bufs, saved):
+                    b.copy_(v)
+        return cache[key]
+
+    def forward(self, z: Tensor, idx_s: Tensor, idx_t: Tensor) -> tuple[Tensor, Tensor]:
+        H, Zd = self.emb_size, self.max_z + 1
         pair = z[idx_s] * Zd + z[idx_t]
-        ctab = _weighted_batch_norm(self.coeff_embed.bn, pre.reshape(Zd * Zd, O * K), ops.histogram(pair, Zd * Zd),
-                                    self.training)
+        cnt_z, cnt_pair = ops.histogram(z, Zd), ops.histogram(pair, Zd * Zd)
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.graph_tables and self.training and grad and z.is_cuda and all(p.requires_grad for p in self.parameters()):
+            xtab, ctab = self._graphed_tables(cnt_z, cnt_pair)(cnt_z, cnt_pair)
+        else:
+            xtab, ctab = self._tables(cnt_z, cnt_pair)
+        need_bwd = torch.is_grad_enabled() and xtab.requires_grad
+        if H % 4 == 0:
+            x = ops.gather_rows(xtab, z, *(ops.bucket_sort(z, Zd, stable=False) if need_bwd else (None, None)))
+        else:
+            x = xtab[z]
         if torch.is_grad_enabled() and ctab.requires_grad:
             kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
         else:
             kptr = kperm = None
-        return x, PairCoeffs(ctab.reshape(Zd * Zd, O, K), pair, kptr, kperm)
+        O = ctab.shape[1] // self.emb_size_coeff
+        return x, PairCoeffs(ctab.reshape(Zd * Zd, O, self.emb_size_coeff), pair, kptr, kperm)
+
+
+class _EmbedTables(nn.Module):
+    """LCAOEmbedding._tables as a module of its own (what torch.cuda.make_graphed_callables wants: the parameters are
+    found through `.parameters()`).  Never registered on the embedding block, so no state_dict entry and no cycle."""
+
+    def __init__(self, emb: "LCAOEmbedding"):
+        super().__init__()
+        self.emb = emb
+
+    def forward(self, cnt_z: Tensor, cnt_pair: Tensor):
+        return self.emb._tables(cnt_z, cnt_pair)
 
 
 class LCAOInteraction(nn.Module):

@@ -81,7 +81,7 @@ class GraphIndex:
         if self._tri_ptr is None:
             i32 = dict(dtype=torch.int32, device=self.src32.device)
             self._tri_ptr = torch.empty(self.E + 1, **i32)
-            scratch = torch.empty(max(self.E, 1), **i32)
+            scratch = torch.empty(self.E + self.E // 4096 + 2, **i32)
             _call("lcao_triplet_offsets", ptr(self.src32), ptr(self.dst32), ptr(self.in_ptr), self.E, ptr(self._tri_ptr),
                   ptr(scratch), stream_ptr())
         return self._tri_ptr

@@ -420,3 +420,48 @@ def test_model_golden_with_tf32x3_gemms():
     worst = max(rel_l2(p.grad, gold["grads_f64"][n]) for n, p in model.named_parameters()
                 if gold["grads_f64"][n] is not None and float(gold["grads_f64"][n].norm()) > 0)
     assert worst < 5e-5, worst
+
+
+def test_graphed_embedding_tables_equal_eager():
+    """LCAOEmbedding.graph_tables replays the static-shape table arithmetic as CUDA graphs: over several training steps
+    on DIFFERENT batches the outputs and the BatchNorm buffers must equal the eager path's bit for bit (same kernels, same
+    order; building the graphs must not disturb the running statistics) and every gradient to FP32 rounding (the
+    table-sized weight-gradient kernel and torch's embedding backward accumulate with atomics: run-to-run order)."""
+    torch.manual_seed(0)
+    kw = dict(cutoff=5.0, cutoff_net="polynomial")
+    m_e, m_g = LCAONet(**kw).to(DEV).train(), LCAONet(**kw).to(DEV).train()
+    m_g.load_state_dict(m_e.state_dict())
+    m_g.emb_layer.graph_tables = True
+    for step in range(3):
+        g = qm9_like_batch(8 + 4 * step, seed=40 + step)
+        outs = []
+        for m in (m_e, m_g):
+            m.zero_grad(set_to_none=True)
+            out = m(GraphBatch(g).to(DEV))
+            torch.nn.functional.mse_loss(out, g["y"].to(DEV)).backward()
+            outs.append(out.detach())
+        assert torch.equal(outs[0], outs[1]), step
+        for (n, p), q in zip(m_e.named_parameters(), m_g.parameters()):
+            assert (p.grad is None) == (q.grad is None), n
+            if p.grad is not None:
+                assert rel_l2(q.grad, p.grad) < 1e-5, (step, n, rel_l2(q.grad, p.grad))
+        for (n, b), c in zip(m_e.named_buffers(), m_g.buffers()):
+            assert torch.equal(b, c), (step, n)
+    # inference falls back to the eager path and still agrees
+    m_e.eval(), m_g.eval()
+    g = qm9_like_batch(5, seed=77)
+    with torch.no_grad():
+        assert torch.equal(m_e(GraphBatch(g).to(DEV)), m_g(GraphBatch(g).to(DEV)))
+
+
+def test_long_exclusive_scans_are_exact():
+    """index arrays beyond one scan block take the two-launch scan: offsets must stay bit-exact (E = 10^5 .. 10^6)."""
+    for n_mol, seed in ((400, 5), (2500, 6)):
+        g = qm9_like_batch(n_mol, seed)
+        ei, n = g["edge_index"], g["z"].shape[0]
+        gi = ops.GraphIndex(ei.to(DEV), n)
+        deg_in = torch.bincount(ei[1], minlength=n)
+        ref = torch.zeros(ei.shape[1] + 1, dtype=torch.int64)
+        ref[1:] = (deg_in[ei[0]] - (ei[0] == ei[1]).long()).cumsum(0)
+        assert torch.equal(gi.tri_ptr.cpu().long(), ref)
+        assert torch.equal(gi.in_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), deg_in.cumsum(0)]))
