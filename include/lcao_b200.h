@@ -38,7 +38,14 @@ extern "C" {
 
 enum { LCAO_CUT_POLYNOMIAL = 0, LCAO_CUT_ENVELOPE = 1, LCAO_CUT_COSINE = 2 };
 enum { LCAO_RBF_HYDROGEN = 0, LCAO_RBF_SPHERICAL_BESSEL = 1 };
-enum { LCAO_ACT_NONE = 0, LCAO_ACT_SILU = 1 };
+/* Activations fused into the kernels: the parameter-free ones `activation_resolver` can return (utils/resolve.py:
+ * nn/activation.py ShiftedSoftplus, torch.nn SiLU / Softplus / ReLU / Tanh / Sigmoid / GELU / ELU / LeakyReLU with their
+ * default hyper-parameters).  Swish with a trainable beta is not fused (the constructor raises). */
+enum {
+  LCAO_ACT_NONE = 0, LCAO_ACT_SILU = 1, LCAO_ACT_SSP = 2 /* softplus(x) - ln 2 */, LCAO_ACT_SOFTPLUS = 3,
+  LCAO_ACT_RELU = 4, LCAO_ACT_TANH = 5, LCAO_ACT_SIGMOID = 6, LCAO_ACT_GELU = 7 /* erf form */, LCAO_ACT_ELU = 8,
+  LCAO_ACT_LEAKY_RELU = 9 /* slope 0.01 */, LCAO_ACT_LAST = 9
+};
 enum { LCAO_GEMM_FP32 = 0, LCAO_GEMM_TF32X3 = 1, LCAO_GEMM_TF32 = 2 };
 
 /* Radial-basis description (host struct, passed by value to the kernel).
@@ -198,16 +205,17 @@ int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, int64_t ldb,
                        float* out, float* pre, void* stream);
 /* out[r,:] = sum_{j in [ptr[r],ptr[r+1])} x[perm[j],:] * (y ? y[perm[j],:] : 1) * scale_r
  * `mean` is a flag word: bit 0: scale_r = 1/max(count,1) instead of 1; bit 1: y holds a pre-activation and the
- * factor is SiLU(y) (the message sum then needs no stored copy of h = SiLU(pre_h)); bit 2: the factor is SiLU'(y)
- * (backward through an activation folded into the reduction that follows it).  Deterministic, no atomics.  x may be NULL when no segment
+ * factor is act(y) (the message sum then needs no stored copy of h = act(pre_h)); bit 2: the factor is act'(y)
+ * (backward through an activation folded into the reduction that follows it); bits 4-7: the activation (LCAO_ACT_*,
+ * 0 = SiLU).  Deterministic, no atomics.  x may be NULL when no segment
  * has any item (edge-less batch): out is zero-filled. */
 int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int64_t ldy, const int32_t* ptr,
                      const int32_t* perm, int64_t R, int32_t C, int32_t mean, float* out, int64_t ldo, void* stream);
-/* backward of the message sum  agg[s] = sum_{e in out(s)} bw[e] * h[e],  h = SiLU(pre_h)  (lcaonet.py:207-214):
- *   d_bw[e,:] = d_agg[src[e],:] * h[e,:] ;  d_pre_h[e,:] = d_agg[src[e],:] * bw[e,:] * SiLU'(pre_h[e,:])
+/* backward of the message sum  agg[s] = sum_{e in out(s)} bw[e] * h[e],  h = act(pre_h)  (lcaonet.py:207-214):
+ *   d_bw[e,:] = d_agg[src[e],:] * h[e,:] ;  d_pre_h[e,:] = d_agg[src[e],:] * bw[e,:] * act'(pre_h[e,:])
  * h may be NULL: it is then recomputed from pre_h. */
 int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
-                 const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream);
+                 const float* pre_h, int64_t E, int32_t C, int32_t act, float* d_bw, float* d_pre_h, void* stream);
 /* out[i,:] = table[idx[i],:] * (mul ? mul[i,:] : 1)   (idx int64 or int32 chosen by idx_is64) */
 int lcao_gather_rows(const float* table, int64_t ldt, const void* idx, int32_t idx_is64, const float* mul, int64_t ldm,
                      int64_t n, int32_t W, float* out, int64_t ldo, void* stream);

@@ -16,6 +16,9 @@ MAX_UNIQUE_ORB, MAX_POLY = 18, 8
 CUT = {"polynomial": 0, "envelope": 1, "cosine": 2}
 RBF = {"hydrogen": 0, "sphericalbessel": 1}
 ACT_NONE, ACT_SILU = 0, 1
+# include/lcao_b200.h LCAO_ACT_*: the parameter-free activations fused into the kernels
+ACT = {"none": 0, "silu": 1, "shiftedsoftplus": 2, "softplus": 3, "relu": 4, "tanh": 5, "sigmoid": 6, "gelu": 7, "elu": 8,
+       "leakyrelu": 9}
 GEMM_FP32, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
 
 
@@ -55,7 +58,7 @@ SIGNATURES = {
     "lcao_twobody_bwd": [_p, _i32, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
     "lcao_edge_pair_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p],
     "lcao_segment_sum": [_p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _p],
-    "lcao_msg_bwd": [_p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _p],
+    "lcao_msg_bwd": [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p],
     "lcao_gather_rows": [_p, _i64, _p, _i32, _p, _i64, _i64, _i32, _p, _i64, _p],
     "lcao_reduce_by_key": [_p, _i64, _p, _p, _i64, _i64, _i32, _p, _p],
     "lcao_linear_fwd": [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p],

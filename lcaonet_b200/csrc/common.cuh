@@ -52,6 +52,44 @@ __device__ __forceinline__ float silu_gradf(float x) {
   float s = sigmoidf_acc(x);
   return s * (1.0f + x * (1.0f - s));
 }
+// generic activation and its derivative as functions of the PRE-activation (torch semantics: F.softplus threshold 20,
+// exact-erf GELU, ELU alpha 1, LeakyReLU slope 0.01); SiLU is the hot case and comes first
+__device__ __forceinline__ float softplusf_acc(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float act_fwdf(int act, float x) {
+  switch (act) {
+    case LCAO_ACT_SILU: return siluf(x);
+    case LCAO_ACT_SSP: return softplusf_acc(x) - 0.69314718055994530942f;
+    case LCAO_ACT_SOFTPLUS: return softplusf_acc(x);
+    case LCAO_ACT_RELU: return fmaxf(x, 0.0f);
+    case LCAO_ACT_TANH: return tanhf(x);
+    case LCAO_ACT_SIGMOID: return sigmoidf_acc(x);
+    case LCAO_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case LCAO_ACT_ELU: return x > 0.0f ? x : expm1f(x);
+    case LCAO_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.01f * x;
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_gradf(int act, float x) {
+  switch (act) {
+    case LCAO_ACT_SILU: return silu_gradf(x);
+    case LCAO_ACT_SSP:
+    case LCAO_ACT_SOFTPLUS: return x > 20.0f ? 1.0f : sigmoidf_acc(x);
+    case LCAO_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
+    case LCAO_ACT_TANH: { const float t = tanhf(x); return 1.0f - t * t; }
+    case LCAO_ACT_SIGMOID: { const float s = sigmoidf_acc(x); return s * (1.0f - s); }
+    case LCAO_ACT_GELU:
+      return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+    case LCAO_ACT_ELU: return x > 0.0f ? 1.0f : expf(x);
+    case LCAO_ACT_LEAKY_RELU: return x > 0.0f ? 1.0f : 0.01f;
+    default: return 1.0f;
+  }
+}
+__device__ __forceinline__ float4 act_fwd4(int act, float4 v) {
+  return make_float4(act_fwdf(act, v.x), act_fwdf(act, v.y), act_fwdf(act, v.z), act_fwdf(act, v.w));
+}
+__device__ __forceinline__ float4 act_grad4(int act, float4 v) {
+  return make_float4(act_gradf(act, v.x), act_gradf(act, v.y), act_gradf(act, v.z), act_gradf(act, v.w));
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

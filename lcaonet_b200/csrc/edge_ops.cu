@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_edge_pair_fwd(
     float4 v = f4_add(ldg4(pa + c), ldg4(pb + c));
     if (bias) v = f4_add(v, ldg4(bias + c));
     if (pre) st4(pre + e * (int64_t)C + c, v);
-    if (act == LCAO_ACT_SILU) v = make_float4(siluf(v.x), siluf(v.y), siluf(v.z), siluf(v.w));
+    if (act != LCAO_ACT_NONE) v = act_fwd4(act, v);
     st4(out + e * (int64_t)C + c, v);
   }
 }
@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
   const int lane = threadIdx.x & 31;
   const int32_t lo = ptr[r], hi = ptr[r + 1];
   const float scale = (mean & 1) ? 1.0f / (float)max(hi - lo, 1) : 1.0f;
-  const bool ysilu = (mean & 2) != 0;   // y holds a pre-activation: the factor is SiLU(y)
-  const bool ygrad = (mean & 4) != 0;   // ... or SiLU'(y) (backward through an activation, folded into the reduction)
+  const bool ysilu = (mean & 2) != 0;   // y holds a pre-activation: the factor is act(y)
+  const bool ygrad = (mean & 4) != 0;   // ... or act'(y) (backward through an activation, folded into the reduction)
+  const int act = ((mean >> 4) & 15) ? ((mean >> 4) & 15) : LCAO_ACT_SILU;
   if (VEC) {
     for (int c = lane * 4; c < C; c += 128) {
       float4 acc = f4_zero();
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
         float4 v = ldg4(x + i * ldx + c);
         if (y) {
           float4 w = ldg4(y + i * ldy + c);
-          if (ysilu) w = make_float4(siluf(w.x), siluf(w.y), siluf(w.z), siluf(w.w));
-          if (ygrad) w = make_float4(silu_gradf(w.x), silu_gradf(w.y), silu_gradf(w.z), silu_gradf(w.w));
+          if (ysilu) w = act_fwd4(act, w);
+          if (ygrad) w = act_grad4(act, w);
           v = f4_mul(v, w);
         }
         acc = f4_add(acc, v);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
       for (int32_t j = lo; j < hi; ++j) {
         const int64_t i = perm ? perm[j] : j;
         float v = x[i * ldx + c];
-        if (y) v *= ysilu ? siluf(y[i * ldy + c]) : ygrad ? silu_gradf(y[i * ldy + c]) : y[i * ldy + c];
+        if (y) v *= ysilu ? act_fwdf(act, y[i * ldy + c]) : ygrad ? act_gradf(act, y[i * ldy + c]) : y[i * ldy + c];
         acc += v;
       }
       out[r * ldo + c] = scale * acc;
@@ -323,10 +324,7 @@ __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float
   const int64_t i = t / C4;
   const int c = (int)(t - i * C4) * 4;
   float4 g = *reinterpret_cast<const float4*>(dY + i * ldy + c);
-  if (act == LCAO_ACT_SILU) {
-    const float4 h = ldg4(H + i * ldh + c);
-    g = make_float4(g.x * silu_gradf(h.x), g.y * silu_gradf(h.y), g.z * silu_gradf(h.z), g.w * silu_gradf(h.w));
-  }
+  if (act != LCAO_ACT_NONE) g = f4_mul(g, act_grad4(act, ldg4(H + i * ldh + c)));
   st4(dH + i * ldd + c, g);
 }
 
@@ -334,7 +332,7 @@ __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float
 //   d_bw[e] = d_agg[src[e]] * h[e] ;  d_pre_h[e] = d_agg[src[e]] * bw[e] * SiLU'(pre_h[e])
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
     const float* __restrict__ d_agg, int64_t lda, const int32_t* __restrict__ src32, const float* __restrict__ h,
-    const float* __restrict__ bw, const float* __restrict__ pre_h, int64_t E, int C, float* __restrict__ d_bw,
+    const float* __restrict__ bw, const float* __restrict__ pre_h, int64_t E, int C, int act, float* __restrict__ d_bw,
     float* __restrict__ d_pre_h) {
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
@@ -343,10 +341,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
   for (int c = lane * 4; c < C; c += 128) {
     const float4 g = ldg4(pa + c), b = ldg4(bw + e * (int64_t)C + c);
     const float4 p = ldg4(pre_h + e * (int64_t)C + c);
-    const float4 hv = h ? ldg4(h + e * (int64_t)C + c) : make_float4(siluf(p.x), siluf(p.y), siluf(p.z), siluf(p.w));
+    const float4 hv = h ? ldg4(h + e * (int64_t)C + c) : act_fwd4(act, p);
     st4(d_bw + e * (int64_t)C + c, f4_mul(g, hv));
-    st4(d_pre_h + e * (int64_t)C + c,
-        make_float4(g.x * b.x * silu_gradf(p.x), g.y * b.y * silu_gradf(p.y), g.z * b.z * silu_gradf(p.z), g.w * b.w * silu_gradf(p.w)));
+    st4(d_pre_h + e * (int64_t)C + c, f4_mul(f4_mul(g, b), act_grad4(act, p)));
   }
 }
 
@@ -522,14 +519,15 @@ extern "C" int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_
 }
 
 extern "C" int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src32, const float* h, const float* bw,
-                            const float* pre_h, int64_t E, int32_t C, float* d_bw, float* d_pre_h, void* stream) {
+                            const float* pre_h, int64_t E, int32_t C, int32_t act, float* d_bw, float* d_pre_h,
+                            void* stream) {
   if (E == 0) return LCAO_OK;
   LCAO_REQUIRE(d_agg && src32 && bw && pre_h && d_bw && d_pre_h, "lcao_msg_bwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && aligned16(d_agg) && (!h || aligned16(h)) && aligned16(bw) && aligned16(pre_h) &&
                    aligned16(d_bw) && aligned16(d_pre_h),
                "lcao_msg_bwd: need C, lda multiples of 4 and 16-byte aligned buffers");
   k_msg_bwd<<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw,
-                                                                                                pre_h, E, C, d_bw, d_pre_h);
+                                                                                                pre_h, E, C, act, d_bw, d_pre_h);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -131,14 +131,14 @@ __global__ void __launch_bounds__(GT) k_gemm(const GemmArgs g) {
       }
       if (g.vecC && n + 3 < g.N) {
         if (g.pre) st4(g.pre + m * g.ldp + n, make_float4(v[0], v[1], v[2], v[3]));
-        if (g.act == LCAO_ACT_SILU) { v[0] = siluf(v[0]); v[1] = siluf(v[1]); v[2] = siluf(v[2]); v[3] = siluf(v[3]); }
+        if (g.act != LCAO_ACT_NONE) { v[0] = act_fwdf(g.act, v[0]); v[1] = act_fwdf(g.act, v[1]); v[2] = act_fwdf(g.act, v[2]); v[3] = act_fwdf(g.act, v[3]); }
         st4(g.C + m * g.ldc + n, make_float4(v[0], v[1], v[2], v[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (n + j >= g.N) continue;
           if (g.pre) g.pre[m * g.ldp + n + j] = v[j];
-          g.C[m * g.ldc + n + j] = (g.act == LCAO_ACT_SILU) ? siluf(v[j]) : v[j];
+          g.C[m * g.ldc + n + j] = act_fwdf(g.act, v[j]);
         }
       }
     }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) k_tiny_rows(const float* __restrict__ X, 
       if (bias) v += __ldg(bias + n);
       if (accumulate) v += Y[(int64_t)m * ldy + n];
       if (pre) pre[(int64_t)m * ldp + n] = v;
-      Y[(int64_t)m * ldy + n] = (act == LCAO_ACT_SILU) ? siluf(v) : v;
+      Y[(int64_t)m * ldy + n] = act_fwdf(act, v);
     }
   }
 }

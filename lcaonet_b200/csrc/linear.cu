@@ -12,7 +12,7 @@ int lcao_simt_linear_wgrad(const float*, int64_t, const float*, int64_t, float*,
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y);
 int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b_trans, const float* bias, const float* G,
                  int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
-                 int accumulate, int x3, cudaStream_t st);
+                 int accumulate, int x3, cudaStream_t st, int gact = LCAO_ACT_SILU);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
                   int Kx, int x3, float* part, cudaStream_t st);
@@ -26,7 +26,7 @@ extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, cons
                                void* stream) {
   if (M == 0 || Nout == 0) return LCAO_OK;
   LCAO_REQUIRE(X && W && Y && K > 0, "lcao_linear_fwd: null buffer");
-  LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_fwd: unsupported activation %d", act);
+  LCAO_REQUIRE(act >= LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_linear_fwd: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = mode != LCAO_GEMM_FP32 && Nout % 16 == 0 && K <= 128 && al16(W) && (!bias || al16(bias)) &&
                   (!pre || (al16(pre) && ldp % 4 == 0)) && lcao_tc_rows_ok(M, K, imin(Nout, 128), ldx, ldy, X, Y);
@@ -78,7 +78,7 @@ extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, i
                                  int32_t mode, float* scratch, void* stream) {
   if (M == 0 || K == 0) return LCAO_OK;
   LCAO_REQUIRE(dY && W && dX && Nout > 0, "lcao_linear_dgrad: null buffer");
-  LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_dgrad: unsupported activation %d", act);
+  LCAO_REQUIRE(act >= LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_linear_dgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   {
     int rc = act_bwd_to_scratch(dY, ldy, H, ldh, act, M, Nout, scratch, stream, "lcao_linear_dgrad");
@@ -109,7 +109,7 @@ extern "C" int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* 
                                      void* stream) {
   if (M == 0 || K == 0) return LCAO_OK;
   LCAO_REQUIRE(dY && W && dX && G && Nout > 0, "lcao_linear_dgrad_act: null buffer");
-  LCAO_REQUIRE(act == LCAO_ACT_SILU, "lcao_linear_dgrad_act: unsupported activation %d", act);
+  LCAO_REQUIRE(act > LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_linear_dgrad_act: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   if (!dgrad_tc(dY, ldy, W, dX, ldx, M, K, Nout, mode) || ldg % 4 != 0 || ((uintptr_t)G & 15)) {
     int rc = lcao_simt_linear_dgrad(dY, ldy, W, dX, ldx, M, K, Nout, 0, st);
@@ -122,7 +122,7 @@ extern "C" int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* 
       const int kc = imin(128, Nout - c0);
       const bool last = c0 + 128 >= Nout;
       int rc = lcao_tc_rows(dY + c0, ldy, W + (int64_t)c0 * K + n0, K, 1, nullptr, last ? G + n0 : nullptr, ldg, dX + n0, ldx,
-                            nullptr, 0, M, kc, nb, LCAO_ACT_NONE, c0 > 0, mode == LCAO_GEMM_TF32X3, st);
+                            nullptr, 0, M, kc, nb, LCAO_ACT_NONE, c0 > 0, mode == LCAO_GEMM_TF32X3, st, act);
       if (rc) return rc;
     }
   }
@@ -134,7 +134,7 @@ extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, i
                                  float* scratch, void* stream) {
   if (M == 0 || K == 0 || Nout == 0) return LCAO_OK;
   LCAO_REQUIRE(dY && X && dW, "lcao_linear_wgrad: null buffer");
-  LCAO_REQUIRE(act == LCAO_ACT_NONE || act == LCAO_ACT_SILU, "lcao_linear_wgrad: unsupported activation %d", act);
+  LCAO_REQUIRE(act >= LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_linear_wgrad: unsupported activation %d", act);
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode);  // decided on the caller's dY, like the scratch query
   float* part = (act == LCAO_ACT_NONE || !H) ? scratch : scratch + M * (int64_t)Nout;

@@ -21,7 +21,7 @@ from torch import Tensor
 from . import _lib, ops
 from .keys import GraphKeys
 from .orbitals import ElecInfo
-from .resolve import activation_resolver, cutoff_kind, init_params, init_resolver, rbf_kind
+from .resolve import activation_code, activation_resolver, cutoff_kind, init_params, init_resolver, rbf_kind
 
 
 # ----------------------------------------------------------------------------------------------
@@ -51,23 +51,18 @@ class Dense(nn.Linear):
         if self.bias is not None and self.bias_init is not None:
             self.bias_init(self.bias)
 
-    def forward(self, x: Tensor, silu: bool = False) -> Tensor:
+    def forward(self, x: Tensor, silu=False) -> Tensor:
+        """`silu`: activation fused into the epilogue — False / True (SiLU) or an LCAO_ACT_* code."""
         return ops.linear(x, self.weight, self.bias, silu)
 
 
-def _require_silu(act: nn.Module):
-    if not isinstance(act, nn.SiLU):
-        raise NotImplementedError(f"activation {type(act).__name__}: only SiLU (the reference default, lcaonet.py:345) "
-                                  "is fused into the B200 kernels")
-
-
 def _mlp(seq: nn.Sequential, x: Tensor) -> Tensor:
-    """Dense layers of an nn.Sequential with the SiLU that follows each one fused into its epilogue."""
+    """Dense layers of an nn.Sequential with the activation that follows each one fused into its epilogue."""
     mods = list(seq)
     i = 0
     while i < len(mods):
-        fused = i + 1 < len(mods) and isinstance(mods[i + 1], nn.SiLU)
-        x = mods[i](x, silu=fused)
+        fused = i + 1 < len(mods) and not isinstance(mods[i + 1], Dense)
+        x = mods[i](x, silu=activation_code(mods[i + 1]) if fused else False)
         i += 2 if fused else 1
     return x
 
@@ -313,7 +308,7 @@ class LCAOInteraction(nn.Module):
                 sinks = tuple(p.grad if (p.requires_grad and p.grad is not None and p.grad.is_contiguous()) else None
                               for p in params)
             return ops.interaction_layer(x, cst.table, rb, unit, *params, cst.pair, cst.kptr, cst.kperm, vmask, lgrp, gi, NL, C,
-                                         sinks)
+                                         sinks, activation_code(fn[1]))
         nw = self.node_weight(x)  # (N, 2C): [:, :C] feeds f_node, [:, C:] is the three-body gate
         xc, xk = nw[:, :C], nw[:, C:]
         if isinstance(cst, PairCoeffs):  # f_coeffs on the species-pair table, contracted per edge
@@ -329,8 +324,9 @@ class LCAOInteraction(nn.Module):
         bw = self.basis_weight(lw)
         w1 = self.f_node[0].weight  # (C, 2C) acting on [x_s ; x_t]  ->  W1a x_s + W1b x_t, per NODE
         u = ops.linear(xc, torch.cat([w1[:, :C], w1[:, C:]], dim=0))  # (N, 2C)
-        a1 = ops.edge_pair(u[:, :C], u[:, C:], self.f_node[0].bias, gi, silu=True)  # (E, C)
-        h = self.f_node[2](a1, silu=True)
+        act = activation_code(self.f_node[1])
+        a1 = ops.edge_pair(u[:, :C], u[:, C:], self.f_node[0].bias, gi, silu=act)  # (E, C)
+        h = self.f_node[2](a1, silu=act)
         agg = ops.mul_segment_sum(bw, h, gi)  # (N, C) sum over out-edges of each centre
         return x + self.out_weight(agg)
 
@@ -359,8 +355,9 @@ class LCAOOut(nn.Module):
             H = self.emb_size
             w1 = self.out_lin_force[0].weight
             u = ops.linear(x, torch.cat([w1[:, :H], w1[:, H:]], dim=0))
-            a = ops.edge_pair(u[:, :H], u[:, H:], self.out_lin_force[0].bias, gi, silu=True)
-            a = self.out_lin_force[2](a, silu=True)
+            act = activation_code(self.out_lin_force[1])
+            a = ops.edge_pair(u[:, :H], u[:, H:], self.out_lin_force[0].bias, gi, silu=act)
+            a = self.out_lin_force[2](a, silu=act)
             f_st = self.out_lin_force[4](a) * unit  # (E, 3)
             return prop, ops.segment_reduce(f_st, gi.out_ptr, gi.out_edge, gi.src32, mean=False)
         cols = [-torch.autograd.grad(prop[:, i].sum(), pos, create_graph=True)[0] for i in range(self.out_size)]
@@ -473,7 +470,7 @@ class LCAONet(nn.Module):
         super().__init__()
         wi = init_resolver(weight_init) if weight_init is not None else None
         act = activation_resolver(activation)
-        _require_silu(act)
+        activation_code(act)  # raises for activations the kernels do not fuse
         if emb_size_conv % 4 or emb_size_coeff % 4 or emb_size_conv > 256:
             raise NotImplementedError("the B200 kernels need emb_size_conv and emb_size_coeff to be multiples of 4 "
                                       f"and emb_size_conv <= 256 (got {emb_size_conv}, {emb_size_coeff})")

@@ -212,10 +212,15 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def linear(x: Tensor, weight: Tensor, bias: Tensor | None = None, silu: bool = False) -> Tensor:
+def _act_arg(act) -> int:
+    """activation argument of the public ops: an LCAO_ACT_* code, or True / False for SiLU / none"""
+    return ACT_SILU if act is True else ACT_NONE if act is False or act is None else int(act)
+
+
+def linear(x: Tensor, weight: Tensor, bias: Tensor | None = None, silu=False) -> Tensor:
     """act(x W^T + b) — nn.Linear semantics (reference nn/base.py:72-81) with an optional fused SiLU.
     Requires the feature sizes to be multiples of 4 only for the vector paths; any size works."""
-    return _Linear.apply(x, weight, bias, ACT_SILU if silu else ACT_NONE)
+    return _Linear.apply(x, weight, bias, _act_arg(silu))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -424,10 +429,10 @@ def _lin_dgrad(dy, ldy, M, w, dx, ldx, accumulate, st):
     _call("lcao_linear_dgrad", ptr(dy), ldy, None, 0, ACT_NONE, ptr(w), ptr(dx), ldx, M, K, Nout, accumulate, _gemm_mode, None, st)
 
 
-def _lin_dgrad_act(dy, ldy, M, w, pre_in, dx, ldx, st):
-    """dx = (dy W) * SiLU'(pre_in): data gradient chained through the activation that produced the layer's input."""
+def _lin_dgrad_act(dy, ldy, M, w, pre_in, dx, ldx, st, act=ACT_SILU):
+    """dx = (dy W) * act'(pre_in): data gradient chained through the activation that produced the layer's input."""
     Nout, K = w.shape
-    _call("lcao_linear_dgrad_act", ptr(dy), ldy, ptr(w), ptr(pre_in), K, ACT_SILU, ptr(dx), ldx, M, K, Nout, _gemm_mode, st)
+    _call("lcao_linear_dgrad_act", ptr(dy), ldy, ptr(w), ptr(pre_in), K, act, ptr(dx), ldx, M, K, Nout, _gemm_mode, st)
 
 
 def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
@@ -444,9 +449,9 @@ def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
     return (None if dw_sink is not None else dw), (None if (db_sink is not None or not has_bias) else db)
 
 
-def _act_bwd(dy, pre, M, C, st):
+def _act_bwd(dy, pre, M, C, st, act=ACT_SILU):
     out = torch.empty(M, C, device=dy.device)
-    _call("lcao_act_bwd", ptr(dy), C, ptr(pre), C, ptr(out), C, M, C, ACT_SILU, st)
+    _call("lcao_act_bwd", ptr(dy), C, ptr(pre), C, ptr(out), C, M, C, act, st)
     return out
 
 
@@ -462,7 +467,7 @@ class _InteractionLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, aux):
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = aux
+        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks, act = aux
         require_cuda(x, table, rb, unit)
         st = stream_ptr()
         dev = x.device
@@ -476,8 +481,8 @@ class _InteractionLayer(torch.autograd.Function):
         # node side: nw = [xc | xk]
         nw, _ = _lin_fwd(x, H, N, w_n, b_n, ACT_NONE, st, False)
         # f_coeffs on the species-pair table
-        t1, pre1 = _lin_fwd(table, K, P * O, w_c0, None, ACT_SILU, st, grad)
-        tab, pre2 = _lin_fwd(t1, C, P * O, w_c2, None, ACT_SILU, st, grad)
+        t1, pre1 = _lin_fwd(table, K, P * O, w_c0, None, act, st, grad)
+        tab, pre2 = _lin_fwd(t1, C, P * O, w_c2, None, act, st, grad)
         B = torch.empty(E, NG, C, device=dev)
         gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=dev)
         psum = torch.empty(E, 1 + valence, C, device=dev)  # [sum_l B_l | valence slot]: the two-body weight's view of B
@@ -499,12 +504,13 @@ class _InteractionLayer(torch.autograd.Function):
         a1 = torch.empty(E, C, device=dev)
         pre_a = torch.empty(E, C, device=dev) if grad else None
         _call("lcao_edge_pair_fwd", ptr(u), 2 * C, u.data_ptr() + 4 * C, 2 * C, ptr(b_1), ptr(gi.src32), ptr(gi.dst32), E, C,
-              ACT_SILU, ptr(a1), ptr(pre_a), st)
+              act, ptr(a1), ptr(pre_a), st)
         # h = SiLU(pre_h) is never stored: the message sum and its backward apply the activation on the fly, which takes
         # one E x C write off the f_node GEMM and one E x C read off each consumer
         pre_h, _ = _lin_fwd(a1, C, E, w_2, b_2, ACT_NONE, st, False)
         agg = torch.empty(N, C, device=dev)
-        _call("lcao_segment_sum", ptr(bw), C, ptr(pre_h), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 2, ptr(agg), C, st)
+        _call("lcao_segment_sum", ptr(bw), C, ptr(pre_h), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 2 | (act << 4), ptr(agg), C,
+              st)
         y, _ = _lin_fwd(agg, C, N, w_o, None, ACT_NONE, st, False)
         out = x + y
         if grad:
@@ -518,7 +524,7 @@ class _InteractionLayer(torch.autograd.Function):
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
          lw, bw, a1, pre_a, pre_h, agg, psum) = ctx.saved_tensors
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks = ctx.aux
+        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks, act = ctx.aux
         # gradient sinks: the parameters' own .grad buffers (order: w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o)
         s_wn, s_bn, s_wc0, s_wc2, s_w3, s_wb, s_w1, s_b1, s_w2, s_b2, s_wo = sinks if sinks is not None else (None,) * 11
         st = stream_ptr()
@@ -536,15 +542,16 @@ class _InteractionLayer(torch.autograd.Function):
         _lin_dgrad(d_out, H, N, w_o, d_agg, C, 0, st)
         # agg[s] = sum_{e in out(s)} bw[e] * h[e]
         d_bw, d_preh = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
-        _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), None, ptr(bw), ptr(pre_h), E, C, ptr(d_bw), ptr(d_preh), st)
+        _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), None, ptr(bw), ptr(pre_h), E, C, act, ptr(d_bw), ptr(d_preh), st)
         # h = silu(f_node.2(a1)) ; a1 = silu(u_a[s] + u_b[t] + b1)
         dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st, s_w2, s_b2)
         # d_prea = d_a1 * SiLU'(pre_a) is never materialised: the two segment sums over it apply the factor on the fly
         d_a1 = torch.empty(E, C, device=dev)
         _lin_dgrad(d_preh, C, E, w_2, d_a1, C, 0, st)
         d_u = torch.empty(N, 2 * C, device=dev)
-        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 4, ptr(d_u), 2 * C, st)
-        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.in_ptr), ptr(gi.in_edge), N, C, 4,
+        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 4 | (act << 4), ptr(d_u),
+              2 * C, st)
+        _call("lcao_segment_sum", ptr(d_a1), C, ptr(pre_a), C, ptr(gi.in_ptr), ptr(gi.in_edge), N, C, 4 | (act << 4),
               d_u.data_ptr() + 4 * C, 2 * C, st)
         d_nw = torch.empty(N, 2 * C, device=dev)
         _lin_dgrad(d_u, 2 * C, N, w_1cat, d_nw, 2 * C, 0, st)  # writes d_xc = d_nw[:, :C]
@@ -585,10 +592,10 @@ class _InteractionLayer(torch.autograd.Function):
         scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.int32, device=dev)
         _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB), E,
               P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), st)
-        d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st)
+        d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st, act)
         dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st, s_wc2)
         d_pre1 = torch.empty(P * O, C, device=dev)
-        _lin_dgrad_act(d_pre2, Cp, P * O, w_c2, pre1, d_pre1, C, st)
+        _lin_dgrad_act(d_pre2, Cp, P * O, w_c2, pre1, d_pre1, C, st, act)
         dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st, s_wc0)
         d_table = torch.empty(P, O, K, device=dev)
         _lin_dgrad(d_pre1, C, P * O, w_c0, d_table, K, 0, st)
@@ -601,13 +608,13 @@ class _InteractionLayer(torch.autograd.Function):
 
 
 def interaction_layer(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, pair, kptr, kperm, vmask,
-                      lgrp, gi, NL, C, grad_sinks=None):
+                      lgrp, gi, NL, C, grad_sinks=None, act=ACT_SILU):
     """grad_sinks: optional 11-tuple of the weights' / biases' `.grad` buffers (contiguous, same shapes; None entries
     allowed).  The backward pass then ACCUMULATES those gradients in place and returns None for them to autograd —
     what AccumulateGrad would do, without the zero-fills and the per-parameter add kernels.  Opt-in
     (`LCAOInteraction.grads_in_place`, set by `dist.FlatGradBucket`): parameter hooks do not fire for them."""
     return _InteractionLayer.apply(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o,
-                                   (pair, kptr, kperm, vmask, lgrp, gi, NL, C, grad_sinks))
+                                   (pair, kptr, kperm, vmask, lgrp, gi, NL, C, grad_sinks, _act_arg(act)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -648,9 +655,9 @@ class _EdgePair(torch.autograd.Function):
         return da, db, dbias, None, None
 
 
-def edge_pair(a, b, bias, gi, silu: bool):
+def edge_pair(a, b, bias, gi, silu):
     """act(a[s_e] + b[t_e] + bias): `W [x_s ; x_t] + b` with W split per node (lcaonet.py:209, :304)."""
-    return _EdgePair.apply(a, b, bias, gi, ACT_SILU if silu else ACT_NONE)
+    return _EdgePair.apply(a, b, bias, gi, _act_arg(silu))
 
 
 class _MulSegSum(torch.autograd.Function):

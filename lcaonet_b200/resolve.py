@@ -42,14 +42,81 @@ def init_params(fn) -> tuple[str, ...]:
     return fn.__code__.co_varnames[: fn.__code__.co_argcount]
 
 
+class Swish(nn.Module):
+    """x * sigmoid(beta x) with an optionally trainable beta (reference nn/activation.py:7-33)."""
+
+    def __init__(self, beta: float = 1.0, train_beta: bool = True):
+        super().__init__()
+        self.train_beta = train_beta
+        if train_beta:
+            self.beta = nn.Parameter(torch.tensor(float(beta)))
+        else:
+            self.register_buffer("beta", torch.tensor(float(beta)))
+
+    def extra_repr(self) -> str:
+        return f"beta={self.beta.item():.2f}, trainable_beta:{self.train_beta}"
+
+    def forward(self, x):
+        return x * torch.sigmoid(self.beta * x)
+
+
+class ShiftedSoftplus(nn.Module):
+    """softplus(x) - ln 2 (reference nn/activation.py:36-65)."""
+
+    def __init__(self, shift: float = math.log(2.0)):
+        super().__init__()
+        self.shift = shift
+
+    def extra_repr(self) -> str:
+        return f"shift={self.shift:.2f}"
+
+    def forward(self, x):
+        return torch.nn.functional.softplus(x) - self.shift
+
+
 def activation_resolver(query) -> nn.Module:
+    """torch.nn activations plus the reference's Swish and ShiftedSoftplus (utils/resolve.py:65-76)."""
     if isinstance(query, nn.Module):
         return query
     q = _norm(query)
-    for name, cls in vars(torch.nn.modules.activation).items():
+    classes = dict(vars(torch.nn.modules.activation), Swish=Swish, ShiftedSoftplus=ShiftedSoftplus)
+    for name, cls in classes.items():
         if isinstance(cls, type) and issubclass(cls, nn.Module) and _norm(name) == q:
             return cls()
     raise ValueError(f"{query} not found")
+
+
+def activation_code(act: nn.Module) -> int:
+    """LCAO_ACT_* code of an activation module, for the kinds the kernels fuse: parameter-free activations with their
+    default hyper-parameters.  Anything else (Swish with a trainable or non-unit beta, PReLU, ...) raises."""
+    from ._lib import ACT
+
+    def default(**kw):
+        return all(getattr(act, k) == v for k, v in kw.items())
+
+    if isinstance(act, nn.SiLU):
+        return ACT["silu"]
+    if isinstance(act, Swish) and not act.train_beta and float(act.beta) == 1.0:
+        return ACT["silu"]
+    if isinstance(act, ShiftedSoftplus) and abs(act.shift - math.log(2.0)) < 1e-12:
+        return ACT["shiftedsoftplus"]
+    if isinstance(act, nn.Softplus) and default(beta=1.0, threshold=20.0):
+        return ACT["softplus"]
+    if type(act) is nn.ReLU:
+        return ACT["relu"]
+    if type(act) is nn.Tanh:
+        return ACT["tanh"]
+    if type(act) is nn.Sigmoid:
+        return ACT["sigmoid"]
+    if isinstance(act, nn.GELU) and default(approximate="none"):
+        return ACT["gelu"]
+    if isinstance(act, nn.ELU) and default(alpha=1.0):
+        return ACT["elu"]
+    if isinstance(act, nn.LeakyReLU) and default(negative_slope=0.01):
+        return ACT["leakyrelu"]
+    raise NotImplementedError(f"activation {act!r}: the B200 kernels fuse SiLU (the reference default, lcaonet.py:345), "
+                              "ShiftedSoftplus, Softplus, ReLU, Tanh, Sigmoid, GELU, ELU and LeakyReLU with default "
+                              "hyper-parameters; Swish only with a fixed beta = 1")
 
 
 def cutoff_kind(query) -> str:

@@ -191,6 +191,18 @@ def _lin(p, name, x):
     return F.linear(x, p[name + ".weight"], p.get(name + ".bias"))
 
 
+# activations `activation_resolver` can return without parameters (utils/resolve.py:65-76, nn/activation.py:36-65);
+# names normalised like the reference does (lower case, no '-', '_', ' ')
+_ACTIVATIONS = {"silu": F.silu, "shiftedsoftplus": lambda x: F.softplus(x) - math.log(2.0), "softplus": F.softplus,
+                "relu": F.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "gelu": F.gelu, "elu": F.elu,
+                "leakyrelu": F.leaky_relu}
+
+
+def _act(cfg):
+    name = cfg.get("activation", "SiLU")
+    return _ACTIVATIONS[str(name).lower().replace("-", "").replace("_", "").replace(" ", "")]
+
+
 def _batch_norm(p, name, x, training: bool, new_stats: dict | None):
     """nn.BatchNorm1d semantics (embed.py:175,232): batch statistics + running-stat update
     (momentum 0.1, unbiased running variance) in training, running statistics in eval."""
@@ -230,13 +242,13 @@ def embedding(p, cfg, z, idx_s, idx_t, training, new_stats=None):
     else:
         coeff_e = eemb
         enc_in = node_z
-    h = F.silu(_lin(p, "emb_layer.node_embed.f_enc.0", enc_in))
-    h = F.silu(_lin(p, "emb_layer.node_embed.f_enc.2", h))
+    h = _act(cfg)(_lin(p, "emb_layer.node_embed.f_enc.0", enc_in))
+    h = _act(cfg)(_lin(p, "emb_layer.node_embed.f_enc.2", h))
     x = _batch_norm(p, "emb_layer.node_embed.bn", h, training, new_stats)
 
     fz = _lin(p, "emb_layer.coeff_embed.f_z.0", torch.cat([coeff_z[idx_s], coeff_z[idx_t]], dim=-1))  # (E, K)
-    fe = F.silu(_lin(p, "emb_layer.coeff_embed.f_e.0", coeff_e))
-    fe = F.silu(_lin(p, "emb_layer.coeff_embed.f_e.2", fe))[idx_t]  # (E, n_orb, K): orbitals of the TARGET
+    fe = _act(cfg)(_lin(p, "emb_layer.coeff_embed.f_e.0", coeff_e))
+    fe = _act(cfg)(_lin(p, "emb_layer.coeff_embed.f_e.2", fe))[idx_t]  # (E, n_orb, K): orbitals of the TARGET
     pre = fe + fe * fz.unsqueeze(1)
     cst = _batch_norm(p, "emb_layer.coeff_embed.bn", pre.reshape(pre.shape[0], -1), training, new_stats)
     return x, cst.reshape(pre.shape)
@@ -250,8 +262,8 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
     x_in = x
     nw = _lin(p, pre + "node_weight", x)
     xc, xk = nw[:, :C], nw[:, C:]
-    c1 = F.silu(_lin(p, pre + "f_coeffs.0", cst))
-    c1 = F.silu(_lin(p, pre + "f_coeffs.2", c1))  # (E, O, C')
+    c1 = _act(cfg)(_lin(p, pre + "f_coeffs.0", cst))
+    c1 = _act(cfg)(_lin(p, pre + "f_coeffs.2", c1))  # (E, O, C')
     # three-body: gather the coefficient rows of the incoming edge (k->s) of every triplet
     w3 = rb[e_ks] * shb  # (T, O)
     if cfg["add_valence"]:
@@ -270,8 +282,8 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
     else:
         lw = torch.einsum("eo,eoc->ec", rb, c2)
     lw = F.normalize(lw, dim=-1)
-    h = F.silu(_lin(p, pre + "f_node.0", torch.cat([xc[idx_s], xc[idx_t]], dim=-1)))
-    h = F.silu(_lin(p, pre + "f_node.2", h))
+    h = _act(cfg)(_lin(p, pre + "f_node.0", torch.cat([xc[idx_s], xc[idx_t]], dim=-1)))
+    h = _act(cfg)(_lin(p, pre + "f_node.2", h))
     msg = _lin(p, pre + "basis_weight", lw) * h
     agg = _segment_sum(msg, idx_s, x.shape[0])  # edges -> source/centre nodes
     if trace is not None:
@@ -282,9 +294,9 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
 # --------------------------------------------------------------------------------------------
 # output block + post-processing (reference: lcaonet.py:271-319, post.py:44-89)
 # --------------------------------------------------------------------------------------------
-def _mlp3(p, pre, x):
-    x = F.silu(_lin(p, pre + ".0", x))
-    x = F.silu(_lin(p, pre + ".2", x))
+def _mlp3(p, pre, x, cfg):
+    x = _act(cfg)(_lin(p, pre + ".0", x))
+    x = _act(cfg)(_lin(p, pre + ".2", x))
     return _lin(p, pre + ".4", x)
 
 
@@ -330,11 +342,11 @@ def forward(params: dict, cfg: dict, graph, training: bool = True, trace: dict |
         if trace is not None:
             trace[f"x{i + 1}"] = x
     ext = cfg.get("is_extensive", True)
-    energy = _per_graph(_mlp3(p, "out_layer.out_lin", x), batch, n_graph, ext)
+    energy = _per_graph(_mlp3(p, "out_layer.out_lin", x, cfg), batch, n_graph, ext)
     forces = None
     if cfg.get("regress_forces", False):
         if cfg.get("direct_forces", True):
-            f_e = _mlp3(p, "out_layer.out_lin_force", torch.cat([x[idx_s], x[idx_t]], dim=-1)) * unit
+            f_e = _mlp3(p, "out_layer.out_lin_force", torch.cat([x[idx_s], x[idx_t]], dim=-1), cfg) * unit
             forces = _segment_sum(f_e, idx_s, x.shape[0])
         else:
             cols = [-torch.autograd.grad(energy[:, i].sum(), pos, create_graph=True)[0] for i in range(energy.shape[1])]

@@ -37,7 +37,7 @@ from lcaonet_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_case(name, kwargs, graph, training=True):
+def _run_case(name, kwargs, graph, training=True):
     res = {"kwargs": kwargs, "training": training,
            "graph": {k: v.detach().clone() for k, v in graph.items()}}
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
@@ -106,7 +106,14 @@ def basis_tables():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    basis_tables()
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
+
+    def run_case(name, kwargs, graph, training=True):
+        if not only or name in only:
+            _run_case(name, kwargs, graph, training)
+
+    if not only or "basis_tables" in only:
+        basis_tables()
     qm9 = synth.qm9_like_batch(6, seed=3, cutoff=5.0, margin=0.05)
     xtl = synth.crystal_like_batch(1, seed=5, cutoff=6.0, margin=0.05)
     fix = synth.reference_fixture_graph()
@@ -126,6 +133,12 @@ def main():
                                                       max_z=5, cutoff=2.0, cutoff_net="cosine", max_orb="4p",
                                                       min_orb="2s", n_per_orb=2, add_valence=True,
                                                       atomref=torch.ones(6, 1), mean=torch.tensor([1.0])), fix)
+    # activations other than the default (utils/resolve.py:65-76): the reference's own ShiftedSoftplus, and a torch.nn one
+    qm9s = synth.qm9_like_batch(3, seed=7, cutoff=5.0, margin=0.05)
+    run_case("qm9_shiftedsoftplus", dict(cutoff=5.0, cutoff_net="polynomial", activation="ShiftedSoftplus",
+                                         regress_forces=True, direct_forces=True, **small), qm9s)
+    run_case("qm9_gelu_valence", dict(cutoff=5.0, cutoff_net="polynomial", activation="gelu", add_valence=True,
+                                      emb_size=16, emb_size_coeff=16, emb_size_conv=16), qm9s)
 
 
 if __name__ == "__main__":

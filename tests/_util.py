@@ -11,7 +11,8 @@ CTOR_DEFAULTS = dict(emb_size=128, emb_size_coeff=128, emb_size_conv=128, out_si
                      weight_init="glorotorthogonal", atomref=None, mean=None, regress_forces=False, direct_forces=True)
 
 CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_autograd_forces",
-         "crystal_direct_forces_mean", "fixture_small", "fixture_cosine_minmaxorb_atomref"]
+         "crystal_direct_forces_mean", "fixture_small", "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus",
+         "qm9_gelu_valence"]
 
 
 def load_golden(name):

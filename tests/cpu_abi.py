@@ -451,8 +451,23 @@ def lcao_twobody_bwd(B, NG, g, d_lw, E, C, NL, valence, compact, dB, d_g, stream
         view(d_g, E, C).copy_(dp * PA)
 
 
+_F = torch.nn.functional
+_ACTS = {0: lambda x: x, 1: _F.silu, 2: lambda x: _F.softplus(x) - math.log(2.0), 3: _F.softplus, 4: torch.relu, 5: torch.tanh,
+         6: torch.sigmoid, 7: _F.gelu, 8: _F.elu, 9: _F.leaky_relu}
+
+
 def _act(x, act):
-    return torch.nn.functional.silu(x) if act == 1 else x
+    return _ACTS[act](x)
+
+
+def _act_grad(h, act):
+    """act'(h) of the activation codes of include/lcao_b200.h (autograd of the torch definition)."""
+    if act == 0:
+        return torch.ones_like(h)
+    with torch.enable_grad():
+        x = h.detach().clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(_ACTS[act](x).sum(), x)
+    return g
 
 
 def lcao_edge_pair_fwd(a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre, stream):
@@ -474,23 +489,22 @@ def lcao_segment_sum(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo, stream):
     X = view(x, n_src, C, ld=ldx)
     if y:
         Y = view(y, n_src, C, ld=ldy)
+        kind = ((mean >> 4) & 15) or 1
         if mean & 4:
-            sg = torch.sigmoid(Y)
-            Y = sg * (1 + Y * (1 - sg))
-        X = X * (torch.nn.functional.silu(Y) if (mean & 2) else Y)
+            Y = _act_grad(Y, kind)
+        X = X * (_act(Y, kind) if (mean & 2) else Y)
     O = view(out, R, C, ld=ldo)
     for r in range(R):
         seg = X[pm[p[r]:p[r + 1]]].sum(0)
         O[r] = seg / max(int(p[r + 1] - p[r]), 1) if (mean & 1) else seg
 
 
-def lcao_msg_bwd(d_agg, lda, src32, h, bw, pre_h, E, C, d_bw, d_pre_h, stream):
+def lcao_msg_bwd(d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h, stream):
     s = view(src32, E, dtype=I32).long()
     g = view(d_agg, int(s.max()) + 1, C, ld=lda)[s]
     p = view(pre_h, E, C)
-    sg = torch.sigmoid(p)
-    view(d_bw, E, C).copy_(g * (view(h, E, C) if h else p * sg))
-    view(d_pre_h, E, C).copy_(g * view(bw, E, C) * (sg * (1 + p * (1 - sg))))
+    view(d_bw, E, C).copy_(g * (view(h, E, C) if h else _act(p, act)))
+    view(d_pre_h, E, C).copy_(g * view(bw, E, C) * _act_grad(p, act))
 
 
 def lcao_gather_rows(table, ldt, idx, is64, mul, ldm, n, W, out, ldo, stream):
@@ -522,10 +536,8 @@ def lcao_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, mode, st
 
 def _dy_eff(dY, ldy, H, ldh, act, M, Nout):
     d = view(dY, M, Nout, ld=ldy)
-    if act == 1 and H:
-        h = view(H, M, Nout, ld=ldh)
-        s = torch.sigmoid(h)
-        d = d * (s * (1 + h * (1 - s)))
+    if act != 0 and H:
+        d = d * _act_grad(view(H, M, Nout, ld=ldh), act)
     return d
 
 
@@ -537,9 +549,7 @@ def lcao_linear_dgrad(dY, ldy, H, ldh, act, W, dX, ldx, M, K, Nout, accumulate, 
 
 def lcao_linear_dgrad_act(dY, ldy, W, G, ldg, act, dX, ldx, M, K, Nout, mode, stream):
     v = view(dY, M, Nout, ld=ldy) @ view(W, Nout, K)
-    h = view(G, M, K, ld=ldg)
-    sg = torch.sigmoid(h)
-    view(dX, M, K, ld=ldx).copy_(v * (sg * (1 + h * (1 - sg))))
+    view(dX, M, K, ld=ldx).copy_(v * _act_grad(view(G, M, K, ld=ldg), act))
 
 
 def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, scratch, stream):
@@ -551,10 +561,8 @@ def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, sc
 
 def lcao_act_bwd(dY, ldy, H, ldh, dH, ldd, M, Cc, act, stream):
     g = view(dY, M, Cc, ld=ldy)
-    if act == 1:
-        h = view(H, M, Cc, ld=ldh)
-        s = torch.sigmoid(h)
-        g = g * (s * (1 + h * (1 - s)))
+    if act != 0:
+        g = g * _act_grad(view(H, M, Cc, ld=ldh), act)
     view(dH, M, Cc, ld=ldd).copy_(g)
 
 

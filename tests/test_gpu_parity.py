@@ -15,7 +15,7 @@ from tests._util import full_cfg, graph_as, load_golden, rel_l2, same_triplets_u
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN_CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
-                "fixture_cosine_minmaxorb_atomref"]
+                "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus", "qm9_gelu_valence"]
 
 
 # ---------------------------------------------------------------------------- index construction
@@ -465,3 +465,41 @@ def test_long_exclusive_scans_are_exact():
         ref[1:] = (deg_in[ei[0]] - (ei[0] == ei[1]).long()).cumsum(0)
         assert torch.equal(gi.tri_ptr.cpu().long(), ref)
         assert torch.equal(gi.in_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), deg_in.cumsum(0)]))
+
+
+@pytest.mark.parametrize("name", ["silu", "shiftedsoftplus", "softplus", "relu", "tanh", "sigmoid", "gelu", "elu", "leakyrelu"])
+@pytest.mark.parametrize("M", [300, 5000])  # CUDA-core and tcgen05 paths
+def test_fused_activations_fwd_bwd(name, M):
+    """every LCAO_ACT_* kind through the dense layer (epilogue + act' backward) and the edge gather-add, against torch."""
+    import math
+
+    from lcaonet_b200._lib import ACT
+    F = torch.nn.functional
+    ref_fn = {"silu": F.silu, "shiftedsoftplus": lambda v: F.softplus(v) - math.log(2.0), "softplus": F.softplus, "relu": F.relu,
+              "tanh": torch.tanh, "sigmoid": torch.sigmoid, "gelu": F.gelu, "elu": F.elu, "leakyrelu": F.leaky_relu}[name]
+    torch.manual_seed(1)
+    K = N = 128
+    x = (2.0 * torch.randn(M, K)).to(DEV).requires_grad_(True)
+    w = (torch.randn(N, K) / K**0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(N).to(DEV).requires_grad_(True)
+    dy = torch.randn(M, N).to(DEV)
+    y = ops.linear(x, w, b, ACT[name])
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), dy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = ref_fn(F.linear(xd, wd, bd))
+    rx, rw, rb = torch.autograd.grad(yr, (xd, wd, bd), dy.double())
+    assert rel_l2(y, yr) < 3e-6
+    assert rel_l2(gx, rx) < 1e-5 and rel_l2(gw, rw) < 1e-5 and rel_l2(gb, rb) < 1e-5
+    # gather-add + activation per edge
+    g = qm9_like_batch(4, seed=9)
+    gi = ops.GraphIndex(g["edge_index"].to(DEV), g["z"].shape[0])
+    a = torch.randn(gi.N, 64, device=DEV, requires_grad=True)
+    c = torch.randn(gi.N, 64, device=DEV, requires_grad=True)
+    out = ops.edge_pair(a, c, None, gi, ACT[name])
+    do = torch.randn_like(out)
+    ga, gc = torch.autograd.grad(out, (a, c), do)
+    ad, cd = a.detach().double().requires_grad_(True), c.detach().double().requires_grad_(True)
+    ei = g["edge_index"].to(DEV)
+    outr = ref_fn(ad[ei[0]] + cd[ei[1]])
+    ra, rc = torch.autograd.grad(outr, (ad, cd), do.double())
+    assert rel_l2(out, outr) < 1e-6 and rel_l2(ga, ra) < 1e-5 and rel_l2(gc, rc) < 1e-5

@@ -10,7 +10,7 @@ from tests import cpu_abi
 from tests._util import load_golden, rel_l2, same_triplets_up_to_duplicate_order
 
 CASES = ["qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
-         "fixture_cosine_minmaxorb_atomref", "qm9_default"]
+         "fixture_cosine_minmaxorb_atomref", "qm9_default", "qm9_shiftedsoftplus", "qm9_gelu_valence"]
 
 
 def _run(name, monkeypatch):
@@ -123,8 +123,14 @@ def test_constructor_errors():
         LCAONet(max_z=0)
     with pytest.raises(ValueError):
         LCAONet(weight_init="nope")
+    with pytest.raises(ValueError):
+        LCAONet(activation="nope")
+    with pytest.raises(NotImplementedError):  # trainable beta: not fused into the kernels
+        LCAONet(activation="swish")
     with pytest.raises(NotImplementedError):
-        LCAONet(activation="ReLU")
+        LCAONet(activation="PReLU")
+    for name in ("ReLU", "shifted_softplus", "Tanh", "gelu", "ELU", "leaky-relu", "softplus", "sigmoid", "SiLU"):
+        LCAONet(activation=name, emb_size=8, emb_size_coeff=8, emb_size_conv=8, n_interaction=1)
 
 
 def test_cpu_tensors_are_rejected_without_the_emulator():
