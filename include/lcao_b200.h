@@ -250,6 +250,9 @@ int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, in
 /* dH = dY * act'(H)  elementwise over (M,C) with row strides (in place allowed: dH == dY) */
 int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
                  int32_t C, int32_t act, void* stream);
+/* Y = act(X) elementwise over (M,C) with row strides (in place allowed).  lcao_linear_fwd's tcgen05 epilogue fuses
+ * SiLU; the other LCAO_ACT_* kinds run as this pass over the GEMM's output. */
+int lcao_act_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M, int32_t C, int32_t act, void* stream);
 
 #ifdef __cplusplus
 }

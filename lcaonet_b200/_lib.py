@@ -66,6 +66,7 @@ SIGNATURES = {
     "lcao_linear_dgrad_act": [_p, _i64, _p, _p, _i64, _i32, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "lcao_linear_wgrad": [_p, _i64, _p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _p],
     "lcao_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p],
+    "lcao_act_fwd": [_p, _i64, _p, _i64, _i64, _i32, _i32, _p],
 }
 
 _lib = None

@@ -84,11 +84,19 @@ __device__ __forceinline__ float act_gradf(int act, float x) {
     default: return 1.0f;
   }
 }
+// GEN = false: SiLU only.  The bandwidth-bound edge kernels are instantiated twice so that the default activation does
+// not carry the code (and registers) of the other eight.
+template <bool GEN>
+__device__ __forceinline__ float act_fwd_t(int act, float x) { return GEN ? act_fwdf(act, x) : siluf(x); }
+template <bool GEN>
+__device__ __forceinline__ float act_grad_t(int act, float x) { return GEN ? act_gradf(act, x) : silu_gradf(x); }
+template <bool GEN>
 __device__ __forceinline__ float4 act_fwd4(int act, float4 v) {
-  return make_float4(act_fwdf(act, v.x), act_fwdf(act, v.y), act_fwdf(act, v.z), act_fwdf(act, v.w));
+  return make_float4(act_fwd_t<GEN>(act, v.x), act_fwd_t<GEN>(act, v.y), act_fwd_t<GEN>(act, v.z), act_fwd_t<GEN>(act, v.w));
 }
+template <bool GEN>
 __device__ __forceinline__ float4 act_grad4(int act, float4 v) {
-  return make_float4(act_gradf(act, v.x), act_gradf(act, v.y), act_gradf(act, v.z), act_gradf(act, v.w));
+  return make_float4(act_grad_t<GEN>(act, v.x), act_grad_t<GEN>(act, v.y), act_grad_t<GEN>(act, v.z), act_grad_t<GEN>(act, v.w));
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

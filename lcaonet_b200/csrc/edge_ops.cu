@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* 
 // ---------------------------------------------------------------------------------------------
 // out[e,:] = act(a[src[e],:] + b[dst[e],:] + bias)
 // ---------------------------------------------------------------------------------------------
+template <bool GEN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_edge_pair_fwd(
     const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, const float* __restrict__ bias,
     const int32_t* __restrict__ src32, const int32_t* __restrict__ dst32, int64_t E, int C, int act,
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_edge_pair_fwd(
     float4 v = f4_add(ldg4(pa + c), ldg4(pb + c));
     if (bias) v = f4_add(v, ldg4(bias + c));
     if (pre) st4(pre + e * (int64_t)C + c, v);
-    if (act != LCAO_ACT_NONE) v = act_fwd4(act, v);
+    if (act != LCAO_ACT_NONE) v = act_fwd4<GEN>(act, v);
     st4(out + e * (int64_t)C + c, v);
   }
 }
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_edge_pair_fwd(
 // sorted-segment sum: out[r,:] = scale_r * sum_{j in seg r} x[perm[j],:] (* y[perm[j],:])
 // warp per output row; vector path when C % 4 == 0 and all strides % 4 == 0, scalar path otherwise
 // ---------------------------------------------------------------------------------------------
-template <bool VEC>
+template <bool VEC, bool GEN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
     const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ ptr,
     const int32_t* __restrict__ perm, int64_t R, int C, int mean, float* __restrict__ out, int64_t ldo) {
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
         float4 v = ldg4(x + i * ldx + c);
         if (y) {
           float4 w = ldg4(y + i * ldy + c);
-          if (ysilu) w = act_fwd4(act, w);
-          if (ygrad) w = act_grad4(act, w);
+          if (ysilu) w = act_fwd4<GEN>(act, w);
+          if (ygrad) w = act_grad4<GEN>(act, w);
           v = f4_mul(v, w);
         }
         acc = f4_add(acc, v);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
       for (int32_t j = lo; j < hi; ++j) {
         const int64_t i = perm ? perm[j] : j;
         float v = x[i * ldx + c];
-        if (y) v *= ysilu ? act_fwdf(act, y[i * ldy + c]) : ygrad ? act_gradf(act, y[i * ldy + c]) : y[i * ldy + c];
+        if (y) v *= ysilu ? act_fwd_t<GEN>(act, y[i * ldy + c]) : ygrad ? act_grad_t<GEN>(act, y[i * ldy + c]) : y[i * ldy + c];
         acc += v;
       }
       out[r * ldo + c] = scale * acc;
@@ -317,6 +318,16 @@ __global__ void __launch_bounds__(256) k_reduce_by_key(const float* __restrict__
   }
 }
 
+// Y = act(X) elementwise (the activations the tcgen05 epilogue does not fuse); X may alias Y
+__global__ void k_act_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M, int C4, int act) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= M * C4) return;
+  const int64_t i = t / C4;
+  const int c = (int)(t - i * C4) * 4;
+  st4(Y + i * ldy + c, act_fwd4<true>(act, *reinterpret_cast<const float4*>(X + i * ldx + c)));
+}
+
+template <bool GEN>
 __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float* __restrict__ H, int64_t ldh,
                           float* __restrict__ dH, int64_t ldd, int64_t M, int C4, int act) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -324,12 +335,13 @@ __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float
   const int64_t i = t / C4;
   const int c = (int)(t - i * C4) * 4;
   float4 g = *reinterpret_cast<const float4*>(dY + i * ldy + c);
-  if (act != LCAO_ACT_NONE) g = f4_mul(g, act_grad4(act, ldg4(H + i * ldh + c)));
+  if (act != LCAO_ACT_NONE) g = f4_mul(g, act_grad4<GEN>(act, ldg4(H + i * ldh + c)));
   st4(dH + i * ldd + c, g);
 }
 
 // backward of  agg[s] = sum_{e in out(s)} bw[e] * h[e]  with  h = SiLU(pre_h):
 //   d_bw[e] = d_agg[src[e]] * h[e] ;  d_pre_h[e] = d_agg[src[e]] * bw[e] * SiLU'(pre_h[e])
+template <bool GEN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
     const float* __restrict__ d_agg, int64_t lda, const int32_t* __restrict__ src32, const float* __restrict__ h,
     const float* __restrict__ bw, const float* __restrict__ pre_h, int64_t E, int C, int act, float* __restrict__ d_bw,
@@ -341,9 +353,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
   for (int c = lane * 4; c < C; c += 128) {
     const float4 g = ldg4(pa + c), b = ldg4(bw + e * (int64_t)C + c);
     const float4 p = ldg4(pre_h + e * (int64_t)C + c);
-    const float4 hv = h ? ldg4(h + e * (int64_t)C + c) : act_fwd4(act, p);
+    const float4 hv = h ? ldg4(h + e * (int64_t)C + c) : act_fwd4<GEN>(act, p);
     st4(d_bw + e * (int64_t)C + c, f4_mul(g, hv));
-    st4(d_pre_h + e * (int64_t)C + c, f4_mul(f4_mul(g, b), act_grad4(act, p)));
+    st4(d_pre_h + e * (int64_t)C + c, f4_mul(f4_mul(g, b), act_grad4<GEN>(act, p)));
   }
 }
 
@@ -445,8 +457,12 @@ extern "C" int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, i
   LCAO_REQUIRE(a && b && src32 && dst32 && out, "lcao_edge_pair_fwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(out),
                "lcao_edge_pair_fwd: need C, lda, ldb multiples of 4 and 16-byte aligned buffers");
-  k_edge_pair_fwd<<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
-      a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre);
+  if (act == LCAO_ACT_NONE || act == LCAO_ACT_SILU)
+    k_edge_pair_fwd<false><<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre);
+  else
+    k_edge_pair_fwd<true><<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -461,8 +477,12 @@ extern "C" int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int
                    aligned16(out) && (!y || aligned16(y));
   const unsigned grid = (unsigned)ceil_div64(R, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) k_segment_sum<true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
-  else k_segment_sum<false><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
+  const int kind = (mean >> 4) & 15;
+  LCAO_REQUIRE(kind <= LCAO_ACT_LAST, "lcao_segment_sum: unsupported activation %d", kind);
+  const bool gen = (mean & 6) != 0 && kind > LCAO_ACT_SILU;  // only the non-default activations take the generic kernel
+  if (vec && !gen) k_segment_sum<true, false><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
+  else if (vec) k_segment_sum<true, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
+  else k_segment_sum<false, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -503,7 +523,20 @@ extern "C" int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_
   LCAO_REQUIRE(dY && dH && (act == LCAO_ACT_NONE || H), "lcao_act_bwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && ldd % 4 == 0 && (act == LCAO_ACT_NONE || ldh % 4 == 0),
                "lcao_act_bwd: need C and strides multiples of 4");
-  k_act_bwd<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
+  const unsigned grid = (unsigned)ceil_div64(M * (C / 4), 256);
+  if (act <= LCAO_ACT_SILU) k_act_bwd<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
+  else k_act_bwd<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_act_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M, int32_t C, int32_t act,
+                            void* stream) {
+  if (M == 0 || C == 0) return LCAO_OK;
+  LCAO_REQUIRE(X && Y && act >= LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_act_fwd: bad arguments");
+  LCAO_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(X) && aligned16(Y),
+               "lcao_act_fwd: need C and strides multiples of 4, 16-byte aligned buffers");
+  k_act_fwd<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, Y, ldy, M, C / 4, act);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -526,8 +559,12 @@ extern "C" int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src3
   LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && aligned16(d_agg) && (!h || aligned16(h)) && aligned16(bw) && aligned16(pre_h) &&
                    aligned16(d_bw) && aligned16(d_pre_h),
                "lcao_msg_bwd: need C, lda multiples of 4 and 16-byte aligned buffers");
-  k_msg_bwd<<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw,
-                                                                                                pre_h, E, C, act, d_bw, d_pre_h);
+  LCAO_REQUIRE(act > LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_msg_bwd: unsupported activation %d", act);
+  const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
+  if (act == LCAO_ACT_SILU)
+    k_msg_bwd<false><<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h);
+  else
+    k_msg_bwd<true><<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -174,8 +174,7 @@ struct RowsArgs {
   const float* A; int64_t lda;
   const float* W; int64_t ldw;
   const float* bias;
-  const float* G; int64_t ldg;     // epilogue: out *= act'(G) (dgrad chained into the previous layer's pre-activation)
-  int gact;                        // ... the activation of that factor (LCAO_ACT_*)
+  const float* G; int64_t ldg;     // epilogue: out *= SiLU'(G) (dgrad chained into the previous layer's pre-activation)
   float* Y; int64_t ldy;
   float* pre; int64_t ldp;
   int64_t M; int Kc; int Nb;
@@ -428,19 +427,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
               if (g.act == LCAO_ACT_SILU) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
-              } else if (g.act != LCAO_ACT_NONE) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = act_fwdf(g.act, o[q]);
               }
               if (g.G) {
                 const float4 h0 = gq[j / 4], h1 = gq[j / 4 + 1];
-                if (g.gact == LCAO_ACT_SILU) {
-                  o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
-                  o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
-                } else {
-                  o[0] *= act_gradf(g.gact, h0.x); o[1] *= act_gradf(g.gact, h0.y); o[2] *= act_gradf(g.gact, h0.z); o[3] *= act_gradf(g.gact, h0.w);
-                  o[4] *= act_gradf(g.gact, h1.x); o[5] *= act_gradf(g.gact, h1.y); o[6] *= act_gradf(g.gact, h1.z); o[7] *= act_gradf(g.gact, h1.w);
-                }
+                o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
+                o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
               }
               if (!(g.debug & 1)) store8(g.Y + m * g.ldy + c0 + j, o, wide);
             }
@@ -760,9 +751,8 @@ bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const 
 
 int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b_trans, const float* bias, const float* G,
                  int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
-                 int accumulate, int x3, cudaStream_t st, int gact) {
+                 int accumulate, int x3, cudaStream_t st) {
   RowsArgs g{};
-  g.gact = gact;
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.G = G; g.ldg = ldg; g.Y = Y; g.ldy = ldy;
   g.pre = pre; g.ldp = ldp; g.M = M; g.Kc = Kc; g.Nb = Nb; g.b_trans = b_trans; g.act = act; g.accumulate = accumulate;
   g.x3 = x3;

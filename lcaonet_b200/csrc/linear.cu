@@ -12,7 +12,7 @@ int lcao_simt_linear_wgrad(const float*, int64_t, const float*, int64_t, float*,
 bool lcao_tc_rows_ok(int64_t M, int Kc, int Nb, int64_t lda, int64_t ldy, const void* A, const void* Y);
 int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b_trans, const float* bias, const float* G,
                  int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
-                 int accumulate, int x3, cudaStream_t st, int gact = LCAO_ACT_SILU);
+                 int accumulate, int x3, cudaStream_t st);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
                   int Kx, int x3, float* part, cudaStream_t st);
@@ -31,12 +31,19 @@ extern "C" int lcao_linear_fwd(const float* X, int64_t ldx, const float* W, cons
   const bool tc = mode != LCAO_GEMM_FP32 && Nout % 16 == 0 && K <= 128 && al16(W) && (!bias || al16(bias)) &&
                   (!pre || (al16(pre) && ldp % 4 == 0)) && lcao_tc_rows_ok(M, K, imin(Nout, 128), ldx, ldy, X, Y);
   if (!tc) return lcao_simt_linear_fwd(X, ldx, W, bias, Y, ldy, pre, ldp, M, K, Nout, act, st);
+  // the tcgen05 epilogue fuses SiLU only (the reference default); the other activations run as one elementwise pass
+  // over the GEMM's output, which keeps the hot kernel free of their code
+  const bool post = act != LCAO_ACT_NONE && act != LCAO_ACT_SILU;
+  float* out = (post && pre) ? pre : Y;
+  const int64_t ldo = (post && pre) ? ldp : ldy;
   for (int n0 = 0; n0 < Nout; n0 += 128) {
     const int nb = imin(128, Nout - n0);
-    int rc = lcao_tc_rows(X, ldx, W + (int64_t)n0 * K, K, 0, bias ? bias + n0 : nullptr, nullptr, 0, Y + n0, ldy,
-                          pre ? pre + n0 : nullptr, ldp, M, K, nb, act, 0, mode == LCAO_GEMM_TF32X3, st);
+    int rc = lcao_tc_rows(X, ldx, W + (int64_t)n0 * K, K, 0, bias ? bias + n0 : nullptr, nullptr, 0, out + n0, ldo,
+                          (pre && !post) ? pre + n0 : nullptr, ldp, M, K, nb, post ? LCAO_ACT_NONE : act, 0,
+                          mode == LCAO_GEMM_TF32X3, st);
     if (rc) return rc;
   }
+  if (post) return lcao_act_fwd(out, ldo, Y, ldy, M, Nout, act, stream);
   return LCAO_OK;
 }
 
@@ -98,8 +105,6 @@ extern "C" int lcao_linear_dgrad(const float* dY, int64_t ldy, const float* H, i
   return LCAO_OK;
 }
 
-extern "C" int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_t ldh, float* dH, int64_t ldd, int64_t M,
-                            int32_t C, int32_t act, void* stream);
 
 // dX = (dY W) * act'(G): the data gradient of a layer whose INPUT came out of an activation with pre-activation G.
 // The tcgen05 kernel applies the factor in its epilogue (last contraction chunk), which saves the separate
@@ -116,13 +121,18 @@ extern "C" int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* 
     if (rc) return rc;
     return lcao_act_bwd(dX, ldx, G, ldg, dX, ldx, M, K, act, stream);  // elementwise, in place
   }
+  if (act != LCAO_ACT_SILU) {  // (the tcgen05 epilogue fuses SiLU' only)
+    int rc = lcao_linear_dgrad(dY, ldy, nullptr, 0, LCAO_ACT_NONE, W, dX, ldx, M, K, Nout, 0, mode, nullptr, stream);
+    if (rc) return rc;
+    return lcao_act_bwd(dX, ldx, G, ldg, dX, ldx, M, K, act, stream);
+  }
   for (int n0 = 0; n0 < K; n0 += 128) {          // output columns
     const int nb = imin(128, K - n0);
     for (int c0 = 0; c0 < Nout; c0 += 128) {     // contraction chunks; the factor goes on the last one
       const int kc = imin(128, Nout - c0);
       const bool last = c0 + 128 >= Nout;
       int rc = lcao_tc_rows(dY + c0, ldy, W + (int64_t)c0 * K + n0, K, 1, nullptr, last ? G + n0 : nullptr, ldg, dX + n0, ldx,
-                            nullptr, 0, M, kc, nb, LCAO_ACT_NONE, c0 > 0, mode == LCAO_GEMM_TF32X3, st, act);
+                            nullptr, 0, M, kc, nb, LCAO_ACT_NONE, c0 > 0, mode == LCAO_GEMM_TF32X3, st);
       if (rc) return rc;
     }
   }

@@ -559,6 +559,10 @@ def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, sc
         view(db, Nout).add_(d.sum(0))
 
 
+def lcao_act_fwd(X, ldx, Y, ldy, M, Cc, act, stream):
+    view(Y, M, Cc, ld=ldy).copy_(_act(view(X, M, Cc, ld=ldx).clone(), act))
+
+
 def lcao_act_bwd(dY, ldy, H, ldh, dH, ldd, M, Cc, act, stream):
     g = view(dY, M, Cc, ld=ldy)
     if act != 0:
