@@ -317,7 +317,7 @@ def run_ours(args):
     def e2e_step():
         b = host.to(dev, non_blocking=True)
         loss = step(b, b["y"])
-        return float(loss)  # D2H read of the step's result (synchronises)
+        return float(loss.detach())  # D2H read of the step's result (synchronises)
 
     for _ in range(2):
         e2e_step()

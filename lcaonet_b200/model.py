@@ -230,6 +230,11 @@ class LCAOEmbedding(nn.Module):
                     for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if b is not None]
             saved = [b.clone() for b in bufs]
             holder = _EmbedTables(self)
+            # (capture runs on a side stream: the AccumulateGrad nodes of the parameters then live on another stream
+            # than the replayed backward, which autograd reports once per process; the accumulation itself is ordered)
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
             cache[key] = torch.cuda.make_graphed_callables(holder, (cnt_z.clone(), cnt_pair.clone()),
                                                            allow_unused_input=True)
             with torch.no_grad():
