@@ -196,7 +196,9 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
+// EPI8: four more epilogue warps (13-16); the two warps of a TMEM lane quadrant take 64 output columns each
+template <bool RP, bool EPI8>
+__global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (g.debug & 32) return;  // (ablation: launch cost only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,13 +229,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
       mbar_init(&raw_full[s], kLoadWarps * 32);
-      mbar_init(&full[s], 4 * 32);
+      mbar_init(&full[s], RP ? 8 * 32 : 4 * 32);
       mbar_init(&hi_empty[s], 1);
     }
     for (int s = 0; s < L; ++s) mbar_init(&lo_empty[s], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], kEpiWarps * 32);
+      mbar_init(&tempty[a], (EPI8 ? 2 : 1) * kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -246,6 +248,36 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
     return;
+  }
+
+  // ---- RP (register-prefetch producers): the 8 warps 4-7 and 9-12 stream A with plain 128-bit loads into REGISTERS,
+  //      three 16 KB chunks ahead of the one they split and store, so the bytes in flight (48 KB per SM) live in the
+  //      register file and a shared-memory stage is only occupied from its store to the commit of its MMAs.  The
+  //      cp.async path below keeps the in-flight bytes in the stages themselves (3 x 16 KB beside the 128 KB weight).
+  const bool is_prod = RP && ((warp >= 9 && warp < 13) || (warp >= 4 && warp < 8));
+  const int pidx = ((warp >= 9 ? warp - 5 : warp - 4) << 5) | lane;  // 0..255 among the producers
+  const int pc = pidx & 7, pr = pidx >> 3;                           // 16-byte column / row (+ 32 j) inside a chunk
+  float4 rbuf[4][4];
+  int64_t ld_mb = blockIdx.x;
+  int ld_kc = 0;
+  uint32_t ld_q = 0, rp_total = 0;
+  auto issue_load = [&](float4 (&b)[4]) {
+    if (ld_q < rp_total) {
+      const int64_t row0 = ld_mb * kBlockM + pr;
+      const float* src = g.A + row0 * g.lda + ld_kc * kChunkK + pc * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b[j] = (row0 + 32 * j < g.M && !(g.debug & 2)) ? ldg4(src + (int64_t)32 * j * g.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (++ld_kc == nchunk) { ld_kc = 0; ld_mb += gridDim.x; }
+      ++ld_q;
+    }
+  };
+  if (is_prod) {
+    const int64_t my_tiles = nblocks > (int64_t)blockIdx.x ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    rp_total = (uint32_t)(my_tiles * nchunk);
+    issue_load(rbuf[0]);
+    issue_load(rbuf[1]);
+    issue_load(rbuf[2]);
   }
 
   // ---- resident B operand (the layer's weight), split hi/lo once per CTA by the 9 non-loader warps while the
@@ -288,7 +320,38 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");  // weights complete (non-loader warps only)
   }
 
-  if (warp >= 9) {
+  if (is_prod) {
+    // ============================== producers: registers -> hi / lo stages ==============================
+    uint32_t it = 0;
+    for (uint32_t q = 0; q < rp_total; q += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q + u < rp_total) {
+          issue_load(rbuf[(u + 3) & 3]);  // chunk q + u + 3
+          const int s = it % R, l = it % L;
+          mbar_wait(&hi_empty[s], ((it / R) & 1) ^ 1);
+          if (g.x3) mbar_wait(&lo_empty[l], ((it / L) & 1) ^ 1);
+          uint8_t* ph = sHi + (size_t)s * kStageBytes;
+          uint8_t* pl = sLo + (size_t)l * kStageBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = sw128_off(pr + 32 * j, pc);
+            if (g.x3 && !(g.debug & 16)) {
+              float4 hi, lo;
+              split4(rbuf[u][j], hi, lo);
+              *reinterpret_cast<float4*>(ph + off) = hi;
+              *reinterpret_cast<float4*>(pl + off) = lo;
+            } else {
+              *reinterpret_cast<float4*>(ph + off) = rbuf[u][j];  // (the tensor core ignores the low mantissa bits)
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&full[s]);
+          ++it;
+        }
+      }
+    }
+  } else if (!RP && warp >= 9 && warp < 13) {
     // ============================== loader warps ==============================
     // warp lw streams rows [32 lw, 32 lw + 32) of the tile: 8 copies per lane and stage; lanes 0-7 / 8-15 / ...
     // cover one 128-byte row each (global) and write its 8 chunks into one swizzled 128-byte smem line
@@ -312,7 +375,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
         cp_async_arrive(&raw_full[s]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (!RP && warp >= 4 && warp < 8) {
     // ============================== split warps: hi in place, lo into the short ring =================
     const int t = threadIdx.x - 128;              // 0..127
     uint32_t it = 0;
@@ -380,31 +443,34 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
     // with 256-bit stores: every store instruction of a thread fills one whole 32-byte sector, so no shared-memory
     // transpose is needed (and its 18 KB go to the operand ring).
     const bool wide = g.wide_store != 0;
+    const int quad = warp & 3;  // TMEM lanes 32 quad .. 32 quad + 31 (a warp reaches the quadrant warp % 4)
+    const int c_begin = (EPI8 && warp >= 13) ? 64 : 0, c_end = EPI8 ? min(g.Nb, c_begin + 64) : g.Nb;
     uint32_t tile = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
       const int acc = tile & 1;
-      const int64_t m = mb * kBlockM + warp * 32 + lane;
+      const int64_t m = mb * kBlockM + quad * 32 + lane;
       // The SiLU' factor rows (G) are fetched one 32-column chunk AHEAD of their use — the first chunk while the
       // tile's MMAs are still running — so that the epilogue never waits on HBM between a TMEM load and its stores.
       float4 gq[8];
       if (g.G && m < g.M) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) gq[q] = (4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 8; ++q)
+          gq[q] = (c_begin + 4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + c_begin + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < ((g.debug & 8) ? 0 : g.Nb); c0 += 32) {
+      for (int c0 = c_begin; c0 < ((g.debug & 8) ? 0 : c_end); c0 += 32) {
         float4 gn[8];
-        if (g.G && m < g.M && c0 + 32 < g.Nb) {
+        if (g.G && m < g.M && c0 + 32 < c_end) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             gn[q] = (c0 + 32 + 4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + c0 + 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + c0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + c0, v);
         if (g.x3) {
           float w[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols + g.Nb + c0, w);
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + g.Nb + c0, w);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
         }
@@ -774,12 +840,21 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   const size_t smem = rows_smem(Kc, Nb, stages, lo_stages);
   static bool attr_set = false;
   if (!attr_set) {
-    LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     attr_set = true;
   }
+  static const int rp = getenv("LCAO_TC_RP") ? atoi(getenv("LCAO_TC_RP")) : 0;
   const int64_t nblocks = (M + kBlockM - 1) / kBlockM;
   const unsigned grid = (unsigned)(nblocks < num_sms() ? nblocks : num_sms());
-  k_tc_rows<<<grid, kRowsThreads, smem, st>>>(g);
+  // eight epilogue warps pay when a CTA has a single tile (node- and table-sized layers: the drain is on the critical
+  // path, 20.5 -> 18.4 us); with many tiles per CTA the drain overlaps the next tile's MMAs and they do not (85 -> 88 us)
+  static const int epi8_env = getenv("LCAO_TC_EPI8") ? atoi(getenv("LCAO_TC_EPI8")) : -1;
+  const bool epi8 = epi8_env >= 0 ? epi8_env != 0 : nblocks <= num_sms();
+  if (rp) k_tc_rows<true, false><<<grid, kRowsThreads, smem, st>>>(g);
+  else if (epi8) k_tc_rows<false, true><<<grid, kRowsThreads + 128, smem, st>>>(g);
+  else k_tc_rows<false, false><<<grid, kRowsThreads, smem, st>>>(g);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
