@@ -175,22 +175,96 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_drb(
   const int lane = threadIdx.x & 31;
   const int Cp = VAL ? 2 * C : C, NG = NL + (VAL ? 1 : 0);
   const float* row = tab + pair[e] * (int64_t)O * Cp;
-  for (int o = 0; o < O; ++o) {
-    const int l = lgrp[o];
-    const float m = VAL ? __ldg(vmask + e * O + o) : 0.f;
-    float dot = 0.f;
+  // eight orbitals at a time: the edge's gradient rows are read once per 128-column slice, the eight table rows are
+  // independent loads, and the eight dots are reduced together by one 9-shuffle butterfly (the per-orbital form paid
+  // a dependent load + 5 shuffles per orbital)
+  for (int ob = 0; ob < O; ob += 8) {
+    float part[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) part[u] = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
-      const float4 g = ldg4(dB + (e * NG + l) * (int64_t)C + c);
-      const float4 a = ldg4(row + (int64_t)o * Cp + c);
-      dot += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
-      if (VAL) {
-        const float4 gv = f4add(g, ldg4(dB + (e * NG + NL) * (int64_t)C + c));
-        const float4 v = ldg4(row + (int64_t)o * Cp + C + c);
-        dot += m * (v.x * gv.x + v.y * gv.y + v.z * gv.z + v.w * gv.w);
+      float4 g[4], gv = f4z();
+#pragma unroll
+      for (int l = 0; l < 4; ++l) g[l] = l < NL ? ldg4(dB + (e * NG + l) * (int64_t)C + c) : f4z();
+      if (VAL) gv = ldg4(dB + (e * NG + NL) * (int64_t)C + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int o = ob + u;
+        if (o < O) {  // warp-uniform
+          const int l = lgrp[o];
+          const float4 gl = l == 0 ? g[0] : l == 1 ? g[1] : l == 2 ? g[2] : g[3];
+          const float4 a = ldg4(row + (int64_t)o * Cp + c);
+          part[u] += a.x * gl.x + a.y * gl.y + a.z * gl.z + a.w * gl.w;
+          if (VAL) {
+            const float4 s = f4add(gl, gv);
+            const float4 v = ldg4(row + (int64_t)o * Cp + C + c);
+            part[u] += __ldg(vmask + e * O + o) * (v.x * s.x + v.y * s.y + v.z * s.z + v.w * s.w);
+          }
+        }
       }
     }
-    dot = warp_sum(dot);
-    if (lane == 0) d_rb[e * O + o] = dot;
+    const float tot = bfly8(part, lane);
+    const int o = ob + bfly8_index(lane);
+    if ((lane & 3) == 0 && o < O) d_rb[e * O + o] = tot;
+  }
+}
+
+// The same for C <= 128, walking the edges in PAIR-SORTED order (kperm): a warp takes 16 consecutive sorted positions
+// and keeps the eight table rows of the current pair in registers, so the 4 KB of table rows are fetched once per run
+// of equal pairs instead of once per edge (crystals with 36 species: 824 MB of L2 reads per call, 280 us -> see notes).
+template <bool VAL>
+__global__ void __launch_bounds__(kWarps * 32) k_pair_contract_drb_sorted(
+    const float* __restrict__ tab, const int64_t* __restrict__ pair, const int32_t* __restrict__ kperm,
+    const float* __restrict__ vmask, const int32_t* __restrict__ lgrp, const float* __restrict__ dB, int64_t E, int O,
+    int C, int NL, float* __restrict__ d_rb) {
+  constexpr int kRun = 16;
+  const int64_t j0 = (blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * kRun;
+  if (j0 >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int n = (int)min((int64_t)kRun, E - j0);
+  const int Cp = VAL ? 2 * C : C, NG = NL + (VAL ? 1 : 0);
+  const bool ok = lane * 4 < C;
+  const int c = lane * 4;
+  const int my_e = kperm[j0 + min(lane, n - 1)];
+  const int64_t my_p = pair[my_e];
+  for (int ob = 0; ob < O; ob += 8) {
+    int lg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) lg[u] = lgrp[min(ob + u, O - 1)];
+    int64_t cur = -1;
+    float4 trow[8], vrow[VAL ? 8 : 1];
+    for (int t = 0; t < n; ++t) {
+      const int64_t e = __shfl_sync(0xffffffffu, my_e, t);
+      const int64_t pk = __shfl_sync(0xffffffffu, my_p, t);
+      if (pk != cur) {  // warp-uniform
+        cur = pk;
+        const float* row = tab + pk * (int64_t)O * Cp;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool live = ok && ob + u < O;
+          trow[u] = live ? ldg4(row + (int64_t)(ob + u) * Cp + c) : f4z();
+          if (VAL) vrow[u] = live ? ldg4(row + (int64_t)(ob + u) * Cp + C + c) : f4z();
+        }
+      }
+      float4 g[4], gv = f4z();
+#pragma unroll
+      for (int l = 0; l < 4; ++l) g[l] = (l < NL && ok) ? ldg4(dB + (e * NG + l) * (int64_t)C + c) : f4z();
+      if (VAL && ok) gv = ldg4(dB + (e * NG + NL) * (int64_t)C + c);
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 gl = lg[u] == 0 ? g[0] : lg[u] == 1 ? g[1] : lg[u] == 2 ? g[2] : g[3];
+        part[u] = trow[u].x * gl.x + trow[u].y * gl.y + trow[u].z * gl.z + trow[u].w * gl.w;
+        if (VAL) {
+          const float4 s = f4add(gl, gv);
+          const float m = __ldg(vmask + e * O + min(ob + u, O - 1));
+          part[u] += m * (vrow[u].x * s.x + vrow[u].y * s.y + vrow[u].z * s.z + vrow[u].w * s.w);
+        }
+      }
+      const float tot = bfly8(part, lane);
+      const int o = ob + bfly8_index(lane);
+      if ((lane & 3) == 0 && o < O) d_rb[e * O + o] = tot;
+    }
   }
 }
 
@@ -282,17 +356,26 @@ __global__ void __launch_bounds__(256) k_pair_reduce_partial(
   }
 }
 
-// ---- stage 2: d_tab[key][o][:] = sum of the key's partials in chunk order (zeros for absent keys)
+// ---- stage 2: d_tab[key][o][:] = sum of the key's partials (zeros for absent keys).  CTA = (key, 32 float4 columns);
+// its 8 sub-rows each add every 8th chunk of the key in chunk order and the 8 sub-sums are combined in a fixed order:
+// deterministic, and a key that owns hundreds of chunks (one or two species in the batch: crystals) is summed by 8
+// independent chains of loads instead of one (355 us -> see profiles/r01_notes.md).
 __global__ void __launch_bounds__(256) k_pair_reduce_final(const int32_t* __restrict__ cptr, int P, int W4,
                                                            const float* __restrict__ partial,
                                                            float* __restrict__ d_tab) {
-  const int64_t t = blockIdx.x * 256ll + threadIdx.x;
-  if (t >= (int64_t)P * W4) return;
-  const int key = (int)(t / W4);
-  const int c = (int)(t - (int64_t)key * W4) * 4;
+  __shared__ float4 s_part[8][32];
+  const int key = blockIdx.x, col = blockIdx.y * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+  const int32_t q0 = cptr[key], q1 = cptr[key + 1];
   float4 acc = f4z();
-  for (int32_t q = cptr[key]; q < cptr[key + 1]; ++q) acc = f4add(acc, ldg4(partial + (int64_t)q * W4 * 4 + c));
-  st4(d_tab + (int64_t)key * W4 * 4 + c, acc);
+  if (col < W4)
+    for (int32_t q = q0 + sub; q < q1; q += 8) acc = f4add(acc, ldg4(partial + ((int64_t)q * W4 + col) * 4));
+  s_part[sub][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (sub == 0 && col < W4) {
+#pragma unroll
+    for (int u = 1; u < 8; ++u) acc = f4add(acc, s_part[u][threadIdx.x]);
+    st4(d_tab + ((int64_t)key * W4 + col) * 4, acc);
+  }
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -370,13 +453,19 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
     LCAO_LAUNCH_CHECK();
   }
   const int W4 = O * Cp / 4;
-  k_pair_reduce_final<<<(unsigned)ceil_div64(P * W4, 256), 256, 0, st>>>(cptr, (int)P, W4, partial, d_tab);
+  k_pair_reduce_final<<<dim3((unsigned)P, (unsigned)((W4 + 31) / 32)), 256, 0, st>>>(cptr, (int)P, W4, partial, d_tab);
   LCAO_LAUNCH_CHECK();
   if (d_rb && E > 0) {
     LCAO_REQUIRE(tab && pair, "lcao_pair_contract_bwd: d_rb needs tab and pair");
-    const unsigned grid = (unsigned)ceil_div64(E, kWarps);
-    if (valence) k_pair_contract_drb<true><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
-    else k_pair_contract_drb<false><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
+    if (C <= 128) {  // pair-sorted walk: table rows stay in registers across a run of equal pairs
+      const unsigned grid = (unsigned)ceil_div64(ceil_div64(E, 16), kWarps);
+      if (valence) k_pair_contract_drb_sorted<true><<<grid, kWarps * 32, 0, st>>>(tab, pair, kperm, vmask, lgrp, dB, E, O, C, NL, d_rb);
+      else k_pair_contract_drb_sorted<false><<<grid, kWarps * 32, 0, st>>>(tab, pair, kperm, vmask, lgrp, dB, E, O, C, NL, d_rb);
+    } else {
+      const unsigned grid = (unsigned)ceil_div64(E, kWarps);
+      if (valence) k_pair_contract_drb<true><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
+      else k_pair_contract_drb<false><<<grid, kWarps * 32, 0, st>>>(tab, pair, vmask, lgrp, dB, E, O, C, NL, d_rb);
+    }
     LCAO_LAUNCH_CHECK();
   }
   return LCAO_OK;

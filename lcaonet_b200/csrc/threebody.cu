@@ -97,30 +97,6 @@ __device__ __forceinline__ float comp4(const float4& a, int l) { return l == 0 ?
 
 // (Packed FP32 pairs — fma.rn.f32x2 / FFMA2 — were tried for the FMA blocks: same FP32 pipe rate (measured 36.8 vs
 // 36.2 TFMA/s, scripts/micro/ffma2.cu) and the forward kernel ran 2x SLOWER with them; see profiles/r01_notes.md.)
-// Sum 8 per-lane partials over the 32 lanes with 9 shuffles; every lane ends up with the total of
-// element  4*bit4(lane) + 2*bit3(lane) + bit2(lane).
-__device__ __forceinline__ float bfly8(const float (&p)[8], int lane) {
-  float q4[4], q2[2];
-  bool up = (lane & 16) != 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float recv = __shfl_xor_sync(0xffffffffu, up ? p[k] : p[k + 4], 16);
-    q4[k] = (up ? p[k + 4] : p[k]) + recv;
-  }
-  up = (lane & 8) != 0;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float recv = __shfl_xor_sync(0xffffffffu, up ? q4[k] : q4[k + 2], 8);
-    q2[k] = (up ? q4[k + 2] : q4[k]) + recv;
-  }
-  up = (lane & 4) != 0;
-  const float recv = __shfl_xor_sync(0xffffffffu, up ? q2[0] : q2[1], 4);
-  float r = (up ? q2[1] : q2[0]) + recv;
-  r += __shfl_xor_sync(0xffffffffu, r, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  return r;
-}
-__device__ __forceinline__ int bfly8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 
 // ---------------------------------------------------------------------------------------------
 // forward
