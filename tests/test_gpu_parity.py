@@ -503,3 +503,44 @@ def test_fused_activations_fwd_bwd(name, M):
     outr = ref_fn(ad[ei[0]] + cd[ei[1]])
     ra, rc = torch.autograd.grad(outr, (ad, cd), do.double())
     assert rel_l2(out, outr) < 1e-6 and rel_l2(ga, ra) < 1e-5 and rel_l2(gc, rc) < 1e-5
+
+
+def test_bucket_sort_many_buckets_multi_block_scan():
+    """more than two scan blocks of buckets (the two-launch scan over the bucket counts) incl. exact block multiples."""
+    for nb, n in ((4096 * 3, 50_000), (20_000, 70_001), (8193, 5)):
+        torch.manual_seed(nb)
+        keys = torch.randint(0, nb, (n,))
+        p, perm = ops.bucket_sort(keys.to(DEV), nb, stable=True)
+        ref_ptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(keys, minlength=nb).cumsum(0)])
+        assert torch.equal(p.cpu().long(), ref_ptr)
+        assert torch.equal(perm.cpu().long(), torch.argsort(keys, stable=True))
+
+
+@pytest.mark.parametrize("name", ["silu", "shiftedsoftplus", "tanh"])
+def test_segment_sum_with_activation_in_flight(name):
+    """lcao_segment_sum flag bits 1 / 2 (factor = act(y) / act'(y)) and lcao_msg_bwd without a stored h, vs torch."""
+    import math
+
+    from lcaonet_b200._lib import ACT
+    F = torch.nn.functional
+    fn = {"silu": F.silu, "shiftedsoftplus": lambda v: F.softplus(v) - math.log(2.0), "tanh": torch.tanh}[name]
+    g = qm9_like_batch(6, seed=21)
+    gi = ops.GraphIndex(g["edge_index"].to(DEV), g["z"].shape[0])
+    E, N, C, act = gi.E, gi.N, 128, ACT[name]
+    torch.manual_seed(3)
+    x, y = torch.randn(E, C, device=DEV), 2.0 * torch.randn(E, C, device=DEV)
+    yd = y.double().requires_grad_(True)
+    fy = fn(yd)
+    (dfy,) = torch.autograd.grad(fy.sum(), yd)
+    src = g["edge_index"][0].to(DEV)
+    P, st = ops.ptr, ops.stream_ptr
+    for flag, factor in ((2, fy.detach()), (4, dfy)):
+        out = torch.empty(N, C, device=DEV)
+        ops._call("lcao_segment_sum", P(x), C, P(y), C, P(gi.out_ptr), P(gi.out_edge), N, C, flag | (act << 4), P(out), C, st())
+        ref = torch.zeros(N, C, dtype=torch.float64, device=DEV).index_add_(0, src, x.double() * factor)
+        assert rel_l2(out, ref) < 2e-6, (name, flag)
+    d_agg, bw = torch.randn(N, C, device=DEV), torch.randn(E, C, device=DEV)
+    d_bw, d_pre = torch.empty(E, C, device=DEV), torch.empty(E, C, device=DEV)
+    ops._call("lcao_msg_bwd", P(d_agg), C, P(gi.src32), None, P(bw), P(y), E, C, act, P(d_bw), P(d_pre), st())
+    ga = d_agg.double()[src]
+    assert rel_l2(d_bw, ga * fy.detach()) < 2e-6 and rel_l2(d_pre, ga * bw.double() * dfy) < 2e-6
