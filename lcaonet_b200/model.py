@@ -223,9 +223,12 @@ class LCAOEmbedding(nn.Module):
     def _graphed_tables(self, cnt_z: Tensor, cnt_pair: Tensor):
         """`_tables` captured (forward and backward) by torch.cuda.make_graphed_callables, built on first use per
         device.  Capture runs the function a few times, so the BatchNorm buffers are restored afterwards."""
-        key = (cnt_z.device, cnt_z.shape, cnt_pair.shape)
+        # the graphs hold raw pointers: key them on the storage of every parameter and buffer (`.to()`, `.float()` ... move them)
+        key = (cnt_z.device, cnt_z.shape, cnt_pair.shape,
+               tuple(t.data_ptr() for t in list(self.parameters()) + list(self.buffers())))
         cache = self.__dict__.setdefault("_graph_cache", {})
         if key not in cache:
+            cache.clear()  # a stale capture is never valid again
             bufs = [b for bn in (self.node_embed.bn, self.coeff_embed.bn)
                     for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if b is not None]
             saved = [b.clone() for b in bufs]

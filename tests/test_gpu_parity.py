@@ -447,6 +447,16 @@ def test_graphed_embedding_tables_equal_eager():
                 assert rel_l2(q.grad, p.grad) < 1e-5, (step, n, rel_l2(q.grad, p.grad))
         for (n, b), c in zip(m_e.named_buffers(), m_g.buffers()):
             assert torch.equal(b, c), (step, n)
+    # moving the parameters invalidates the captured pointers: the graphs must be rebuilt, not replayed on freed storage
+    m_g = m_g.cpu().to(DEV)
+    g = qm9_like_batch(7, seed=91)
+    outs = []
+    for m in (m_e, m_g):
+        m.zero_grad(set_to_none=True)
+        out = m(GraphBatch(g).to(DEV))
+        torch.nn.functional.mse_loss(out, g["y"].to(DEV)).backward()
+        outs.append(out.detach())
+    assert torch.equal(outs[0], outs[1])
     # inference falls back to the eager path and still agrees
     m_e.eval(), m_g.eval()
     g = qm9_like_batch(5, seed=77)
