@@ -163,6 +163,20 @@ int64_t lcao_pair_contract_bwd_scratch(int64_t E, int64_t P, int32_t O, int32_t 
 /* Gram matrices of an existing B (E,NG,C): gram (E, NL(NL+1)/2) FP64, for callers that built B themselves. */
 int lcao_coeff_gram(const float* B, int32_t NG, int64_t E, int32_t C, int32_t NL, double* gram, void* stream);
 
+/* ---- embedding block: count-weighted BatchNorm over table rows (embed.py:175,194,232,249) -------- */
+/* nn.BatchNorm1d over a batch given as its R DISTINCT rows x (R,F) and their multiplicities counts (R) (the node rows
+ * depend on the species, the coefficient rows on the species pair: DESIGN.md R6).  training != 0: batch statistics
+ * (biased variance), running_mean / running_var (nullable together) updated with `momentum` and the unbiased variance,
+ * *num_batches_tracked (nullable) incremented; training == 0: the running statistics normalise.  gamma / beta nullable
+ * (affine=False).  save_mean / save_rstd (F) are kept for the backward pass. */
+int lcao_table_norm_fwd(const float* x, const float* counts, const float* gamma, const float* beta, int64_t R, int32_t F,
+                        float eps, float momentum, int32_t training, float* running_mean, float* running_var,
+                        int64_t* num_batches_tracked, float* y, float* save_mean, float* save_rstd, void* stream);
+/* dx (R,F), dgamma (F), dbeta (F) (the last two nullable) of the above; dy is the gradient w.r.t. every table row. */
+int lcao_table_norm_bwd(const float* dy, const float* x, const float* counts, const float* gamma, const float* save_mean,
+                        const float* save_rstd, int64_t R, int32_t F, int32_t training, float* dx, float* dgamma,
+                        float* dbeta, void* stream);
+
 /* ---- three-body message passing (lcaonet.py:173-189, shbf.py:75-87) --------------------------- */
 /* gate[n,:] = sigmoid(xk[n,:]) per node (lcaonet.py:186-188), computed once per layer */
 int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t M, int32_t C, void* stream);

@@ -1,0 +1,150 @@
+// Count-weighted BatchNorm over table rows, forward and backward (embed.py:175,194,232,249 = nn.BatchNorm1d).
+//
+// The reference normalises (N, F) node rows and (E, O*K) coefficient rows; both are functions of the species (pair)
+// only, so the batch is given as its R DISTINCT rows plus their multiplicities: with n = sum_r c_r and
+// w_r = c_r / n,
+//   mean = sum_r w_r x_r ;  var = sum_r w_r (x_r - mean)^2 (biased) ;  y_r = (x_r - mean) rstd * gamma + beta
+//   running_mean <- (1-m) running_mean + m mean ;  running_var <- (1-m) running_var + m var n/(n-1) ;  tracked += 1
+// and, for the backward pass (rows with c_r = 0 still receive y_r, hence the un-weighted sums over dy):
+//   dbeta = sum_r dy_r ;  dgamma = sum_r dy_r xhat_r ;  dx_r = rstd gamma (dy_r - w_r dbeta - w_r xhat_r dgamma)
+// (eval mode: mean / var are the running statistics and dx_r = rstd gamma dy_r).
+//
+// CTA = 32 feature columns x 32 row lanes (row lane j takes rows j, j+32, ...); column sums are combined through
+// shared memory in a fixed order: deterministic.  The tables have 37 .. (max_z+1)^2 rows of 128 .. 1024 features
+// (5.6 MB at most, L2 resident): the job of these two kernels is to replace ~100 torch launches per step, not bandwidth.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kCols = 32, kLanes = 32;
+
+// sum over the 32 row lanes of a column (threadIdx.y), result broadcast to all of them
+__device__ __forceinline__ float column_sum(float v, float (*s)[kCols + 1]) {
+  s[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLanes; ++j) t += s[j][threadIdx.x];
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ float total_count(const float* __restrict__ counts, int R, float (*s)[kCols + 1]) {
+  float c = 0.f;
+  for (int r = threadIdx.y * kCols + threadIdx.x; r < R; r += kCols * kLanes) c += counts[r];
+  // all 1024 threads hold partials: reduce columns first, then across the 32 column sums (same value for every thread)
+  const float col = column_sum(c, s);
+  s[0][threadIdx.x] = col;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) t += s[0][j];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kCols * kLanes) k_wbn_fwd(
+    const float* __restrict__ x, const float* __restrict__ counts, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int R, int F, float eps, float momentum, int training, float* running_mean,
+    float* running_var, int64_t* tracked, float* __restrict__ y, float* __restrict__ save_mean,
+    float* __restrict__ save_rstd) {
+  __shared__ float s[kLanes][kCols + 1];
+  const int f = blockIdx.x * kCols + threadIdx.x;
+  const bool ok = f < F;
+  float mean, var, n = 0.f;
+  if (training) {
+    n = total_count(counts, R, s);
+    float a = 0.f;
+    if (ok)
+      for (int r = threadIdx.y; r < R; r += kLanes) a = fmaf(counts[r], x[(int64_t)r * F + f], a);
+    mean = column_sum(a, s) / n;
+    float b = 0.f;
+    if (ok)
+      for (int r = threadIdx.y; r < R; r += kLanes) {
+        const float d = x[(int64_t)r * F + f] - mean;
+        b = fmaf(counts[r] * d, d, b);
+      }
+    var = column_sum(b, s) / n;
+  } else {
+    mean = ok ? running_mean[f] : 0.f;
+    var = ok ? running_var[f] : 1.f;
+  }
+  const float rstd = rsqrtf(var + eps);
+  if (ok) {
+    const float g = gamma ? gamma[f] * rstd : rstd, b0 = beta ? beta[f] : 0.f;
+    for (int r = threadIdx.y; r < R; r += kLanes) y[(int64_t)r * F + f] = fmaf(x[(int64_t)r * F + f] - mean, g, b0);
+    if (threadIdx.y == 0) {
+      save_mean[f] = mean;
+      save_rstd[f] = rstd;
+      if (training && running_mean) {
+        running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * mean;
+        running_var[f] = (1.f - momentum) * running_var[f] + momentum * var * (n / (n - 1.f));
+      }
+    }
+  }
+  if (training && tracked && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *tracked += 1;
+}
+
+__global__ void __launch_bounds__(kCols * kLanes) k_wbn_bwd(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ counts,
+    const float* __restrict__ gamma, const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int R,
+    int F, int training, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s[kLanes][kCols + 1];
+  const int f = blockIdx.x * kCols + threadIdx.x;
+  const bool ok = f < F;
+  const float n = training ? total_count(counts, R, s) : 1.f;
+  const float mean = ok ? save_mean[f] : 0.f, rstd = ok ? save_rstd[f] : 0.f;
+  float a = 0.f, b = 0.f;
+  if (ok)
+    for (int r = threadIdx.y; r < R; r += kLanes) {
+      const float g = dy[(int64_t)r * F + f];
+      a += g;
+      b = fmaf(g, (x[(int64_t)r * F + f] - mean) * rstd, b);
+    }
+  const float db = column_sum(a, s), dg = column_sum(b, s);
+  if (!ok) return;
+  const float sc = rstd * (gamma ? gamma[f] : 1.f);
+  for (int r = threadIdx.y; r < R; r += kLanes) {
+    const float g = dy[(int64_t)r * F + f];
+    float v = g;
+    if (training) {
+      const float w = counts[r] / n, xh = (x[(int64_t)r * F + f] - mean) * rstd;
+      v = g - w * db - w * xh * dg;
+    }
+    dx[(int64_t)r * F + f] = sc * v;
+  }
+  if (threadIdx.y == 0) {
+    if (dgamma) dgamma[f] = dg;
+    if (dbeta) dbeta[f] = db;
+  }
+}
+
+}  // namespace
+
+extern "C" int lcao_table_norm_fwd(const float* x, const float* counts, const float* gamma, const float* beta, int64_t R,
+                                   int32_t F, float eps, float momentum, int32_t training, float* running_mean,
+                                   float* running_var, int64_t* num_batches_tracked, float* y, float* save_mean,
+                                   float* save_rstd, void* stream) {
+  if (R == 0 || F == 0) return LCAO_OK;
+  LCAO_REQUIRE(x && y && save_mean && save_rstd && R < (1ll << 31), "lcao_table_norm_fwd: null buffer");
+  LCAO_REQUIRE(training ? counts != nullptr : (running_mean && running_var),
+               "lcao_table_norm_fwd: training needs counts, evaluation needs the running statistics");
+  LCAO_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "lcao_table_norm_fwd: pass both running buffers or neither");
+  k_wbn_fwd<<<(unsigned)((F + kCols - 1) / kCols), dim3(kCols, kLanes), 0, (cudaStream_t)stream>>>(
+      x, counts, gamma, beta, (int)R, F, eps, momentum, training, running_mean, running_var, num_batches_tracked, y, save_mean,
+      save_rstd);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_table_norm_bwd(const float* dy, const float* x, const float* counts, const float* gamma,
+                                   const float* save_mean, const float* save_rstd, int64_t R, int32_t F, int32_t training,
+                                   float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (R == 0 || F == 0) return LCAO_OK;
+  LCAO_REQUIRE(dy && x && save_mean && save_rstd && dx && (!training || counts) && R < (1ll << 31),
+               "lcao_table_norm_bwd: null buffer");
+  k_wbn_bwd<<<(unsigned)((F + kCols - 1) / kCols), dim3(kCols, kLanes), 0, (cudaStream_t)stream>>>(
+      dy, x, counts, gamma, save_mean, save_rstd, (int)R, F, training, dx, dgamma, dbeta);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}

@@ -74,6 +74,13 @@ def _weighted_batch_norm(bn: nn.BatchNorm1d, table: Tensor, counts: Tensor, trai
     functions of the species (pair) only, so the batch statistics are the count-weighted statistics of
     the distinct rows — same numbers, O(#species^2) work.  Updates the running statistics exactly like
     nn.BatchNorm1d (momentum, unbiased running variance, num_batches_tracked)."""
+    stats = training or not bn.track_running_stats  # normalise with batch statistics
+    if table.dtype == torch.float32 and (bn.momentum is not None or not stats) and (bn.weight is None) == (bn.bias is None):
+        # one kernel forward, one backward (lcao_table_norm_*): statistics, running buffers, normalisation, affine
+        upd = training and bn.track_running_stats
+        return ops.table_norm(table, counts.to(torch.float32), bn.weight, bn.bias,
+                              bn.running_mean if (upd or not stats) else None, bn.running_var if (upd or not stats) else None,
+                              bn.num_batches_tracked if upd else None, stats, float(bn.momentum or 0.0), float(bn.eps))
     if training or not bn.track_running_stats:
         n = counts.sum()
         w = (counts / n).unsqueeze(1)

@@ -618,6 +618,45 @@ def interaction_layer(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b
 
 
 # ------------------------------------------------------------------------------------------------
+# count-weighted BatchNorm over table rows (embedding block)
+# ------------------------------------------------------------------------------------------------
+class _TableNorm(torch.autograd.Function):
+    """nn.BatchNorm1d over a batch given as DISTINCT rows + multiplicities (embed.py:175,194,232,249)."""
+
+    @staticmethod
+    def forward(ctx, x, counts, weight, bias, running_mean, running_var, tracked, training: bool, momentum: float,
+                eps: float):
+        require_cuda(x)
+        x = x.contiguous()
+        R, F = x.shape
+        y = torch.empty_like(x)
+        mean, rstd = torch.empty(F, device=x.device), torch.empty(F, device=x.device)
+        _call("lcao_table_norm_fwd", ptr(x), ptr(counts), ptr(weight), ptr(bias), R, F, eps, momentum, 1 if training else 0,
+              ptr(running_mean), ptr(running_var), ptr(tracked), ptr(y), ptr(mean), ptr(rstd), stream_ptr())
+        ctx.training = training
+        ctx.save_for_backward(x, counts, weight, mean, rstd)
+        ctx.mark_non_differentiable(*[t for t in (running_mean, running_var, tracked) if t is not None])
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, counts, weight, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        R, F = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty(F, device=x.device) if weight is not None else None
+        db = torch.empty(F, device=x.device) if weight is not None else None
+        _call("lcao_table_norm_bwd", ptr(dy), ptr(x), ptr(counts), ptr(weight), ptr(mean), ptr(rstd), R, F,
+              1 if ctx.training else 0, ptr(dx), ptr(dg), ptr(db), stream_ptr())
+        return dx, None, dg, db, None, None, None, None, None, None
+
+
+def table_norm(x, counts, weight, bias, running_mean, running_var, tracked, training, momentum, eps):
+    return _TableNorm.apply(x, counts, weight, bias, running_mean, running_var, tracked, training, momentum, eps)
+
+
+# ------------------------------------------------------------------------------------------------
 # gathers / segment sums
 # ------------------------------------------------------------------------------------------------
 class _EdgePair(torch.autograd.Function):

@@ -559,6 +559,48 @@ def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, sc
         view(db, Nout).add_(d.sum(0))
 
 
+def lcao_table_norm_fwd(x, counts, gamma, beta, R, Fd, eps, momentum, training, rmean, rvar, tracked, y, smean, srstd, stream):
+    X = view(x, R, Fd)
+    if training:
+        c = view(counts, R)
+        n = c.sum()
+        w = (c / n).unsqueeze(1)
+        mean = (w * X).sum(0)
+        var = (w * (X - mean) ** 2).sum(0)
+        if rmean:
+            view(rmean, Fd).mul_(1 - momentum).add_(momentum * mean)
+            view(rvar, Fd).mul_(1 - momentum).add_(momentum * var * (n / (n - 1)))
+        if tracked:
+            view(tracked, 1, dtype=I64).add_(1)
+    else:
+        mean, var = view(rmean, Fd).clone(), view(rvar, Fd).clone()
+    rstd = torch.rsqrt(var + eps)
+    out = (X - mean) * rstd
+    if gamma:
+        out = out * view(gamma, Fd) + view(beta, Fd)
+    view(y, R, Fd).copy_(out)
+    view(smean, Fd).copy_(mean)
+    view(srstd, Fd).copy_(rstd)
+
+
+def lcao_table_norm_bwd(dy, x, counts, gamma, smean, srstd, R, Fd, training, dx, dgamma, dbeta, stream):
+    G, X = view(dy, R, Fd), view(x, R, Fd)
+    mean, rstd = view(smean, Fd), view(srstd, Fd)
+    xh = (X - mean) * rstd
+    db, dg = G.sum(0), (G * xh).sum(0)
+    sc = rstd * (view(gamma, Fd) if gamma else 1.0)
+    v = G
+    if training:
+        c = view(counts, R)
+        w = (c / c.sum()).unsqueeze(1)
+        v = G - w * db - w * xh * dg
+    view(dx, R, Fd).copy_(sc * v)
+    if dgamma:
+        view(dgamma, Fd).copy_(dg)
+    if dbeta:
+        view(dbeta, Fd).copy_(db)
+
+
 def lcao_act_fwd(X, ldx, Y, ldy, M, Cc, act, stream):
     view(Y, M, Cc, ld=ldy).copy_(_act(view(X, M, Cc, ld=ldx).clone(), act))
 

@@ -554,3 +554,36 @@ def test_segment_sum_with_activation_in_flight(name):
     ops._call("lcao_msg_bwd", P(d_agg), C, P(gi.src32), None, P(bw), P(y), E, C, act, P(d_bw), P(d_pre), st())
     ga = d_agg.double()[src]
     assert rel_l2(d_bw, ga * fy.detach()) < 2e-6 and rel_l2(d_pre, ga * bw.double() * dfy) < 2e-6
+
+
+@pytest.mark.parametrize("R,Fd,training", [(37, 128, True), (1369, 1024, True), (1369, 1000, False), (5, 33, True)])
+def test_table_norm_vs_weighted_batchnorm(R, Fd, training):
+    """lcao_table_norm_fwd/bwd against nn.BatchNorm1d applied to the EXPANDED batch (rows repeated by their counts) in
+    FP64: outputs, running statistics, num_batches_tracked and all gradients; rows with a zero count included."""
+    torch.manual_seed(R + Fd)
+    x = torch.randn(R, Fd)
+    counts = torch.randint(0, 7, (R,)).float()
+    counts[0] = 3.0
+    bn = torch.nn.BatchNorm1d(Fd).double()
+    bn.weight.data.uniform_(0.5, 1.5), bn.bias.data.normal_()
+    bn.running_mean.normal_(), bn.running_var.uniform_(0.5, 2.0)
+    bn.train(training)
+    rm, rv = bn.running_mean.clone().float().to(DEV), bn.running_var.clone().float().to(DEV)
+    tracked = bn.num_batches_tracked.clone().to(DEV)
+    # reference: the expanded batch, with one tagged copy of every table row appended to read y / dy at all rows
+    xd = x.double().requires_grad_(True)
+    rep = torch.repeat_interleave(torch.arange(R), counts.long())
+    yb = bn(xd[rep])
+    mean = xd[rep].mean(0) if training else bn.running_mean
+    var = xd[rep].var(0, unbiased=False) if training else bn.running_var
+    y_ref = (xd - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+    dy = torch.randn(R, Fd)
+    gx, gw, gb = torch.autograd.grad(y_ref, (xd, bn.weight, bn.bias), dy.double())
+    xg = x.to(DEV).requires_grad_(True)
+    w, b = bn.weight.detach().float().to(DEV).requires_grad_(True), bn.bias.detach().float().to(DEV).requires_grad_(True)
+    y = ops.table_norm(xg, counts.to(DEV), w, b, rm, rv, tracked if training else None, training, 0.1, bn.eps)
+    dx, dw, db = torch.autograd.grad(y, (xg, w, b), dy.to(DEV))
+    assert rel_l2(y, y_ref) < 2e-6 and rel_l2(yb, y_ref[rep]) < 1e-12
+    assert rel_l2(dx, gx) < 1e-5 and rel_l2(dw, gw) < 1e-5 and rel_l2(db, gb) < 1e-5
+    assert rel_l2(rm, bn.running_mean) < 2e-6 and rel_l2(rv, bn.running_var) < 2e-6
+    assert int(tracked) == int(bn.num_batches_tracked)
