@@ -12,6 +12,7 @@ There is no CPU path: tensors must live on a CUDA (sm_100a) device.
 from __future__ import annotations
 
 import math
+import weakref
 from fractions import Fraction
 
 import torch
@@ -257,8 +258,19 @@ class LCAOEmbedding(nn.Module):
         pair = z[idx_s] * Zd + z[idx_t]
         cnt_z, cnt_pair = ops.histogram(z, Zd), ops.histogram(pair, Zd * Zd)
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if self.graph_tables and self.training and grad and z.is_cuda and all(p.requires_grad for p in self.parameters()):
+        use_graph = self.graph_tables and self.training and grad and z.is_cuda and all(p.requires_grad for p in self.parameters())
+        if use_graph:
+            # a captured forward/backward pair serves ONE outstanding forward: its outputs and saved activations are static
+            # buffers.  If the previous graphed forward is still alive and has not been back-propagated (two forwards
+            # before a backward), this call takes the eager path instead of overwriting them.
+            last = self.__dict__.get("_graph_last")
+            if last is not None and last[0]() is not None and not last[1][0]:
+                use_graph = False
+        if use_graph:
             xtab, ctab = self._graphed_tables(cnt_z, cnt_pair)(cnt_z, cnt_pair)
+            done = [False]
+            ctab.register_hook(lambda g, d=done: d.__setitem__(0, True))
+            self.__dict__["_graph_last"] = (weakref.ref(ctab), done)
         else:
             xtab, ctab = self._tables(cnt_z, cnt_pair)
         need_bwd = torch.is_grad_enabled() and xtab.requires_grad

@@ -587,3 +587,26 @@ def test_table_norm_vs_weighted_batchnorm(R, Fd, training):
     assert rel_l2(dx, gx) < 1e-5 and rel_l2(dw, gw) < 1e-5 and rel_l2(db, gb) < 1e-5
     assert rel_l2(rm, bn.running_mean) < 2e-6 and rel_l2(rv, bn.running_var) < 2e-6
     assert int(tracked) == int(bn.num_batches_tracked)
+
+
+def test_graphed_embedding_two_forwards_before_backward():
+    """the captured graphs serve one outstanding forward: a second forward before the first backward must not clobber
+    the first one's tables (it takes the eager path) — gradients of the summed loss equal the eager model's."""
+    torch.manual_seed(0)
+    kw = dict(cutoff=5.0, cutoff_net="polynomial", emb_size=32, emb_size_coeff=32, emb_size_conv=32)
+    m_e, m_g = LCAONet(**kw).to(DEV).train(), LCAONet(**kw).to(DEV).train()
+    m_g.load_state_dict(m_e.state_dict())
+    m_g.emb_layer.graph_tables = True
+    ga, gb = qm9_like_batch(5, seed=61), qm9_like_batch(9, seed=62)
+    for m in (m_e, m_g):
+        oa = m(GraphBatch(ga).to(DEV))
+        ob = m(GraphBatch(gb).to(DEV))
+        ((oa**2).mean() + 3.0 * (ob**2).mean()).backward()
+    for (n, p), q in zip(m_e.named_parameters(), m_g.parameters()):
+        assert rel_l2(q.grad, p.grad) < 1e-5, n
+    # ... and the next step replays the graphs again
+    for m in (m_e, m_g):
+        m.zero_grad(set_to_none=True)
+        (m(GraphBatch(ga).to(DEV))**2).mean().backward()
+    for (n, p), q in zip(m_e.named_parameters(), m_g.parameters()):
+        assert rel_l2(q.grad, p.grad) < 1e-5, n
