@@ -386,60 +386,78 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
             for (int v = 0; v < V4; ++v) gr[jj][v] = okc[v] ? ldg4(d_tbw + (int64_t)e * C + (lane + 32 * v) * 4) : zero4();
           }
         }
-        float part[8], part2[FORCES ? 8 : 1];
-        float4 ar = lds4(sa + j0 * 4), ar2;
-        if constexpr (FORCES) ar2 = lds4(s_a2[warp] + j0 * 4);
+        // FORCES needs two contractions of Gt with the in-edge's rows per pair (weights w Y_l and w Y'_l): instead of
+        // forming both combined rows, the NL dots D_l = Gt . GB_l are taken once (NL FMAs per channel) and both scalars
+        // follow from them after the butterfly: 24 instead of 44 arithmetic instructions per pair and lane.
+        float part[FORCES ? 1 : 8], partD[FORCES ? NL : 1][8];
+        float4 ar = lds4(sa + j0 * 4);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          part[jj] = 0.f;
-          if constexpr (FORCES) part2[jj] = 0.f;
+          if constexpr (FORCES) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) partD[l][jj] = 0.f;
+          } else {
+            part[jj] = 0.f;
+          }
           if (!GUARD || jj < nj) {
             const float4 ar_next = lds4(sa + (j0 + jj + 1) * 4);
-            float4 ar2_next;
-            if constexpr (FORCES) ar2_next = lds4(s_a2[warp] + (j0 + jj + 1) * 4);
-            float d = 0.f, d2 = 0.f;
+            float d = 0.f, dl[NL];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) dl[l] = 0.f;
 #pragma unroll
             for (int v = 0; v < V4; ++v) {
-              float4 t = scale4(ar.x, gb[0][v]);
-              if (NL > 1) t = fma4(ar.y, gb[1][v], t);
-              if (NL > 2) t = fma4(ar.z, gb[2][v], t);
-              if (NL > 3) t = fma4(ar.w, gb[3][v], t);
-              d += dot4(t, gr[jj][v]);
               if constexpr (FORCES) {
-                float4 t2 = scale4(ar2.x, gb[0][v]);
-                if (NL > 1) t2 = fma4(ar2.y, gb[1][v], t2);
-                if (NL > 2) t2 = fma4(ar2.z, gb[2][v], t2);
-                if (NL > 3) t2 = fma4(ar2.w, gb[3][v], t2);
-                d2 += dot4(t2, gr[jj][v]);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) dl[l] += dot4(gb[l][v], gr[jj][v]);
+              } else {
+                float4 t = scale4(ar.x, gb[0][v]);
+                if (NL > 1) t = fma4(ar.y, gb[1][v], t);
+                if (NL > 2) t = fma4(ar.z, gb[2][v], t);
+                if (NL > 3) t = fma4(ar.w, gb[3][v], t);
+                d += dot4(t, gr[jj][v]);
               }
               dacc[0][v] = fma4(ar.x, gr[jj][v], dacc[0][v]);
               if (NL > 1) dacc[1][v] = fma4(ar.y, gr[jj][v], dacc[1][v]);
               if (NL > 2) dacc[2][v] = fma4(ar.z, gr[jj][v], dacc[2][v]);
               if (NL > 3) dacc[3][v] = fma4(ar.w, gr[jj][v], dacc[3][v]);
             }
-            part[jj] = d;
-            if constexpr (FORCES) part2[jj] = d2;
+            if constexpr (FORCES) {
+#pragma unroll
+              for (int l = 0; l < NL; ++l) partD[l][jj] = dl[l];
+            } else {
+              part[jj] = d;
+            }
             ar = ar_next;
-            if constexpr (FORCES) ar2 = ar2_next;
           }
         }
         // ---- per pair scalars: the quad `jsub` of the warp finishes pair (out j0 + jsub, this in-edge)
-        const float dotv = bfly8(part, lane);
+        float dotv, dot2v = 0.f;
         {
           const int slot = j0 + jsub;  // dead slots carry a = 0, flag = 0 and a zero dot
-          const float4 ar = lds4(sa + slot * 4);
+          const float4 as = lds4(sa + slot * 4);
+          if constexpr (FORCES) {
+            const float4 as2 = lds4(s_a2[warp] + slot * 4);
+            dotv = 0.f;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+              const float D = bfly8(partD[l], lane);
+              dotv = fmaf(comp4(as, l), D, dotv);
+              dot2v = fmaf(comp4(as2, l), D, dot2v);
+            }
+          } else {
+            dotv = bfly8(part, lane);
+          }
           const float sc = -sf[slot] * dotv;
           int p = 0;
 #pragma unroll
           for (int x = 0; x < NL; ++x)
 #pragma unroll
-            for (int y = x; y < NL; ++y) h[p++] += sc * comp4(ar, x) * comp4(ar, y);
+            for (int y = x; y < NL; ++y) h[p++] += sc * comp4(as, x) * comp4(as, y);
         }
         if constexpr (FORCES) {
           // dL/dcos of pair (j0 + jl) is finished on its coefficient lane j0 + jl, which still holds the pair's cos /
           // w / flag and both directions; the two dots come from the quad that owns butterfly element jl (lane bits
           // 4,3,2 = bits 2,1,0 of jl).
-          const float dot2v = bfly8(part2, lane);
           const int jl = (lane - j0) & 7;
           const int srcl = (((jl >> 2) & 1) << 4) | (((jl >> 1) & 1) << 3) | ((jl & 1) << 2);
           const float dt = __shfl_sync(0xffffffffu, dotv, srcl);
