@@ -266,8 +266,17 @@ class LCAOEmbedding(nn.Module):
             last = self.__dict__.get("_graph_last")
             if last is not None and last[0]() is not None and not last[1][0]:
                 use_graph = False
+        graphed = None
         if use_graph:
-            xtab, ctab = self._graphed_tables(cnt_z, cnt_pair)(cnt_z, cnt_pair)
+            try:
+                graphed = self._graphed_tables(cnt_z, cnt_pair)
+            except RuntimeError as e:  # capture refused (driver / allocator state): stay on the eager path, once and for all
+                import warnings
+                warnings.warn(f"LCAOEmbedding.graph_tables: CUDA graph capture failed ({e}); using the eager path")
+                self.graph_tables = False
+                use_graph = False
+        if use_graph:
+            xtab, ctab = graphed(cnt_z, cnt_pair)
             done = [False]
             ctab.register_hook(lambda g, d=done: d.__setitem__(0, True))
             self.__dict__["_graph_last"] = (weakref.ref(ctab), done)
