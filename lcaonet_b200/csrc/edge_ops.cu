@@ -114,17 +114,19 @@ __device__ __forceinline__ void twobody_load(const float* __restrict__ B, const 
   }
 }
 
-template <bool VAL>
+// NV = float4 column slices per lane (1 for C <= 128, 2 up to 256): the register arrays are sized by it, which keeps
+// the common C = 128 case at 5+ resident CTAs per SM (73 registers with two slices limited it to 3)
+template <bool VAL, int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_fwd(const float* __restrict__ B, int NG,
                                                                    const float* __restrict__ g, int64_t E, int C,
                                                                    int NL, float* __restrict__ lw) {
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
-  float4 p[2];
+  float4 p[NV];
   float n2 = 0.f;
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < NV; ++v) {
     const int c = lane * 4 + v * 128;
     p[v] = f4_zero();
     if (c < C) {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_fwd(const float* 
   n2 = warp_sum(n2);
   const float inv = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < NV; ++v) {
     const int c = lane * 4 + v * 128;
     if (c < C) st4(lw + e * (int64_t)C + c, f4_scale(inv, p[v]));
   }
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_fwd(const float* 
 // backward: dp = (dlw - lw (lw.dlw)) / |p|  (or dlw/eps when clamped);
 // dgA = dp*PA, dgV = dp*PV ; dPA = (1+gA) dp, dPV = (1+gV) dp ;
 // stored groups: dB[l] = dPA for every l < NL ; dB[NL] = dPV - dPA   (PA = sum_l B_l - B_NL)
-template <bool VAL>
+template <bool VAL, int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* __restrict__ B, int NG,
                                                                    const float* __restrict__ g,
                                                                    const float* __restrict__ d_lw, int64_t E, int C,
@@ -156,10 +158,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* 
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
-  float4 p[2], PA[2], PV[2], gA[2], gV[2], dl[2];
+  float4 p[NV], PA[NV], PV[NV], gA[NV], gV[NV], dl[NV];
   float n2 = 0.f, pd = 0.f;
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < NV; ++v) {
     const int c = lane * 4 + v * 128;
     p[v] = f4_zero(); dl[v] = f4_zero();
     if (c < C) {
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* 
   // lw = p*inv ; lw.dlw = pd*inv ; dp = (dl - p*inv*pd*inv) * inv
   const float coef = clamped ? 0.f : pd * inv * inv;
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < NV; ++v) {
     const int c = lane * 4 + v * 128;
     if (c < C) {
       float4 dp = f4_scale(inv, f4_sub(dl[v], f4_scale(coef, p[v])));
@@ -430,8 +432,13 @@ extern "C" int lcao_twobody_fwd(const float* B, int32_t NG, const float* g, int6
                "lcao_twobody_fwd: need C %% 4 == 0, C <= 256, NG == NL + valence (C=%d NG=%d NL=%d)", C, NG, NL);
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-  if (valence) k_twobody_fwd<true><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
-  else k_twobody_fwd<false><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+  if (C <= 128) {
+    if (valence) k_twobody_fwd<true, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+    else k_twobody_fwd<false, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+  } else {
+    if (valence) k_twobody_fwd<true, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+    else k_twobody_fwd<false, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+  }
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -444,8 +451,13 @@ extern "C" int lcao_twobody_bwd(const float* B, int32_t NG, const float* g, cons
                "lcao_twobody_bwd: need C %% 4 == 0, C <= 256, NG == NL + valence");
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-  if (valence) k_twobody_bwd<true><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
-  else k_twobody_bwd<false><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+  if (C <= 128) {
+    if (valence) k_twobody_bwd<true, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+    else k_twobody_bwd<false, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+  } else {
+    if (valence) k_twobody_bwd<true, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+    else k_twobody_bwd<false, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+  }
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
