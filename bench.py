@@ -388,7 +388,7 @@ def run_ours(args):
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
                         "share_of_step": dom["share"]}
         cpu = None
-        if world == 1 or True:
+        if world == 1:
             best, _ = cpu_oracle_step_time(32, reps=args.cpu_reps, threads=os.cpu_count())
             cpu = {"value": 32 / best, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"32 QM9-shape molecules (BASELINE configs[0]), fwd+bwd, best of {args.cpu_reps}, oracle port of the reference"}

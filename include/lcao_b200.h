@@ -73,6 +73,13 @@ const char* lcao_last_error(void);
 int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,
                      int32_t* perm, int32_t* scratch, int32_t stable, void* stream);
 
+/* Range check of the integer inputs of forward(batch) before they index device memory: *status (one int32, device)
+ * receives bit 1 if some z is outside [1, max_z], bit 2 if some batch index is outside [0, n_graph), bit 4 if some
+ * edge_index entry is outside [0, N); 0 = all valid.  z / batch may be NULL (skipped).  The reference raises IndexError
+ * for such inputs (nn.Embedding / index_select: embed.py:41,91, base.py:38, lcaonet.py:462). */
+int lcao_validate_graph(const int64_t* z, int64_t N, int64_t max_z, const int64_t* batch, int64_t n_graph,
+                        const int64_t* edge_index, int64_t E, int32_t* status, void* stream);
+
 /* Everything the fused kernels need from edge_index (2,E), in one call:
  *   src32/dst32 (E)            int32 copies of edge_index rows
  *   in_ptr (N+1), in_edge (E)  in-CSR;   in_src (E) = src32[in_edge]
@@ -154,7 +161,8 @@ int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, const float* r
                            float* B, double* gram, float* psum, void* stream);
 /* d_tab (P,O,Cp) = keyed reduction of rb[e,o] dB[e,l(o),:] over the edges of each pair, deterministic
  * (two stages, no atomics); (kptr (P+1), kperm (E)) = edges grouped by pair (lcao_bucket_sort).
- * d_rb (E,O) written if non-NULL (autograd forces).  scratch: lcao_pair_contract_bwd_scratch() BYTES. */
+ * d_rb (E,O) written if non-NULL (autograd forces); d_tab may be NULL when only d_rb is wanted (the positions-only
+ * pass of autograd forces).  scratch: lcao_pair_contract_bwd_scratch() BYTES. */
 int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, const int32_t* kptr, const int32_t* kperm,
                            const float* rb, const float* vmask, const int32_t* lgrp, const float* dB, int64_t E,
                            int64_t P, int32_t O, int32_t C, int32_t NL, int32_t valence, float* d_tab, float* d_rb,

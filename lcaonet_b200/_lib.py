@@ -37,6 +37,7 @@ _p, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 # name -> argtypes (must mirror include/lcao_b200.h; tests/test_abi.py checks every symbol is exported)
 SIGNATURES = {
     "lcao_bucket_sort": [_p, _p, _i64, _i64, _p, _p, _p, _i32, _p],
+    "lcao_validate_graph": [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p],
     "lcao_graph_index_build": [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "lcao_triplet_offsets": [_p, _p, _p, _i64, _p, _p, _p],
     "lcao_triplets_fill": [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p],

@@ -232,6 +232,22 @@ __global__ void k_triplets_fill(const int32_t* __restrict__ src32, const int32_t
   }
 }
 
+// Range check of the caller's integer inputs before any of them indexes device memory (the reference raises
+// IndexError from nn.Embedding / index_select for the same inputs: embed.py:41,91, base.py:38, lcaonet.py:462).
+// status bits: 1 = z outside [1, max_z], 2 = batch index outside [0, n_graph), 4 = edge_index outside [0, N).
+__global__ void k_validate(const int64_t* __restrict__ z, int64_t N, int64_t max_z, const int64_t* __restrict__ batch,
+                           int64_t n_graph, const int64_t* __restrict__ ei, int64_t E, int32_t* __restrict__ status) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < N) {
+    if (z && (z[i] < 1 || z[i] > max_z)) bad |= 1;
+    if (batch && (batch[i] < 0 || batch[i] >= n_graph)) bad |= 2;
+  }
+  if (i < 2 * E && (ei[i] < 0 || ei[i] >= N)) bad |= 4;
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if (bad && (threadIdx.x & 31) == 0) atomicOr(status, bad);
+}
+
 int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr, int32_t* perm,
                      int32_t* aux, int32_t* scratch, bool stable, cudaStream_t st) {
   int32_t* cursor = scratch;     // nb
@@ -262,6 +278,19 @@ extern "C" int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t
   LCAO_REQUIRE(n >= 0 && nb >= 0 && ptr && scratch && (n == 0 || (keys && perm)), "lcao_bucket_sort: bad arguments");
   LCAO_REQUIRE(n < (1ll << 31) && nb < (1ll << 31), "lcao_bucket_sort: sizes must fit int32");
   return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, stable != 0, (cudaStream_t)stream);
+}
+
+extern "C" int lcao_validate_graph(const int64_t* z, int64_t N, int64_t max_z, const int64_t* batch, int64_t n_graph,
+                                   const int64_t* edge_index, int64_t E, int32_t* status, void* stream) {
+  LCAO_REQUIRE(status && N >= 0 && E >= 0 && (E == 0 || edge_index), "lcao_validate_graph: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  LCAO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  const int64_t n = N > 2 * E ? N : 2 * E;
+  if (n > 0) {
+    k_validate<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(z, N, max_z, batch, n_graph, edge_index, E, status);
+    LCAO_LAUNCH_CHECK();
+  }
+  return LCAO_OK;
 }
 
 extern "C" int lcao_graph_index_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* src32, int32_t* dst32,

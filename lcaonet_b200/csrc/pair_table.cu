@@ -430,7 +430,7 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
                                       const float* rb, const float* vmask, const int32_t* lgrp, const float* dB,
                                       int64_t E, int64_t P, int32_t O, int32_t C, int32_t NL, int32_t valence,
                                       float* d_tab, float* d_rb, void* scratch, void* stream) {
-  LCAO_REQUIRE(P > 0 && P < (1 << 30) && d_tab && scratch && kptr, "lcao_pair_contract_bwd: null buffer");
+  LCAO_REQUIRE(P > 0 && P < (1 << 30) && (d_tab || d_rb) && (!d_tab || scratch) && kptr, "lcao_pair_contract_bwd: null buffer");
   LCAO_REQUIRE(E == 0 || (kperm && rb && lgrp && dB && (!valence || vmask)), "lcao_pair_contract_bwd: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && O > 0 && O <= LCAO_MAX_ORB && NL >= 1 && NL <= 4,
                "lcao_pair_contract_bwd: need C %% 4 == 0, O <= %d, 1 <= NL <= 4", LCAO_MAX_ORB);
@@ -440,6 +440,7 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
   float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ((P + 1 + 3) / 4) * 16);
   const int Cp = valence ? 2 * C : C;
   const int64_t chunks = ceil_div64(E, kChunk) + P;
+  if (d_tab) {  // (d_tab == NULL: only d_rb is wanted — the positions-only pass of autograd forces)
   k_chunk_ptr<<<1, 1024, 0, st>>>(kptr, (int)P, cptr);
   LCAO_LAUNCH_CHECK();
   if (E > 0) {
@@ -455,6 +456,7 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
   const int W4 = O * Cp / 4;
   k_pair_reduce_final<<<dim3((unsigned)P, (unsigned)((W4 + 31) / 32)), 256, 0, st>>>(cptr, (int)P, W4, partial, d_tab);
   LCAO_LAUNCH_CHECK();
+  }
   if (d_rb && E > 0) {
     LCAO_REQUIRE(tab && pair, "lcao_pair_contract_bwd: d_rb needs tab and pair");
     if (C <= 128) {  // pair-sorted walk: table rows stay in registers across a run of equal pairs

@@ -17,10 +17,11 @@ class FlatGradBucket:
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
+        self.views, off = [], 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
+        self.attach()
         # the interaction blocks may now write their weight gradients straight into these views
         for m in module.modules():
             if hasattr(m, "grads_in_place"):
@@ -29,10 +30,24 @@ class FlatGradBucket:
             if hasattr(m, "graph_tables") and self.flat.is_cuda:
                 m.graph_tables = True
 
+    def attach(self) -> None:
+        """(Re-)point every `.grad` at its view of the flat buffer.  `optimizer.zero_grad()` / `module.zero_grad()` set
+        the grads to None by default (`set_to_none=True`) and autograd then allocates fresh ones: use `bucket.zero()`
+        instead — but if it happened, the gradient found in a detached `.grad` is copied back so nothing is lost."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None or g.data_ptr() != v.data_ptr():
+                if g is not None:
+                    v.copy_(g)
+                p.grad = v
+
     def zero(self) -> None:
+        """Replaces `zero_grad()`: clears the flat buffer and keeps every `.grad` attached to it."""
         self.flat.zero_()
+        self.attach()
 
     def all_reduce_mean(self) -> None:
+        self.attach()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.mul_(1.0 / dist.get_world_size())

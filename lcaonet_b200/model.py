@@ -174,12 +174,21 @@ class PairCoeffs:
     (`ops.pair_contract`): the (E, O, K) tensor and the E*O-row GEMMs of the reference never exist.
     `materialize()` returns the reference-shaped tensor for callers that want it."""
 
-    def __init__(self, table: Tensor, pair: Tensor, kptr: Tensor | None, kperm: Tensor | None):
+    def __init__(self, table: Tensor, pair: Tensor, kptr: Tensor | None = None, kperm: Tensor | None = None):
         self.table, self.pair, self.kptr, self.kperm = table, pair, kptr, kperm
+
+    def grouping(self) -> tuple[Tensor, Tensor]:
+        """(kptr, kperm): edges grouped by species pair.  Built on
+        first use — every backward through the pair table needs it (d table: keyed reduction; d rb: pair-sorted walk),
+        whichever of the embedding / interaction parameters or the positions is being differentiated."""
+        if self.kptr is None:
+            with torch.no_grad():
+                self.kptr, self.kperm = ops.bucket_sort(self.pair, self.table.shape[0], stable=False)
+        return self.kptr, self.kperm
 
     def materialize(self) -> Tensor:
         P, O, K = self.table.shape
-        return ops.gather_rows(self.table.reshape(P, O * K), self.pair, self.kptr, self.kperm).reshape(-1, O, K)
+        return ops.gather_rows(self.table.reshape(P, O * K), self.pair, *self.grouping()).reshape(-1, O, K)
 
 
 class LCAOEmbedding(nn.Module):
@@ -287,12 +296,8 @@ class LCAOEmbedding(nn.Module):
             x = ops.gather_rows(xtab, z, *(ops.bucket_sort(z, Zd, stable=False) if need_bwd else (None, None)))
         else:
             x = xtab[z]
-        if torch.is_grad_enabled() and ctab.requires_grad:
-            kptr, kperm = ops.bucket_sort(pair, Zd * Zd, stable=False)
-        else:
-            kptr = kperm = None
         O = ctab.shape[1] // self.emb_size_coeff
-        return x, PairCoeffs(ctab.reshape(Zd * Zd, O, self.emb_size_coeff), pair, kptr, kperm)
+        return x, PairCoeffs(ctab.reshape(Zd * Zd, O, self.emb_size_coeff), pair)
 
 
 class _EmbedTables(nn.Module):
@@ -343,13 +348,13 @@ class LCAOInteraction(nn.Module):
             if self.grads_in_place and torch.is_grad_enabled():
                 sinks = tuple(p.grad if (p.requires_grad and p.grad is not None and p.grad.is_contiguous()) else None
                               for p in params)
-            return ops.interaction_layer(x, cst.table, rb, unit, *params, cst.pair, cst.kptr, cst.kperm, vmask, lgrp, gi, NL, C,
+            return ops.interaction_layer(x, cst.table, rb, unit, *params, cst.pair, cst.grouping, vmask, lgrp, gi, NL, C,
                                          sinks, activation_code(fn[1]))
         nw = self.node_weight(x)  # (N, 2C): [:, :C] feeds f_node, [:, C:] is the three-body gate
         xc, xk = nw[:, :C], nw[:, C:]
         if isinstance(cst, PairCoeffs):  # f_coeffs on the species-pair table, contracted per edge
             tab = _mlp(self.f_coeffs, cst.table)  # (P, O, C')
-            B, gram = ops.pair_contract(tab, cst.pair, cst.kptr, cst.kperm, rb, vmask, lgrp, NL, C)  # (E, NL(+1), C)
+            B, gram = ops.pair_contract(tab, cst.pair, cst.grouping, rb, vmask, lgrp, NL, C)  # (E, NL(+1), C)
         else:  # a materialised (E, O, K) coefficient tensor, as in the reference signature
             cst1 = _mlp(self.f_coeffs, cst)  # (E, O, C')
             B, gram = ops.coeff_contract(cst1, rb, vmask, lgrp, NL, C), None
@@ -396,7 +401,9 @@ class LCAOOut(nn.Module):
             a = self.out_lin_force[2](a, silu=act)
             f_st = self.out_lin_force[4](a) * unit  # (E, 3)
             return prop, ops.segment_reduce(f_st, gi.out_ptr, gi.out_edge, gi.src32, mean=False)
-        cols = [-torch.autograd.grad(prop[:, i].sum(), pos, create_graph=True)[0] for i in range(self.out_size)]
+        # d E / d pos only: the backward kernels skip every parameter gradient inside this pass (ops.positions_only)
+        with ops.positions_only():
+            cols = [-torch.autograd.grad(prop[:, i].sum(), pos, create_graph=True)[0] for i in range(self.out_size)]
         return prop, (cols[0] if len(cols) == 1 else torch.stack(cols, dim=1).squeeze(1))
 
 
@@ -518,6 +525,9 @@ class LCAONet(nn.Module):
         # write the reference's triplet side-effect keys (idx_k_3b, edge_idx_*_3b, angles_3b) into the
         # batch; costs one host sync (T is data dependent) — set False for a fully asynchronous forward
         self.side_effect_keys = True
+        # range-check z / batch / edge_index on the device before they index anything (IndexError like the reference's
+        # nn.Embedding / index_select); costs one host sync per forward — set False when the caller vouches for the batch
+        self.validate_inputs = True
 
         elec_info = ElecInfo(max_z, max_orb, min_orb, n_per_orb)
         if elec_info.n_orb > 64:
@@ -580,6 +590,8 @@ class LCAONet(nn.Module):
         _lib.require_cuda(z, pos, edge_index, lattice, shift)
         N, n_graph = z.shape[0], lattice.shape[0]
         idx_s, idx_t = edge_index[0], edge_index[1]
+        if self.validate_inputs:
+            ops.validate_graph(z, self.max_z, batch_idx, n_graph, edge_index)
 
         # indices: CSR by target / by source built on the GPU (replaces torch_sparse, lcaonet.py:462-477)
         gi = ops.GraphIndex(edge_index, N)

@@ -18,7 +18,9 @@ from ._lib import ACT_NONE, ACT_SILU, LcaoError, call, ptr, require_cuda, stream
 
 # GEMM arithmetic mode for the dense layers: fp32 CUDA cores, 3xTF32 tcgen05 (fp32-equivalent), 1xTF32
 GEMM_MODES = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "tf32": _lib.GEMM_TF32}
-_gemm_mode = _lib.GEMM_FP32
+# The default is the tcgen05 path in its FP32-equivalent arithmetic (3xTF32 operand split, FP32 accumulation in TMEM):
+# it is the mode the parity tests and the benchmark run.  "fp32" selects the CUDA-core kernels (gemm_simt.cu).
+_gemm_mode = _lib.GEMM_TF32X3
 
 # launch counter: every C-ABI compute call increments it (bench.py reports it as gpu_launches)
 n_calls = 0
@@ -31,6 +33,41 @@ def set_gemm_mode(mode: str) -> None:
 
 def get_gemm_mode() -> str:
     return {v: k for k, v in GEMM_MODES.items()}[_gemm_mode]
+
+
+class positions_only:
+    """Context for `torch.autograd.grad(energy, pos)` (autograd forces, reference lcaonet.py:310-317): inside it the
+    backward kernels skip every PARAMETER gradient — the engine would discard them anyway — and never touch the
+    in-place gradient sinks, which belong to the loss's own backward pass.  A plain module-level flag: autograd runs
+    CUDA backward nodes on its device thread, so a thread-local would not be seen there."""
+    active = False
+
+    def __enter__(self):
+        self._prev = positions_only.active
+        positions_only.active = True
+
+    def __exit__(self, *exc):
+        positions_only.active = self._prev
+        return False
+
+
+def validate_graph(z: Tensor, max_z: int, batch: Tensor | None, n_graph: int, edge_index: Tensor) -> None:
+    """Raise IndexError when z, batch or edge_index would index out of range (the reference raises the same from
+    nn.Embedding / index_select: embed.py:41,91, base.py:38, lcaonet.py:462).  One small kernel + one host sync."""
+    require_cuda(z, edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must be an int64 tensor of shape (2, E)")
+    if z.dtype != torch.int64 or (batch is not None and batch.dtype != torch.int64):
+        raise ValueError("z and batch must be int64 tensors")
+    status = torch.empty(1, dtype=torch.int32, device=z.device)
+    ei = edge_index.contiguous()
+    _call("lcao_validate_graph", ptr(z.contiguous()), z.numel(), int(max_z), ptr(batch.contiguous() if batch is not None else None),
+          int(n_graph), ptr(ei), ei.shape[1], ptr(status), stream_ptr())
+    bad = int(status.item())
+    if bad:
+        what = [m for b, m in ((1, f"atomic numbers outside [1, {max_z}]"), (2, f"batch indices outside [0, {n_graph})"),
+                               (4, f"edge_index entries outside [0, {z.numel()})")) if bad & b]
+        raise IndexError("index out of range in the input batch: " + "; ".join(what))
 
 
 def _call(name, *args):
@@ -190,7 +227,7 @@ class _Linear(torch.autograd.Function):
         dy2 = _rows(dy)
         st = stream_ptr()
         need_dx = ctx.needs_input_grad[0]
-        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        need_dw = (ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])) and not positions_only.active
         if ctx.act != ACT_NONE:  # dH = dY * act'(pre), shared by the data and the weight gradient
             dh = torch.empty(M, Nout, device=dy.device)
             _call("lcao_act_bwd", ptr(dy2), _ld(dy2), ptr(pre), Nout, ptr(dh), Nout, M, Nout, ctx.act, st)
@@ -265,7 +302,7 @@ class _PairContract(torch.autograd.Function):
     """B and its Gram matrices from the species-pair coefficient table (see lcao_pair_contract_fwd)."""
 
     @staticmethod
-    def forward(ctx, tab, pair, kptr, kperm, rb, vmask, lgrp, NL: int, C: int):
+    def forward(ctx, tab, pair, grouping, rb, vmask, lgrp, NL: int, C: int):
         require_cuda(tab, pair, rb)
         tab = tab.contiguous()
         P, O, Cp = tab.shape
@@ -277,32 +314,42 @@ class _PairContract(torch.autograd.Function):
         gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=tab.device)
         _call("lcao_pair_contract_fwd", ptr(tab), ptr(pair), ptr(rb), ptr(vmask), ptr(lgrp), E, O, C, NL, valence, ptr(B),
               ptr(gram), None, stream_ptr())
-        ctx.dims = (E, P, O, C, NL, valence)
-        ctx.save_for_backward(tab, pair, kptr, kperm, rb, vmask, lgrp)
+        ctx.dims, ctx.grouping = (E, P, O, C, NL, valence), grouping
+        ctx.save_for_backward(tab, pair, rb, vmask, lgrp)
         ctx.mark_non_differentiable(gram)
         return B, gram
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dB, _dgram):
-        tab, pair, kptr, kperm, rb, vmask, lgrp = ctx.saved_tensors
+        tab, pair, rb, vmask, lgrp = ctx.saved_tensors
         E, P, O, C, NL, valence = ctx.dims
-        if kptr is None:
-            raise LcaoError("pair_contract: the (kptr, kperm) grouping of edges by pair is needed for the backward pass")
+        kptr, kperm = _grouping(ctx.grouping, pair, P)
         dB = dB.contiguous()
         d_tab = torch.empty_like(tab)
-        d_rb = torch.empty_like(rb) if ctx.needs_input_grad[4] else None
+        d_rb = torch.empty_like(rb) if ctx.needs_input_grad[3] else None
         nbytes = int(_lib.load().lcao_pair_contract_bwd_scratch(E, P, O, C, valence))
         scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.int32, device=tab.device)
         _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB),
               E, P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), stream_ptr())
-        return d_tab, None, None, None, d_rb, None, None, None, None
+        return d_tab, None, None, d_rb, None, None, None, None
 
 
-def pair_contract(tab, pair, kptr, kperm, rb, vmask, lgrp, NL, C):
+def _grouping(grouping, pair, P):
+    """(kptr, kperm) from whatever the caller supplied: a callable that builds them on demand (PairCoeffs.grouping), a
+    ready (kptr, kperm) tuple, or None (built here)."""
+    if callable(grouping):
+        return grouping()
+    if grouping is not None and grouping[0] is not None:
+        return grouping
+    with torch.no_grad():
+        return bucket_sort(pair, P, stable=False)
+
+
+def pair_contract(tab, pair, grouping, rb, vmask, lgrp, NL, C):
     """(B, gram): B[e,l,:] = sum_{o in l} rb[e,o] tab[pair[e],o,:] (+ valence slot) — the orbital sums of
     lcaonet.py:180-183 and :200-203 with f_coeffs (lcaonet.py:170) evaluated on the species-pair table."""
-    return _PairContract.apply(tab, pair, kptr, kperm, rb.contiguous(), vmask, lgrp, NL, C)
+    return _PairContract.apply(tab, pair, grouping, rb.contiguous(), vmask, lgrp, NL, C)
 
 
 def coeff_gram(B, NL):
@@ -467,7 +514,7 @@ class _InteractionLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, aux):
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks, act = aux
+        pair, grouping, vmask, lgrp, gi, NL, C, sinks, act = aux
         require_cuda(x, table, rb, unit)
         st = stream_ptr()
         dev = x.device
@@ -524,7 +571,11 @@ class _InteractionLayer(torch.autograd.Function):
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
          lw, bw, a1, pre_a, pre_h, agg, psum) = ctx.saved_tensors
-        pair, kptr, kperm, vmask, lgrp, gi, NL, C, sinks, act = ctx.aux
+        pair, grouping, vmask, lgrp, gi, NL, C, sinks, act = ctx.aux
+        # `positions_only` (autograd forces): no parameter gradient is wanted from this pass, and the sinks are not its to write
+        wg = not positions_only.active
+        if not wg:
+            sinks = None
         # gradient sinks: the parameters' own .grad buffers (order: w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o)
         s_wn, s_bn, s_wc0, s_wc2, s_w3, s_wb, s_w1, s_b1, s_w2, s_b2, s_wo = sinks if sinks is not None else (None,) * 11
         st = stream_ptr()
@@ -536,15 +587,18 @@ class _InteractionLayer(torch.autograd.Function):
         Cp, NG = C * (1 + valence), NL + valence
         need_rb, need_unit = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
         d_out = d_out.contiguous()
+        dw_n = db_n = dw_c0 = dw_c2 = dw_3 = dw_b = dw_1 = db_1 = dw_2 = db_2 = dw_o = d_table = None
         # x_out = x + out_weight(agg)
-        dw_o, _ = _lin_wgrad(d_out, H, agg, C, N, w_o, False, st, s_wo)
+        if wg:
+            dw_o, _ = _lin_wgrad(d_out, H, agg, C, N, w_o, False, st, s_wo)
         d_agg = torch.empty(N, C, device=dev)
         _lin_dgrad(d_out, H, N, w_o, d_agg, C, 0, st)
         # agg[s] = sum_{e in out(s)} bw[e] * h[e]
         d_bw, d_preh = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
         _call("lcao_msg_bwd", ptr(d_agg), C, ptr(gi.src32), None, ptr(bw), ptr(pre_h), E, C, act, ptr(d_bw), ptr(d_preh), st)
         # h = silu(f_node.2(a1)) ; a1 = silu(u_a[s] + u_b[t] + b1)
-        dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st, s_w2, s_b2)
+        if wg:
+            dw_2, db_2 = _lin_wgrad(d_preh, C, a1, C, E, w_2, True, st, s_w2, s_b2)
         # d_prea = d_a1 * SiLU'(pre_a) is never materialised: the two segment sums over it apply the factor on the fly
         d_a1 = torch.empty(E, C, device=dev)
         _lin_dgrad(d_preh, C, E, w_2, d_a1, C, 0, st)
@@ -555,23 +609,26 @@ class _InteractionLayer(torch.autograd.Function):
               d_u.data_ptr() + 4 * C, 2 * C, st)
         d_nw = torch.empty(N, 2 * C, device=dev)
         _lin_dgrad(d_u, 2 * C, N, w_1cat, d_nw, 2 * C, 0, st)  # writes d_xc = d_nw[:, :C]
-        # the bias b_1 enters once per edge through the u_a half: d b_1 = column sums of d_u[:, :C]
-        dw_1cat, db_cat = _lin_wgrad(d_u, 2 * C, nw, 2 * C, N, w_1cat, True, st)
-        dw_1, db_1 = torch.cat([dw_1cat[:C], dw_1cat[C:]], dim=1), db_cat[:C]
-        if s_w1 is not None:
-            s_w1.add_(dw_1)
-            dw_1 = None
-        if s_b1 is not None:
-            s_b1.add_(db_1)
-            db_1 = None
+        if wg:
+            # the bias b_1 enters once per edge through the u_a half: d b_1 = column sums of d_u[:, :C]
+            dw_1cat, db_cat = _lin_wgrad(d_u, 2 * C, nw, 2 * C, N, w_1cat, True, st)
+            dw_1, db_1 = torch.cat([dw_1cat[:C], dw_1cat[C:]], dim=1), db_cat[:C]
+            if s_w1 is not None:
+                s_w1.add_(dw_1)
+                dw_1 = None
+            if s_b1 is not None:
+                s_b1.add_(db_1)
+                db_1 = None
         # bw = basis_weight(lw) ; lw = twobody(B, g) ; g = f_three(tbw) ; tbw = threebody(B, ...)
-        dw_b, _ = _lin_wgrad(d_bw, C, lw, C, E, w_b, False, st, s_wb)
+        if wg:
+            dw_b, _ = _lin_wgrad(d_bw, C, lw, C, E, w_b, False, st, s_wb)
         d_lw = d_preh  # reuse
         _lin_dgrad(d_bw, C, E, w_b, d_lw, C, 0, st)
         dP = torch.empty(E, 1 + valence, C, device=dev)
         d_g = torch.empty(E, Cp, device=dev)
         _call("lcao_twobody_bwd", ptr(psum), 1 + valence, ptr(g), ptr(d_lw), E, C, 1, valence, 1, ptr(dP), ptr(d_g), st)
-        dw_3, _ = _lin_wgrad(d_g, Cp, tbw, C, E, w_3, False, st, s_w3)
+        if wg:
+            dw_3, _ = _lin_wgrad(d_g, Cp, tbw, C, E, w_3, False, st, s_w3)
         d_tbw = d_bw  # reuse
         _lin_dgrad(d_g, Cp, E, w_3, d_tbw, C, 0, st)
         dB = torch.empty(E, NG, C, device=dev)
@@ -584,37 +641,44 @@ class _InteractionLayer(torch.autograd.Function):
         _call("lcao_segment_sum", ptr(q), C, None, 0, ptr(gi.out_ptr), ptr(gi.out_edge), N, C, 0, d_nw.data_ptr() + 4 * C,
               2 * C, st)  # d_xk = d_nw[:, C:]
         # B = pair_contract(tab, rb) ; tab = f_coeffs(table)
-        if kptr is None:
-            raise LcaoError("interaction_layer: the (kptr, kperm) grouping of edges by pair is needed for the backward pass")
-        d_tab = torch.empty(P, O, Cp, device=dev)
+        need_tab = wg and (ctx.needs_input_grad[1] or any(ctx.needs_input_grad[6:8]))
         d_rb = torch.empty(E, O, device=dev) if need_rb else None
-        nbytes = int(_lib.load().lcao_pair_contract_bwd_scratch(E, P, O, C, valence))
-        scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.int32, device=dev)
-        _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB), E,
-              P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), st)
-        d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st, act)
-        dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st, s_wc2)
-        d_pre1 = torch.empty(P * O, C, device=dev)
-        _lin_dgrad_act(d_pre2, Cp, P * O, w_c2, pre1, d_pre1, C, st, act)
-        dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st, s_wc0)
-        d_table = torch.empty(P, O, K, device=dev)
-        _lin_dgrad(d_pre1, C, P * O, w_c0, d_table, K, 0, st)
+        if need_tab or need_rb:
+            kptr, kperm = _grouping(grouping, pair, P)
+            d_tab = torch.empty(P, O, Cp, device=dev) if need_tab else None
+            scratch = None
+            if need_tab:
+                nbytes = int(_lib.load().lcao_pair_contract_bwd_scratch(E, P, O, C, valence))
+                scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.int32, device=dev)
+            _call("lcao_pair_contract_bwd", ptr(tab), ptr(pair), ptr(kptr), ptr(kperm), ptr(rb), ptr(vmask), ptr(lgrp), ptr(dB), E,
+                  P, O, C, NL, valence, ptr(d_tab), ptr(d_rb), ptr(scratch), st)
+        if need_tab:
+            d_pre2 = _act_bwd(d_tab, pre2, P * O, Cp, st, act)
+            dw_c2, _ = _lin_wgrad(d_pre2, Cp, t1, C, P * O, w_c2, False, st, s_wc2)
+            d_pre1 = torch.empty(P * O, C, device=dev)
+            _lin_dgrad_act(d_pre2, Cp, P * O, w_c2, pre1, d_pre1, C, st, act)
+            dw_c0, _ = _lin_wgrad(d_pre1, C, table, K, P * O, w_c0, False, st, s_wc0)
+            if ctx.needs_input_grad[1]:
+                d_table = torch.empty(P, O, K, device=dev)
+                _lin_dgrad(d_pre1, C, P * O, w_c0, d_table, K, 0, st)
         # nw = node_weight(x) ; residual
-        dw_n, db_n = _lin_wgrad(d_nw, 2 * C, x, H, N, w_n, True, st, s_wn, s_bn)
+        if wg:
+            dw_n, db_n = _lin_wgrad(d_nw, 2 * C, x, H, N, w_n, True, st, s_wn, s_bn)
         dx = d_out.clone()
         _lin_dgrad(d_nw, 2 * C, N, w_n, dx, H, 1, st)
         d_unit = (du_ks + du_st) if need_unit else None
         return dx, d_table, d_rb, d_unit, dw_n, db_n, dw_c0, dw_c2, dw_3, dw_b, dw_1, db_1, dw_2, db_2, dw_o, None
 
 
-def interaction_layer(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, pair, kptr, kperm, vmask,
+def interaction_layer(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o, pair, grouping, vmask,
                       lgrp, gi, NL, C, grad_sinks=None, act=ACT_SILU):
     """grad_sinks: optional 11-tuple of the weights' / biases' `.grad` buffers (contiguous, same shapes; None entries
     allowed).  The backward pass then ACCUMULATES those gradients in place and returns None for them to autograd —
-    what AccumulateGrad would do, without the zero-fills and the per-parameter add kernels.  Opt-in
+    what AccumulateGrad would do, without the zero-fills and the per-parameter add kernels.  `grouping`: callable
+    returning (kptr, kperm), a ready tuple, or None (see `_grouping`).  Opt-in
     (`LCAOInteraction.grads_in_place`, set by `dist.FlatGradBucket`): parameter hooks do not fire for them."""
     return _InteractionLayer.apply(x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o,
-                                   (pair, kptr, kperm, vmask, lgrp, gi, NL, C, grad_sinks, _act_arg(act)))
+                                   (pair, grouping, vmask, lgrp, gi, NL, C, grad_sinks, _act_arg(act)))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -59,6 +59,20 @@ def lcao_bucket_sort(keys, sec, n, nb, ptr, perm, scratch, stable, stream):
         view(perm, n, dtype=I32).copy_(o)
 
 
+def lcao_validate_graph(z, N, max_z, batch, n_graph, ei, E, status, stream):
+    bad = 0
+    zz, bb = view(z, N, dtype=I64), view(batch, N, dtype=I64)
+    if zz is not None and N and bool(((zz < 1) | (zz > max_z)).any()):
+        bad |= 1
+    if bb is not None and N and bool(((bb < 0) | (bb >= n_graph)).any()):
+        bad |= 2
+    if E:
+        e = view(ei, 2 * E, dtype=I64)
+        if bool(((e < 0) | (e >= N)).any()):
+            bad |= 4
+    view(status, 1, dtype=I32).fill_(bad)
+
+
 def lcao_graph_index_build(ei, E, N, src32, dst32, in_ptr, in_edge, in_src, out_ptr, out_edge, tri_ptr, scratch, stream):
     e = view(ei, 2, E, dtype=I64) if E else torch.empty(2, 0, dtype=I64)
     s, t = e[0], e[1]
@@ -340,9 +354,10 @@ def lcao_pair_contract_bwd(tab, pair, kptr, kperm, rb, vmask, lgrp, dB, E, P, O,
         m = view(vmask, E, O)
         dv = dl + d[:, NL].unsqueeze(1)
         contrib[..., C:] = (r * m).unsqueeze(-1) * dv
-    out = view(d_tab, P, O * Cp)
-    out.zero_()
-    out.index_add_(0, key_of, contrib.reshape(E, O * Cp))
+    if d_tab:
+        out = view(d_tab, P, O * Cp)
+        out.zero_()
+        out.index_add_(0, key_of, contrib.reshape(E, O * Cp))
     if d_rb:
         pr = view(pair, E, dtype=I64)
         c = view(tab, P, O * Cp).reshape(P, O, Cp)[pr]

@@ -183,7 +183,7 @@ def test_pair_contract_vs_restatement(C, NL, valence, O, P, monkeypatch):
     def fn(tab, pair, rb, vmask, lgrp):
         tab, rb = tab.clone().requires_grad_(True), rb.clone().requires_grad_(True)
         kptr, kperm = ops.bucket_sort(pair, P, stable=False)
-        B, gram = ops.pair_contract(tab, pair, kptr, kperm, rb, vmask, lgrp, NL, C)
+        B, gram = ops.pair_contract(tab, pair, (kptr, kperm), rb, vmask, lgrp, NL, C)
         (B * torch.linspace(-1, 2, C, device=B.device)).sum().backward()
         return B.detach(), gram, tab.grad, rb.grad
 
@@ -387,6 +387,7 @@ def test_linear_tensor_core_modes(mode, tol, M, K, N, silu, bias):
     ref = torch.nn.functional.silu(ref) if silu else ref
     probe = torch.randn(M, N, device=DEV, dtype=torch.float64)
     grads = torch.autograd.grad((ref * probe).sum(), [xd, wd] + ([bd] if bias else []))
+    prev = ops.get_gemm_mode()
     ops.set_gemm_mode(mode)
     try:
         xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
@@ -395,7 +396,7 @@ def test_linear_tensor_core_modes(mode, tol, M, K, N, silu, bias):
         (y * probe.float()).sum().backward()
         torch.cuda.synchronize()
     finally:
-        ops.set_gemm_mode("fp32")
+        ops.set_gemm_mode(prev)
     assert rel_l2(y, ref) < tol
     # the weight gradient sums M terms in FP32: allow the sqrt(M) * eps growth any FP32 reduction shows
     tol_w = max(2 * tol, 2e-8 * M**0.5)

@@ -139,3 +139,87 @@ def test_cpu_tensors_are_rejected_without_the_emulator():
     model = LCAONet(**gold["kwargs"])
     with pytest.raises(LcaoError):
         model(GraphBatch(gold["graph"]))
+
+
+# ---- round-1 ADVICE regressions ---------------------------------------------------------------------------------------
+def _grads(model):
+    return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def test_grad_bucket_with_autograd_forces_equals_plain_path(monkeypatch):
+    """In-place gradient sinks (FlatGradBucket) + autograd forces: the d E / d pos pass must not leak parameter
+    gradients of E.sum() into the sinks.  Two steps, so stale state would show."""
+    from lcaonet_b200.dist import FlatGradBucket
+    res = []
+    for use_bucket in (False, True):
+        gold, model, g, _ = _run("crystal_autograd_forces", monkeypatch)
+        bucket = FlatGradBucket(model) if use_bucket else None
+        for _ in range(2):
+            if bucket is not None:
+                bucket.zero()
+            else:
+                model.zero_grad(set_to_none=True)
+            energy, forces = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+            (energy**2).mean().backward()
+        res.append((energy.detach(), forces.detach(), _grads(model)))
+    (e0, f0, g0), (e1, f1, g1) = res
+    assert rel_l2(e1, e0) < 1e-6 and rel_l2(f1, f0) < 1e-6 and g0.keys() == g1.keys()
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) < 1e-5, n
+    worst = max(rel_l2(g1[n], gold["grads_energy_f64"][n]) for n in g1 if float(gold["grads_energy_f64"][n].norm()) > 0)
+    assert worst < 2e-4, worst
+
+
+@pytest.mark.parametrize("freeze", ["all", "embedding"])
+def test_frozen_parameters_still_backpropagate(freeze, monkeypatch):
+    """Frozen model + autograd forces (MD / inference) and frozen embedding + trainable interaction blocks (fine
+    tuning): the pair grouping the backward kernels need is built on demand."""
+    gold, model, g, _ = _run("crystal_autograd_forces", monkeypatch)
+    for n, p in model.named_parameters():
+        if freeze == "all" or n.startswith("emb_layer"):
+            p.requires_grad_(False)
+    energy, forces = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+    assert rel_l2(forces, gold["forces_f64"]) < 2e-5
+    if freeze == "embedding":
+        (energy**2).mean().backward()
+        for n, p in model.named_parameters():
+            ref = gold["grads_energy_f64"][n]
+            if n.startswith("emb_layer"):
+                assert p.grad is None
+            elif ref is not None and float(ref.norm()) > 0:
+                assert rel_l2(p.grad, ref) < 2e-4, n
+
+
+def test_out_of_range_indices_raise_index_error(monkeypatch):
+    """z > max_z, batch >= n_graph, edge_index >= N: IndexError (as the reference's nn.Embedding / index_select),
+    not a silent out-of-bounds access."""
+    cpu_abi.install(monkeypatch)
+    gold = load_golden("qm9_default_eval")
+    model = LCAONet(**gold["kwargs"])
+    for key, bad in (("z", 37), ("z", 0), ("batch", 99), ("edge_index", 10**6), ("edge_index", -1)):
+        g = GraphBatch({k: v.clone() for k, v in gold["graph"].items()})
+        g[key].view(-1)[3] = bad
+        with pytest.raises(IndexError):
+            model(g)
+    model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))  # and the clean batch passes
+
+
+def test_grad_bucket_survives_zero_grad(monkeypatch):
+    """optimizer.zero_grad() (set_to_none=True) detaches every .grad from the flat buffer: all_reduce_mean() re-attaches
+    them and keeps the gradient that was accumulated meanwhile."""
+    from lcaonet_b200.dist import FlatGradBucket
+    gold, model, g, out = _run("qm9_default_eval", monkeypatch)
+    model.train()
+    bucket = FlatGradBucket(model)
+    model.zero_grad(set_to_none=True)
+    out = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+    (out**2).mean().backward()
+    want = _grads(model)
+    bucket.all_reduce_mean()
+    off = 0
+    for p in bucket.params:
+        assert p.grad.data_ptr() == bucket.flat[off: off + p.numel()].data_ptr()
+        off += p.numel()
+    for n, p in model.named_parameters():
+        if n in want:
+            assert torch.equal(p.grad, want[n]), n
