@@ -139,6 +139,17 @@ def main():
                                          regress_forces=True, direct_forces=True, **small), qm9s)
     run_case("qm9_gelu_valence", dict(cutoff=5.0, cutoff_net="polynomial", activation="gelu", add_valence=True,
                                       emb_size=16, emb_size_coeff=16, emb_size_conv=16), qm9s)
+    # ---- the BASELINE.json configurations at their REAL widths (round-1 verdict: the benchmarked sizes had no
+    #      reference-derived golden).  configs[0]: 32 QM9-like molecules, default model 128/128/128 x3.
+    run_case("cfg1_qm9_32mol", dict(cutoff=5.0, cutoff_net="polynomial"), synth.qm9_like_batch(32, seed=0, cutoff=5.0, margin=0.05))
+    # configs[2]: add_valence + extend_orb + n_per_orb=2, max_z=36 at width 128 (O = 16, C' = 256)
+    run_case("cfg3_valence_width128", dict(cutoff=5.0, cutoff_net="polynomial", add_valence=True, extend_orb=True,
+                                           n_per_orb=2, max_z=36), qm9)
+    # configs[3]: periodic crystal cell (64 atoms, cutoff 6.0, ~49 neighbours/atom), energy + autograd forces at width 128
+    run_case("cfg4_crystal_width128", dict(cutoff=6.0, cutoff_net="polynomial", regress_forces=True, direct_forces=False),
+             xtl)
+    # spherical-Bessel radial basis (rbf.py:145-182)
+    run_case("qm9_sphericalbessel", dict(cutoff=5.0, cutoff_net="polynomial", rbf_type="sphericalbessel", **small), qm9s)
 
 
 if __name__ == "__main__":

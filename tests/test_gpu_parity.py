@@ -15,7 +15,8 @@ from tests._util import full_cfg, graph_as, load_golden, rel_l2, same_triplets_u
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN_CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
-                "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus", "qm9_gelu_valence"]
+                "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel",
+                "cfg1_qm9_32mol", "cfg3_valence_width128"]
 
 
 # ---------------------------------------------------------------------------- index construction
@@ -263,6 +264,11 @@ def test_model_matches_reference_golden(name):
         (g["idx_k_3b"], g["edge_idx_ks_3b"], g["edge_idx_st_3b"]),
         (trip["idx_k_3b"], trip["edge_idx_ks_3b"], trip["edge_idx_st_3b"]))
     assert torch.allclose(g["edge_dist"].cpu().double(), gold["edge_dist_f64"], rtol=1e-6, atol=1e-6)
+    # cos(theta) per triplet (lcaonet.py:431-435): same multiset always, same positions when no (k, s) pair is duplicated
+    ang = g["angles_3b"].cpu()
+    assert torch.allclose(ang.sort().values, gold["angles_f32"].sort().values, atol=2e-6)
+    if torch.equal(g["edge_idx_ks_3b"].cpu().to(torch.int32), trip["edge_idx_ks_3b"]):
+        assert torch.allclose(ang, gold["angles_f32"], atol=2e-6)
     loss.backward()
     worst, worst_ref = 0.0, 0.0
     for n, p in model.named_parameters():
@@ -281,12 +287,13 @@ def test_model_matches_reference_golden(name):
 
 def test_autograd_forces_match_reference_golden():
     from tests.test_host_logic_cpu import _check_autograd_forces
-    gold = load_golden("crystal_autograd_forces")
-    model = LCAONet(**gold["kwargs"])
-    model.load_state_dict(gold["state_dict"], strict=True)
-    model = model.to(DEV).train(gold["training"])
-    out = model(GraphBatch(gold["graph"]).to(DEV))
-    _check_autograd_forces(gold, model, out, 1e-5, 5e-5)
+    for name in ("crystal_autograd_forces", "cfg4_crystal_width128"):
+        gold = load_golden(name)
+        model = LCAONet(**gold["kwargs"])
+        model.load_state_dict(gold["state_dict"], strict=True)
+        model = model.to(DEV).train(gold["training"])
+        out = model(GraphBatch(gold["graph"]).to(DEV))
+        _check_autograd_forces(gold, model, out, 1e-5, 5e-5)
 
 
 def test_degenerate_graphs_match_oracle():
@@ -410,13 +417,14 @@ def test_model_golden_with_tf32x3_gemms():
     model = LCAONet(**gold["kwargs"])
     model.load_state_dict(gold["state_dict"], strict=True)
     model = model.to(DEV).train()
+    prev = ops.get_gemm_mode()
     ops.set_gemm_mode("tf32x3")
     try:
         out = model(GraphBatch(gold["graph"]).to(DEV))
         (out**2).mean().backward()
         torch.cuda.synchronize()
     finally:
-        ops.set_gemm_mode("fp32")
+        ops.set_gemm_mode(prev)
     assert rel_l2(out, gold["energy_f64"]) < 1e-5
     worst = max(rel_l2(p.grad, gold["grads_f64"][n]) for n, p in model.named_parameters()
                 if gold["grads_f64"][n] is not None and float(gold["grads_f64"][n].norm()) > 0)

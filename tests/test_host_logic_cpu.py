@@ -10,7 +10,8 @@ from tests import cpu_abi
 from tests._util import load_golden, rel_l2, same_triplets_up_to_duplicate_order
 
 CASES = ["qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
-         "fixture_cosine_minmaxorb_atomref", "qm9_default", "qm9_shiftedsoftplus", "qm9_gelu_valence"]
+         "fixture_cosine_minmaxorb_atomref", "qm9_default", "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel",
+         "cfg3_valence_width128"]
 
 
 def _run(name, monkeypatch):
