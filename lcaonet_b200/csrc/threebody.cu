@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tb_common.cuh"
 
 namespace {
 
@@ -34,66 +35,6 @@ constexpr int kFwdWarps = 2;   // forward CTA: 2 warps x 8 out-edges per pass
 constexpr int kBwdWarps = 4;   // backward CTA: 4 warps, one in-edge per warp at a time (2 measured slower: 168 vs 128 registers)
 constexpr int kR = 8;          // forward: out-edge accumulators per warp
 constexpr int kIB = 4;         // forward: in-edges per coefficient batch (kR * kIB = 32 pairs = one per lane)
-constexpr int kJS = 64;        // backward (forces): out-edges whose d_unit partials live in shared memory
-constexpr float kEps = 1e-12f; // F.normalize eps (lcaonet.py:184)
-
-template <int NL>
-__device__ __forceinline__ void sph_harm(float c, float (&Y)[4]) {
-  Y[0] = LCAO_Y0;
-  Y[1] = (NL > 1) ? LCAO_Y1 * c : 0.f;
-  Y[2] = (NL > 2) ? fmaf(LCAO_Y2A * c, c, -LCAO_Y2B) : 0.f;
-  Y[3] = (NL > 3) ? LCAO_Y3 * c * fmaf(5.0f * c, c, -3.0f) : 0.f;
-}
-template <int NL>
-__device__ __forceinline__ void sph_harm_grad(float c, float (&dY)[4]) {
-  dY[0] = 0.f;
-  dY[1] = (NL > 1) ? LCAO_Y1 : 0.f;
-  dY[2] = (NL > 2) ? 2.0f * LCAO_Y2A * c : 0.f;
-  dY[3] = (NL > 3) ? LCAO_Y3 * fmaf(15.0f * c, c, -3.0f) : 0.f;
-}
-
-// |sum_l Y_l B_l|^2 = Y^T G Y from the upper-triangular FP64 Gram matrix g (NL(NL+1)/2 entries)
-template <int NL>
-__device__ __forceinline__ double quad_form(const double* g, const float (&Y)[4]) {
-  double s = 0.0;
-  int i = 0;
-#pragma unroll
-  for (int a = 0; a < NL; ++a)
-#pragma unroll
-    for (int b = a; b < NL; ++b) {
-      const double t = (double)Y[a] * (double)Y[b] * g[i++];
-      s += (a == b) ? t : 2.0 * t;
-    }
-  return s;
-}
-// sum_l X_l (G Y)_l  (bilinear form with the symmetric Gram matrix)
-template <int NL>
-__device__ __forceinline__ double bilin_form(const double* g, const float (&X)[4], const float (&Y)[4]) {
-  double s = 0.0;
-  int i = 0;
-#pragma unroll
-  for (int a = 0; a < NL; ++a)
-#pragma unroll
-    for (int b = a; b < NL; ++b) {
-      const double gg = g[i++];
-      s += (a == b) ? (double)X[a] * Y[a] * gg : ((double)X[a] * Y[b] + (double)X[b] * Y[a]) * gg;
-    }
-  return s;
-}
-
-__device__ __forceinline__ float4 fma4(float a, float4 x, float4 acc) {
-  return make_float4(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y), fmaf(a, x.z, acc.z), fmaf(a, x.w, acc.w));
-}
-__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
-__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 scale4(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
-__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ float4 sigmoid4(float4 x) {
-  return make_float4(sigmoidf_acc(x.x), sigmoidf_acc(x.y), sigmoidf_acc(x.z), sigmoidf_acc(x.w));
-}
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float comp4(const float4& a, int l) { return l == 0 ? a.x : l == 1 ? a.y : l == 2 ? a.z : a.w; }
 
 // (Packed FP32 pairs — fma.rn.f32x2 / FFMA2 — were tried for the FMA blocks: same FP32 pipe rate (measured 36.8 vs
 // 36.2 TFMA/s, scripts/micro/ffma2.cu) and the forward kernel ran 2x SLOWER with them; see profiles/r01_notes.md.)
@@ -556,6 +497,20 @@ int tile_in(const char* env, int dflt, int lo, int hi) {
 
 }  // namespace
 
+// warp-level tensor-core formulation (threebody_mma.cu): the default for C <= 128
+int lcao_tb_mma_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
+                    const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
+                    const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, float* tbw, cudaStream_t st);
+int lcao_tb_mma_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
+                    const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
+                    const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, const float* d_tbw, const float* dP, float* dB,
+                    float* q, float* du_ks, float* du_st, cudaStream_t st);
+// LCAO_TB_IMPL=simt forces the FP32-pipe kernels of this file (A/B measurements); they also serve C > 128
+static bool use_mma(int C) {
+  static const bool simt = [] { const char* s = getenv("LCAO_TB_IMPL"); return s && s[0] == 's'; }();
+  return !simt && C <= 128;
+}
+
 #define TB_DISPATCH(NL, V4, CALL)   \
   switch ((NL) * 10 + (V4)) {       \
     case 11: { CALL(1, 1); } break; \
@@ -578,6 +533,7 @@ extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldg % 4 == 0,
                "lcao_threebody_fwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL (C=%d NL=%d NG=%d)", C, NL, NG);
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_mma(C)) return lcao_tb_mma_fwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, tbw, st);
   const int V4 = C <= 128 ? 1 : 2;
   static const int per_sm_f = tile_in("LCAO_TB_GRID_FWD", 48, 1, 64);
   const unsigned grid = (unsigned)(N < 148ll * per_sm_f ? N : 148ll * per_sm_f);
@@ -603,6 +559,9 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE((d_unit_ks == nullptr) == (d_unit_st == nullptr), "lcao_threebody_bwd: pass both d_unit buffers or neither");
   LCAO_REQUIRE(NG <= NL + 1, "lcao_threebody_bwd: at most one valence group (NG <= NL + 1)");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_mma(C))
+    return lcao_tb_mma_bwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, d_tbw, dP, dB, q,
+                           d_unit_ks, d_unit_st, st);
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
   const bool full = C == 128 * V4;

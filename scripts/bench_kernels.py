@@ -120,6 +120,48 @@ def edge():
     print(f"graph index build: {t_i:.3f} ms", flush=True)
 
 
+def tb():
+    """three-body kernels alone, QM9-shape (config 2) and crystal (config 4, 64 cells) graphs; realistic B / Gram from
+    the pair-table kernel so the coefficient chain sees sane norms"""
+    from lcaonet_b200.synth import crystal_like_batch
+    P, st = ops.ptr, ops.stream_ptr
+    C, NL, O = 128, 3, 8
+    for name, g in (("qm9 1024 mol", qm9_like_batch(1024, seed=1000)), ("crystal 64 cells", crystal_like_batch(64, seed=1000))):
+        g = g.to(DEV)
+        N, E = g["z"].shape[0], g["edge_index"].shape[1]
+        gi = ops.GraphIndex(g["edge_index"], N)
+        Zd = 37
+        z = g["z"]
+        pair = (z[g["edge_index"][0]] * Zd + z[g["edge_index"][1]]).contiguous()
+        torch.manual_seed(0)
+        tab = torch.randn(Zd * Zd, O, C, device=DEV)
+        rb = torch.randn(E, O, device=DEV)
+        lgrp = torch.tensor([0, 0, 1, 0, 1, 0, 2, 1], dtype=torch.int32, device=DEV)
+        B = torch.empty(E, NL, C, device=DEV)
+        gram = torch.empty(E, NL * (NL + 1) // 2, dtype=torch.float64, device=DEV)
+        ops._call("lcao_pair_contract_fwd", P(tab), P(pair), P(rb), None, P(lgrp), E, O, C, NL, 0, P(B), P(gram), None, st())
+        unit = torch.nn.functional.normalize(torch.randn(E, 3, device=DEV), dim=1)
+        xk = torch.sigmoid(torch.randn(N, C, device=DEV))
+        tbw, dB, q = torch.empty(E, C, device=DEV), torch.empty(E, NL, C, device=DEV), torch.empty(E, C, device=DEV)
+        du1, du2 = torch.empty(E, 3, device=DEV), torch.empty(E, 3, device=DEV)
+        d_tbw = torch.randn(E, C, device=DEV)
+        args = (P(B), NL, P(gram), P(unit), P(xk), xk.stride(0), P(gi.in_ptr), P(gi.in_edge), P(gi.in_src), P(gi.out_ptr),
+                P(gi.out_edge), N, E, C, NL)
+        t_f = timeit(lambda: ops._call("lcao_threebody_fwd", *args, P(tbw), st()), reps=9)
+        t_b = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), None, P(dB), P(q), None, None, st()), reps=9)
+        t_bf = timeit(lambda: ops._call("lcao_threebody_bwd", *args, P(d_tbw), None, P(dB), P(q), P(du1), P(du2), st()), reps=9)
+        T = gi.num_triplets()
+        bf = E * (4 * NL * C + 48 + 12 + 8 + 4 * C) + N * (4 * C + 8)
+        bb = E * (4 * NL * C + 48 + 4 * C + 12 + 8 + 4 * NL * C + 4 * C) + N * (4 * C + 8)
+        peak = 6556.5
+        print(f"threebody[{os.environ.get('LCAO_TB_IMPL', 'mma')}] {name}: N={N} E={E} T={T}: fwd {t_f:.3f} ms ({bf/t_f/1e6:.0f} GB/s, "
+              f"{bf/t_f/1e6/peak:.2f}) | bwd {t_b:.3f} ms ({bb/t_b/1e6:.0f} GB/s, {bb/t_b/1e6/peak:.2f}) | bwd+forces {t_bf:.3f} ms "
+              f"({bb/t_bf/1e6/peak:.2f})", flush=True)
+        # checksums for A/B comparisons between implementations (LCAO_TB_IMPL=simt)
+        print(f"  checksums: tbw {float(tbw.double().abs().sum()):.9e} dB {float(dB.double().abs().sum()):.9e} q "
+              f"{float(q.double().abs().sum()):.9e} du {float((du1 + du2).double().abs().sum()):.9e}", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
@@ -128,3 +170,5 @@ if __name__ == "__main__":
         gemm_small()
     if what in ("edge", "all"):
         edge()
+    if what in ("tb", "all"):
+        tb()
