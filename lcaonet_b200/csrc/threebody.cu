@@ -497,18 +497,15 @@ int tile_in(const char* env, int dflt, int lo, int hi) {
 
 }  // namespace
 
-// warp-level tensor-core formulation (threebody_mma.cu): the default for C <= 128
+// warp-level tensor-core formulation with bulk-copy staging (threebody_mma.cu): the default forward for C <= 128
 int lcao_tb_mma_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
                     const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
                     const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, float* tbw, cudaStream_t st);
-int lcao_tb_mma_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
-                    const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
-                    const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, const float* d_tbw, const float* dP, float* dB,
-                    float* q, float* du_ks, float* du_st, cudaStream_t st);
-// LCAO_TB_IMPL=simt forces the FP32-pipe kernels of this file (A/B measurements); they also serve C > 128
-static bool use_mma(int C) {
+// LCAO_TB_IMPL=simt forces the FP32-pipe forward kernel of this file (A/B measurements); it also serves C > 128 and
+// buffers that are not 16-byte aligned (the bulk copies need that)
+static bool use_mma(int C, const void* B, const void* gate, int64_t ldg) {
   static const bool simt = [] { const char* s = getenv("LCAO_TB_IMPL"); return s && s[0] == 's'; }();
-  return !simt && C <= 128;
+  return !simt && C <= 128 && ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(gate)) & 15u) == 0 && ldg % 4 == 0;
 }
 
 #define TB_DISPATCH(NL, V4, CALL)   \
@@ -533,7 +530,7 @@ extern "C" int lcao_threebody_fwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE(C % 4 == 0 && C > 0 && C <= 256 && NL >= 1 && NL <= 4 && NG >= NL && ldg % 4 == 0,
                "lcao_threebody_fwd: need C %% 4 == 0, C <= 256, 1 <= NL <= 4, NG >= NL (C=%d NL=%d NG=%d)", C, NL, NG);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_mma(C)) return lcao_tb_mma_fwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, tbw, st);
+  if (use_mma(C, B, gate, ldg)) return lcao_tb_mma_fwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, tbw, st);
   const int V4 = C <= 128 ? 1 : 2;
   static const int per_sm_f = tile_in("LCAO_TB_GRID_FWD", 48, 1, 64);
   const unsigned grid = (unsigned)(N < 148ll * per_sm_f ? N : 148ll * per_sm_f);
@@ -559,9 +556,6 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE((d_unit_ks == nullptr) == (d_unit_st == nullptr), "lcao_threebody_bwd: pass both d_unit buffers or neither");
   LCAO_REQUIRE(NG <= NL + 1, "lcao_threebody_bwd: at most one valence group (NG <= NL + 1)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_mma(C))
-    return lcao_tb_mma_bwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, d_tbw, dP, dB, q,
-                           d_unit_ks, d_unit_st, st);
   const bool forces = d_unit_ks != nullptr;
   const int V4 = C <= 128 ? 1 : 2;
   const bool full = C == 128 * V4;

@@ -47,3 +47,21 @@ def test_dataset_reads_the_reference_layout(tmp_path):
             ds[4]
     with pytest.raises(FileNotFoundError):
         GraphDataset(os.path.join(tmp_path, "missing"))
+
+
+@pytest.mark.parametrize("maker", [lambda: qm9_like_batch(9, seed=4), lambda: crystal_like_batch(3, seed=2)])
+def test_sample_pool_collates_like_the_host_loop(maker):
+    from lcaonet_b200.data import SamplePool, collate_window
+    g = maker()
+    samples = split(g)
+    for pool in (SamplePool(samples), SamplePool.from_batch(g)):
+        assert len(pool) == len(samples)
+        ids = torch.tensor([len(samples) - 1, 0, 2, 2])
+        got, want = pool.batch(ids), collate([samples[i] for i in ids.tolist()])
+        assert set(got.keys()) == set(want.keys())
+        for k, v in want.items():
+            assert torch.equal(got[k], v), k
+        win = collate_window(pool.window(1, 3))
+        want = collate(samples[1:3])
+        for k, v in want.items():
+            assert torch.equal(win[k], v), k
