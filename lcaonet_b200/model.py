@@ -22,7 +22,7 @@ from torch import Tensor
 from . import _lib, ops
 from .keys import GraphKeys
 from .orbitals import ElecInfo
-from .resolve import activation_code, activation_resolver, cutoff_kind, init_params, init_resolver, rbf_kind
+from .resolve import activation_code, activation_resolver, cutoff_kind, init_params, init_resolver, rbf_kind, swish_beta
 
 
 # ----------------------------------------------------------------------------------------------
@@ -63,7 +63,12 @@ def _mlp(seq: nn.Sequential, x: Tensor) -> Tensor:
     i = 0
     while i < len(mods):
         fused = i + 1 < len(mods) and not isinstance(mods[i + 1], Dense)
-        x = mods[i](x, silu=activation_code(mods[i + 1]) if fused else False)
+        beta = swish_beta(mods[i + 1]) if fused else None
+        if beta is not None:  # Swish: SiLU kernel on beta-scaled weights, then 1 / beta (see resolve.swish_beta)
+            d = mods[i]
+            x = ops.linear(x, d.weight * beta, d.bias * beta if d.bias is not None else None, True) / beta
+        else:
+            x = mods[i](x, silu=activation_code(mods[i + 1]) if fused else False)
         i += 2 if fused else 1
     return x
 
@@ -345,7 +350,15 @@ class LCAOInteraction(nn.Module):
             params = (self.node_weight.weight, self.node_weight.bias, fc[0].weight, fc[2].weight, self.f_three[0].weight,
                       self.basis_weight.weight, fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias, self.out_weight.weight)
             sinks = None
-            if self.grads_in_place and torch.is_grad_enabled():
+            beta = swish_beta(fn[1])
+            if beta is not None:
+                # Swish: every activation site becomes SiLU on beta-scaled weights (resolve.swish_beta).  The factors that are
+                # left over cancel or fold into the next layer: tab comes out as beta * tab, which both of its consumers
+                # normalise away (lcaonet.py:184,204); a1 and h come out times beta -> f_node.2 keeps its weight, its bias
+                # and out_weight absorb the rest.
+                w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o = params
+                params = (w_n, b_n, w_c0 * beta, w_c2, w_3, w_b, w_1 * beta, b_1 * beta, w_2, b_2 * beta, w_o / beta)
+            elif self.grads_in_place and torch.is_grad_enabled():
                 sinks = tuple(p.grad if (p.requires_grad and p.grad is not None and p.grad.is_contiguous()) else None
                               for p in params)
             return ops.interaction_layer(x, cst.table, rb, unit, *params, cst.pair, cst.grouping, vmask, lgrp, gi, NL, C,
@@ -364,11 +377,16 @@ class LCAOInteraction(nn.Module):
         lw = ops.twobody(B, g, NL, 1 if self.add_valence else 0, link)  # (E, C)
         bw = self.basis_weight(lw)
         w1 = self.f_node[0].weight  # (C, 2C) acting on [x_s ; x_t]  ->  W1a x_s + W1b x_t, per NODE
+        act, beta = activation_code(self.f_node[1]), swish_beta(self.f_node[1])
+        b1, w2, b2 = self.f_node[0].bias, self.f_node[2].weight, self.f_node[2].bias
+        if beta is not None:  # Swish = SiLU on beta-scaled weights (resolve.swish_beta); a1 comes out times beta
+            w1, b1, b2 = w1 * beta, b1 * beta, b2 * beta
         u = ops.linear(xc, torch.cat([w1[:, :C], w1[:, C:]], dim=0))  # (N, 2C)
-        act = activation_code(self.f_node[1])
-        a1 = ops.edge_pair(u[:, :C], u[:, C:], self.f_node[0].bias, gi, silu=act)  # (E, C)
-        h = self.f_node[2](a1, silu=act)
+        a1 = ops.edge_pair(u[:, :C], u[:, C:], b1, gi, silu=act)  # (E, C)
+        h = ops.linear(a1, w2, b2, act)
         agg = ops.mul_segment_sum(bw, h, gi)  # (N, C) sum over out-edges of each centre
+        if beta is not None:
+            agg = agg / beta
         return x + self.out_weight(agg)
 
 
@@ -394,11 +412,16 @@ class LCAOOut(nn.Module):
             return prop
         if self.direct_forces:
             H = self.emb_size
-            w1 = self.out_lin_force[0].weight
+            w1, b1 = self.out_lin_force[0].weight, self.out_lin_force[0].bias
+            w2, b2 = self.out_lin_force[2].weight, self.out_lin_force[2].bias
+            act, beta = activation_code(self.out_lin_force[1]), swish_beta(self.out_lin_force[1])
+            if beta is not None:  # Swish = SiLU on beta-scaled weights (resolve.swish_beta): a comes out times beta, twice
+                w1, b1, b2 = w1 * beta, b1 * beta, b2 * beta
             u = ops.linear(x, torch.cat([w1[:, :H], w1[:, H:]], dim=0))
-            act = activation_code(self.out_lin_force[1])
-            a = ops.edge_pair(u[:, :H], u[:, H:], self.out_lin_force[0].bias, gi, silu=act)
-            a = self.out_lin_force[2](a, silu=act)
+            a = ops.edge_pair(u[:, :H], u[:, H:], b1, gi, silu=act)
+            a = ops.linear(a, w2, b2, act)
+            if beta is not None:
+                a = a / beta
             f_st = self.out_lin_force[4](a) * unit  # (E, 3)
             return prop, ops.segment_reduce(f_st, gi.out_ptr, gi.out_edge, gi.src32, mean=False)
         # d E / d pos only: the backward kernels skip every parameter gradient inside this pass (ops.positions_only)
@@ -439,15 +462,49 @@ def _laguerre(n: int, l: int) -> list[int]:
             for i in range(k + 1)]
 
 
+def _cutoff_value(kind: int, r: float, rc: float) -> float:
+    """host-side cutoff functions (cutoff.py:32-67) for the constructor-time quadrature of `integral_norm`"""
+    if r > rc:
+        return 0.0
+    q = r / rc
+    if kind == _lib.CUT["polynomial"]:
+        return (1.0 - q) ** 3 * (1.0 + 3.0 * q + 6.0 * q * q)  # = 1 - 10 q^3 + 15 q^4 - 6 q^5
+    if kind == _lib.CUT["envelope"]:
+        return (1.0 - q) ** 3 * (1.0 + 3.0 * q + 6.0 * q**2 + 10.0 * q**3 + 15.0 * q**4)  # p = 5: 1 - 21 q^5 + 35 q^6 - 15 q^7
+    return 0.5 * (math.cos(math.pi * q) + 1.0)
+
+
+def _radial_norm_integral(sp, u: int) -> float:
+    """int_0^rc (r R_u(r))^2 dr of the spec's orbital u in float64 (reference: scipy.integrate.quad, rbf.py:122-126);
+    composite Gauss-Legendre on 64 panels x 16 points — the integrand is a polynomial times exp(-zeta) times a smooth
+    cutoff, so this agrees with quad to ~1e-14 relative."""
+    import numpy as np
+    n, l, rc, a0 = sp.n[u], sp.l[u], float(sp.rc), float(sp.a0)
+    xs, ws = np.polynomial.legendre.leggauss(16)
+    total = 0.0
+    edges = np.linspace(0.0, rc, 65)
+    for a, b in zip(edges[:-1], edges[1:]):
+        for x, w in zip(xs, ws):
+            r = 0.5 * (b - a) * x + 0.5 * (a + b)
+            zeta = 2.0 / n / a0 * r
+            poly = 0.0
+            for i in range(sp.deg[u], -1, -1):
+                poly = poly * zeta + sp.poly[u][i]
+            f = _cutoff_value(sp.cutoff_kind, r, rc) * sp.norm[u] * poly * zeta**l * math.exp(-0.5 * zeta)
+            total += 0.5 * (b - a) * w * (r * f) ** 2
+    return total
+
+
 class RadialBasis(nn.Module):
     """Hydrogen-like R_nl(r) x cutoff (reference nn/rbf.py:34-142; spherical-Bessel variant :145-182),
     described by an `lcao_basis_spec` that the geometry kernel evaluates."""
 
     def __init__(self, cutoff: float, elec_info: ElecInfo, cutoff_net: str, rbf_type: str = "hydrogen",
-                 bohr_radius: float = 0.529):
+                 bohr_radius: float = 0.529, integral_norm: bool = False):
         super().__init__()
         self.cutoff, self.elec_info, self.n_orb = cutoff, elec_info, elec_info.n_orb
         self.cutoff_net, self.rbf_type, self.bohr_radius = cutoff_net, rbf_type, bohr_radius
+        self.integral_norm = integral_norm
         nl = elec_info.nl_list[:: elec_info.n_per_orb].tolist()
         if len(nl) > _lib.MAX_UNIQUE_ORB:
             raise ValueError("too many orbitals")
@@ -462,6 +519,10 @@ class RadialBasis(nn.Module):
                                     / math.factorial(n + l) ** 3)
             for i, c in enumerate(coef):
                 sp.poly[u][i] = float(c)
+            if integral_norm and sp.rbf_kind == _lib.RBF["hydrogen"]:
+                # rbf.py:92-93,107-127: prefactor -2/(n a0), then scaled so that int_0^rc (r R(r))^2 dr = 1 (cutoff included)
+                sp.norm[u] = -2.0 / n / bohr_radius
+                sp.norm[u] = sp.norm[u] / (math.sqrt(_radial_norm_integral(sp, u)) + 1e-12)
         self.spec = sp
 
     def extra_repr(self) -> str:

@@ -96,8 +96,8 @@ def activation_code(act: nn.Module) -> int:
 
     if isinstance(act, nn.SiLU):
         return ACT["silu"]
-    if isinstance(act, Swish) and not act.train_beta and float(act.beta) == 1.0:
-        return ACT["silu"]
+    if isinstance(act, Swish):  # x sigmoid(beta x) = SiLU(beta x) / beta: the callers scale the layer around the kernel
+        return ACT["silu"]      # (`swish_beta`), so that beta stays an ordinary, trainable tensor
     if isinstance(act, ShiftedSoftplus) and abs(act.shift - math.log(2.0)) < 1e-12:
         return ACT["shiftedsoftplus"]
     if isinstance(act, nn.Softplus) and default(beta=1.0, threshold=20.0):
@@ -116,7 +116,15 @@ def activation_code(act: nn.Module) -> int:
         return ACT["leakyrelu"]
     raise NotImplementedError(f"activation {act!r}: the B200 kernels fuse SiLU (the reference default, lcaonet.py:345), "
                               "ShiftedSoftplus, Softplus, ReLU, Tanh, Sigmoid, GELU, ELU and LeakyReLU with default "
-                              "hyper-parameters; Swish only with a fixed beta = 1")
+                              "hyper-parameters, and Swish (trainable beta included)")
+
+
+def swish_beta(act: nn.Module):
+    """beta of a Swish activation (a 0-d tensor, possibly a Parameter), or None for every other activation.
+    Swish_beta(W x + b) = SiLU((beta W) x + beta b) / beta: a Dense layer followed by Swish is evaluated by the SiLU
+    kernels on beta-scaled weights, and the 1/beta goes into whatever consumes the result — beta enters only through
+    small torch ops on weights, so autograd delivers d loss / d beta without any kernel knowing about it."""
+    return act.beta if isinstance(act, Swish) else None
 
 
 def cutoff_kind(query) -> str:

@@ -198,9 +198,14 @@ _ACTIVATIONS = {"silu": F.silu, "shiftedsoftplus": lambda x: F.softplus(x) - mat
                 "leakyrelu": F.leaky_relu}
 
 
-def _act(cfg):
-    name = cfg.get("activation", "SiLU")
-    return _ACTIVATIONS[str(name).lower().replace("-", "").replace("_", "").replace(" ", "")]
+def _act(cfg, p=None):
+    name = str(cfg.get("activation", "SiLU")).lower().replace("-", "").replace("_", "").replace(" ", "")
+    if name == "swish":
+        # nn/activation.py:7-33: x sigmoid(beta x); the reference shares ONE Swish module (one trainable beta) between all
+        # its blocks, so every site uses the first `.beta` entry of the state dict (where its gradient accumulates)
+        beta = p[next(k for k in p if k.endswith(".beta"))]
+        return lambda x: x * torch.sigmoid(beta * x)
+    return _ACTIVATIONS[name]
 
 
 def _batch_norm(p, name, x, training: bool, new_stats: dict | None):
@@ -242,13 +247,13 @@ def embedding(p, cfg, z, idx_s, idx_t, training, new_stats=None):
     else:
         coeff_e = eemb
         enc_in = node_z
-    h = _act(cfg)(_lin(p, "emb_layer.node_embed.f_enc.0", enc_in))
-    h = _act(cfg)(_lin(p, "emb_layer.node_embed.f_enc.2", h))
+    h = _act(cfg, p)(_lin(p, "emb_layer.node_embed.f_enc.0", enc_in))
+    h = _act(cfg, p)(_lin(p, "emb_layer.node_embed.f_enc.2", h))
     x = _batch_norm(p, "emb_layer.node_embed.bn", h, training, new_stats)
 
     fz = _lin(p, "emb_layer.coeff_embed.f_z.0", torch.cat([coeff_z[idx_s], coeff_z[idx_t]], dim=-1))  # (E, K)
-    fe = _act(cfg)(_lin(p, "emb_layer.coeff_embed.f_e.0", coeff_e))
-    fe = _act(cfg)(_lin(p, "emb_layer.coeff_embed.f_e.2", fe))[idx_t]  # (E, n_orb, K): orbitals of the TARGET
+    fe = _act(cfg, p)(_lin(p, "emb_layer.coeff_embed.f_e.0", coeff_e))
+    fe = _act(cfg, p)(_lin(p, "emb_layer.coeff_embed.f_e.2", fe))[idx_t]  # (E, n_orb, K): orbitals of the TARGET
     pre = fe + fe * fz.unsqueeze(1)
     cst = _batch_norm(p, "emb_layer.coeff_embed.bn", pre.reshape(pre.shape[0], -1), training, new_stats)
     return x, cst.reshape(pre.shape)
@@ -262,8 +267,8 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
     x_in = x
     nw = _lin(p, pre + "node_weight", x)
     xc, xk = nw[:, :C], nw[:, C:]
-    c1 = _act(cfg)(_lin(p, pre + "f_coeffs.0", cst))
-    c1 = _act(cfg)(_lin(p, pre + "f_coeffs.2", c1))  # (E, O, C')
+    c1 = _act(cfg, p)(_lin(p, pre + "f_coeffs.0", cst))
+    c1 = _act(cfg, p)(_lin(p, pre + "f_coeffs.2", c1))  # (E, O, C')
     # three-body: gather the coefficient rows of the incoming edge (k->s) of every triplet
     w3 = rb[e_ks] * shb  # (T, O)
     if cfg["add_valence"]:
@@ -282,8 +287,8 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
     else:
         lw = torch.einsum("eo,eoc->ec", rb, c2)
     lw = F.normalize(lw, dim=-1)
-    h = _act(cfg)(_lin(p, pre + "f_node.0", torch.cat([xc[idx_s], xc[idx_t]], dim=-1)))
-    h = _act(cfg)(_lin(p, pre + "f_node.2", h))
+    h = _act(cfg, p)(_lin(p, pre + "f_node.0", torch.cat([xc[idx_s], xc[idx_t]], dim=-1)))
+    h = _act(cfg, p)(_lin(p, pre + "f_node.2", h))
     msg = _lin(p, pre + "basis_weight", lw) * h
     agg = _segment_sum(msg, idx_s, x.shape[0])  # edges -> source/centre nodes
     if trace is not None:
@@ -295,8 +300,8 @@ def interaction(p, pre, cfg, x, cst, vmask, rb, shb, idx_s, idx_t, tri_k, e_ks, 
 # output block + post-processing (reference: lcaonet.py:271-319, post.py:44-89)
 # --------------------------------------------------------------------------------------------
 def _mlp3(p, pre, x, cfg):
-    x = _act(cfg)(_lin(p, pre + ".0", x))
-    x = _act(cfg)(_lin(p, pre + ".2", x))
+    x = _act(cfg, p)(_lin(p, pre + ".0", x))
+    x = _act(cfg, p)(_lin(p, pre + ".2", x))
     return _lin(p, pre + ".4", x)
 
 

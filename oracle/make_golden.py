@@ -98,10 +98,38 @@ def basis_tables():
             rbf = HydrogenRadialBasis(rc, ei, cuts[cname](rc))
             out["rb"][(max_z, max_orb, npo, rc, cname)] = rbf(out["r"])
         out["shb"][(max_z, max_orb, npo)] = SphericalHarmonicsBasis(ei)(out["c"])
+    # integral_norm=True (rbf.py:107-127): coefficients from scipy quad at constructor time
+    out["rb_integral_norm"] = {}
+    for rc, cname in ((5.0, "polynomial"), (6.0, "envelope"), (3.0, "cosine")):
+        ei = RefElecInfo(36, None, None, 1)
+        with torch.no_grad():
+            out["rb_integral_norm"][(rc, cname)] = HydrogenRadialBasis(rc, ei, cuts[cname](rc), integral_norm=True)(out["r"])
     out["tables"] = {"ELEC_TABLE": ref_elec.ELEC_TABLE, "VALENCE_TABLE": ref_elec.VALENCE_TABLE,
                      "NL_LIST": ref_elec.NL_LIST, "MAX_ELEC_IDX": ref_elec.MAX_ELEC_IDX}
     torch.save(out, os.path.join(OUT, "basis_tables.pt"))
     print("basis_tables written")
+
+
+def scheduler_table():
+    """learning rates of the reference's WarmupCosineDecayAnnealingLR (train/scheduler.py) for two settings"""
+    import torch.optim.lr_scheduler as L
+    orig = L.LRScheduler.__init__
+    L.LRScheduler.__init__ = lambda self, optimizer, last_epoch=-1, verbose=None: orig(self, optimizer, last_epoch)  # torch >= 2.7 dropped `verbose`
+    from lcaonet.train.scheduler import WarmupCosineDecayAnnealingLR
+    out = []
+    for kw, lr0 in ((dict(num_epoch=60, num_warmup=5, T_max=7), 1e-5),
+                    (dict(num_epoch=40, num_warmup=3, T_max=4, eta_min=1e-6, lr_max=5e-4, decay_coef=2.0), 1e-4)):
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr0)
+        sch = WarmupCosineDecayAnnealingLR(opt, **kw)
+        lrs = []
+        for _ in range(kw["num_epoch"]):
+            opt.step()
+            sch.step()
+            lrs.append(opt.param_groups[0]["lr"])
+        out.append({"kwargs": kw, "lr0": lr0, "lrs": lrs})
+    L.LRScheduler.__init__ = orig
+    torch.save(out, os.path.join(OUT, "scheduler_lrs.pt"))
+    print("scheduler_lrs written")
 
 
 def main():
@@ -114,6 +142,8 @@ def main():
 
     if not only or "basis_tables" in only:
         basis_tables()
+    if not only or "scheduler_lrs" in only:
+        scheduler_table()
     qm9 = synth.qm9_like_batch(6, seed=3, cutoff=5.0, margin=0.05)
     xtl = synth.crystal_like_batch(1, seed=5, cutoff=6.0, margin=0.05)
     fix = synth.reference_fixture_graph()
@@ -148,6 +178,9 @@ def main():
     # configs[3]: periodic crystal cell (64 atoms, cutoff 6.0, ~49 neighbours/atom), energy + autograd forces at width 128
     run_case("cfg4_crystal_width128", dict(cutoff=6.0, cutoff_net="polynomial", regress_forces=True, direct_forces=False),
              xtl)
+    # Swish with its trainable beta (nn/activation.py:7-33): beta's own gradient is part of the golden
+    run_case("qm9_swish", dict(cutoff=5.0, cutoff_net="polynomial", activation="swish", regress_forces=True,
+                               direct_forces=True, add_valence=True, **small), qm9s)
     # spherical-Bessel radial basis (rbf.py:145-182)
     run_case("qm9_sphericalbessel", dict(cutoff=5.0, cutoff_net="polynomial", rbf_type="sphericalbessel", **small), qm9s)
 

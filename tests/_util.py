@@ -12,7 +12,7 @@ CTOR_DEFAULTS = dict(emb_size=128, emb_size_coeff=128, emb_size_conv=128, out_si
 
 CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_autograd_forces",
          "crystal_direct_forces_mean", "fixture_small", "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus",
-         "qm9_gelu_valence", "qm9_sphericalbessel", "cfg1_qm9_32mol", "cfg3_valence_width128", "cfg4_crystal_width128"]
+         "qm9_gelu_valence", "qm9_sphericalbessel", "qm9_swish", "cfg1_qm9_32mol", "cfg3_valence_width128", "cfg4_crystal_width128"]
 
 
 def load_golden(name):

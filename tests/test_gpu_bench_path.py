@@ -16,7 +16,7 @@ DEV = "cuda"
 # every training-mode golden; the first three are BASELINE.json configs[0] / [2] / [3] at width 128
 BENCH_PATH_CASES = ["cfg1_qm9_32mol", "cfg3_valence_width128", "cfg4_crystal_width128", "qm9_default", "qm9_valence_ext_2perorb",
                     "crystal_autograd_forces", "crystal_direct_forces_mean", "fixture_cosine_minmaxorb_atomref",
-                    "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel"]
+                    "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel", "qm9_swish"]
 
 
 def _bucket_grads(model, bucket):
@@ -125,3 +125,41 @@ def test_config2_batch_slice_against_the_fp64_oracle():
     worst = max(rel_l2(q.grad, p[n].grad) for n, q in model.named_parameters()
                 if p[n].grad is not None and float(p[n].grad.norm()) > 1e-8)
     assert worst < 1e-4, worst
+
+
+def test_device_collated_stream_feeds_fresh_batches():
+    """BASELINE.json configs[4] (stream): batches collated ON THE GPU from a resident pool (SamplePool.batch) and windows
+    streamed from the host (SamplePool.window + collate_window) are the batches the host loop would build — bit for bit —
+    and a training loop over fresh batches runs through the bench path (bucket, graphed tables) with the same energies
+    as the plain path."""
+    from lcaonet_b200.data import SamplePool, collate, collate_window, split
+    g = qm9_like_batch(24, seed=77, cutoff=5.0)
+    samples = split(g)
+    pool = SamplePool.from_batch(g)
+    pool_dev = pool.to(DEV)
+    torch.manual_seed(0)
+    kw = dict(cutoff=5.0, cutoff_net="polynomial", emb_size=64, emb_size_coeff=64, emb_size_conv=64)
+    m_plain, m_fast = LCAONet(**kw).to(DEV).train(), LCAONet(**kw).to(DEV).train()
+    m_fast.load_state_dict(m_plain.state_dict())
+    bucket = FlatGradBucket(m_fast)
+    gen = torch.Generator().manual_seed(5)
+    for step in range(3):
+        ids = torch.randperm(24, generator=gen)[:8]
+        want = collate([samples[i] for i in ids.tolist()])
+        got = pool_dev.batch(ids.to(DEV))
+        for k, v in want.items():
+            assert torch.equal(got[k].cpu(), v), k
+        lo = 4 * step
+        win = collate_window(pool.window(lo, lo + 8).to(DEV))
+        for k, v in collate(samples[lo:lo + 8]).items():
+            assert torch.equal(win[k].cpu(), v), k
+        bucket.zero()
+        m_plain.zero_grad(set_to_none=True)
+        e_fast = m_fast(got)
+        e_plain = m_plain(GraphBatch(want).to(DEV))
+        assert rel_l2(e_fast, e_plain) < 1e-6
+        torch.nn.functional.mse_loss(e_fast, got["y"]).backward()
+        torch.nn.functional.mse_loss(e_plain, want["y"].to(DEV)).backward()
+        for (n, p), q in zip(m_plain.named_parameters(), m_fast.parameters()):
+            if p.grad is not None and float(p.grad.norm()) > 0:
+                assert rel_l2(q.grad, p.grad) < 2e-5, (step, n)

@@ -15,7 +15,7 @@ from tests._util import full_cfg, graph_as, load_golden, rel_l2, same_triplets_u
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN_CASES = ["qm9_default", "qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
-                "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel",
+                "fixture_cosine_minmaxorb_atomref", "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel", "qm9_swish",
                 "cfg1_qm9_32mol", "cfg3_valence_width128"]
 
 
@@ -240,6 +240,18 @@ def test_edge_gathers_and_segment_sums_vs_restatement(monkeypatch):
     out_g, out_c, _ = _both(fn, monkeypatch, ei, u, x, y, bias, g["batch"])
     for a, b in zip(out_g, out_c):
         assert rel_l2(a, b) < 1e-5
+
+
+def test_integral_norm_radial_basis_on_gpu():
+    """HydrogenRadialBasis(integral_norm=True) (rbf.py:107-127) through the geometry kernel vs the reference's table"""
+    from lcaonet_b200.model import RadialBasis
+    from lcaonet_b200.orbitals import ElecInfo
+    tab = load_golden("basis_tables")
+    r = tab["r"][1:]  # (r = 0 is not a distance the geometry kernel sees)
+    for (rc, cname), want in tab["rb_integral_norm"].items():
+        rbf = RadialBasis(rc, ElecInfo(36, None, None, 1), cname, "hydrogen", integral_norm=True)
+        got = rbf(r.float().to(DEV))
+        assert rel_l2(got, want[1:]) < 2e-6, (rc, cname)
 
 
 # ---------------------------------------------------------------------------- end to end vs the reference

@@ -11,7 +11,7 @@ from tests._util import load_golden, rel_l2, same_triplets_up_to_duplicate_order
 
 CASES = ["qm9_default_eval", "qm9_valence_ext_2perorb", "crystal_direct_forces_mean",
          "fixture_cosine_minmaxorb_atomref", "qm9_default", "qm9_shiftedsoftplus", "qm9_gelu_valence", "qm9_sphericalbessel",
-         "cfg3_valence_width128"]
+         "cfg3_valence_width128", "qm9_swish"]
 
 
 def _run(name, monkeypatch):
@@ -126,11 +126,9 @@ def test_constructor_errors():
         LCAONet(weight_init="nope")
     with pytest.raises(ValueError):
         LCAONet(activation="nope")
-    with pytest.raises(NotImplementedError):  # trainable beta: not fused into the kernels
-        LCAONet(activation="swish")
     with pytest.raises(NotImplementedError):
         LCAONet(activation="PReLU")
-    for name in ("ReLU", "shifted_softplus", "Tanh", "gelu", "ELU", "leaky-relu", "softplus", "sigmoid", "SiLU"):
+    for name in ("swish", "ReLU", "shifted_softplus", "Tanh", "gelu", "ELU", "leaky-relu", "softplus", "sigmoid", "SiLU"):
         LCAONet(activation=name, emb_size=8, emb_size_coeff=8, emb_size_conv=8, n_interaction=1)
 
 
@@ -224,3 +222,32 @@ def test_grad_bucket_survives_zero_grad(monkeypatch):
     for n, p in model.named_parameters():
         if n in want:
             assert torch.equal(p.grad, want[n]), n
+
+
+def test_swish_beta_is_trained(monkeypatch):
+    """Swish's trainable beta (nn/activation.py:7-33) enters through beta-scaled effective weights around the SiLU kernels:
+    its gradient must match the reference's, on both interaction paths, and a non-unit beta must still give the
+    reference's function (checked against a plain torch evaluation of one Dense + Swish)."""
+    gold = load_golden("qm9_swish")
+    names = [n for n in gold["grads_f64"] if n.endswith(".beta")]
+    assert names, "the reference registers beta as a parameter"
+    for fused in (True, False):
+        cpu_abi.install(monkeypatch)
+        model = LCAONet(**gold["kwargs"])
+        model.load_state_dict(gold["state_dict"], strict=True)
+        for layer in model.int_layers:
+            layer.fused_node = fused
+        energy, forces = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+        ((energy**2).mean() + (forces**2).mean()).backward()
+        got = dict(model.named_parameters())
+        for n in names:
+            if n in got:  # (shared parameter: named_parameters lists it once)
+                assert rel_l2(got[n].grad, gold["grads_f64"][n]) < 2e-4, (fused, n)
+    from lcaonet_b200.model import Dense, _mlp
+    from lcaonet_b200.resolve import Swish
+    cpu_abi.install(monkeypatch)
+    torch.manual_seed(0)
+    seq = torch.nn.Sequential(Dense(8, 8, True), Swish(beta=0.7))
+    x = torch.randn(5, 8)
+    want = seq[1](torch.nn.functional.linear(x, seq[0].weight, seq[0].bias))
+    assert rel_l2(_mlp(seq, x), want) < 1e-6
