@@ -272,6 +272,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = LCAONet(**model_kw).to(dev).train()
     model.side_effect_keys = not args.no_side_effect_keys
+    model.out_layer.force_training = False  # (crystal workload: forces are evaluated, the loss is on the energy)
     broadcast_module(model)
     bucket = FlatGradBucket(model)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)

@@ -398,6 +398,9 @@ class LCAOOut(nn.Module):
         super().__init__()
         self.emb_size, self.out_size, self.is_extensive = emb_size, out_size, is_extensive
         self.regress_forces, self.direct_forces = regress_forces, direct_forces
+        # autograd forces: None = differentiable forces (double backward) in training mode, first-order kernels in eval
+        # mode; True / False force either.  False is the fast choice for a training loop whose loss is on the energy only.
+        self.force_training = None
         self.out_lin = nn.Sequential(Dense(emb_size, emb_size, True, weight_init), activation,
                                      Dense(emb_size, emb_size // 2, True, weight_init), activation,
                                      Dense(emb_size // 2, out_size, False, weight_init))
@@ -424,9 +427,16 @@ class LCAOOut(nn.Module):
                 a = a / beta
             f_st = self.out_lin_force[4](a) * unit  # (E, 3)
             return prop, ops.segment_reduce(f_st, gi.out_ptr, gi.out_edge, gi.src32, mean=False)
-        # d E / d pos only: the backward kernels skip every parameter gradient inside this pass (ops.positions_only)
+        # F = -dE/dpos (lcaonet.py:310-317).  The reference always builds the graph of this backward pass (create_graph=True)
+        # so that a loss on the forces can be trained; here that graph is what switches the operators from their fused
+        # backward kernels to the re-evaluated differentiable form (second_order.py), so it is built only when the forces can
+        # be trained on: in training mode, unless `force_training` says otherwise.  Only d E / d pos is wanted from this
+        # pass: the backward kernels skip every parameter gradient inside it (ops.positions_only).
+        graph = self.training if self.force_training is None else bool(self.force_training)
+        graph = graph and torch.is_grad_enabled()
         with ops.positions_only():
-            cols = [-torch.autograd.grad(prop[:, i].sum(), pos, create_graph=True)[0] for i in range(self.out_size)]
+            cols = [-torch.autograd.grad(prop[:, i].sum(), pos, create_graph=graph, retain_graph=True)[0]
+                    for i in range(self.out_size)]
         return prop, (cols[0] if len(cols) == 1 else torch.stack(cols, dim=1).squeeze(1))
 
 

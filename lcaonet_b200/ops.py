@@ -13,7 +13,7 @@ import torch
 from torch import Tensor
 from torch.autograd.function import once_differentiable
 
-from . import _lib
+from . import _lib, second_order
 from ._lib import ACT_NONE, ACT_SILU, LcaoError, call, ptr, require_cuda, stream_ptr
 
 # GEMM arithmetic mode for the dense layers: fp32 CUDA cores, 3xTF32 tcgen05 (fp32-equivalent), 1xTF32
@@ -173,17 +173,22 @@ class _GeomBasis(torch.autograd.Function):
         drb = torch.empty(E, n_orb, device=dev) if need_grad else None
         _call("lcao_geom_basis_fwd", ptr(pos_c), ptr(shift_c), ptr(lat_c), ptr(batch), ptr(gi.src32), ptr(gi.dst32), E,
               ctypes.byref(spec), ptr(dist), ptr(unit), ptr(rb), ptr(drb), stream_ptr())
-        ctx.gi, ctx.n_orb = gi, n_orb
-        ctx.save_for_backward(dist, unit, drb)
+        ctx.gi, ctx.n_orb, ctx.spec = gi, n_orb, spec
+        ctx.save_for_backward(dist, unit, drb, pos, shift, lattice, batch)
         return dist, unit, rb
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, d_dist, d_unit, d_rb):
-        dist, unit, drb = ctx.saved_tensors
+        dist, unit, drb, pos, shift, lattice, batch = ctx.saved_tensors
         gi = ctx.gi
         if drb is None:
             return (None,) * 7
+        if torch.is_grad_enabled():  # create_graph=True: this backward is itself differentiated (training on autograd forces)
+            with torch.enable_grad():
+                (pos_,) = second_order.aliases([pos])
+                outs = second_order.geom_basis(pos_, shift, lattice, batch, gi.src32, gi.dst32, ctx.spec, ctx.n_orb)
+                (d_pos,) = second_order.grads_with_graph(outs, [pos_], [d_dist, d_unit, d_rb], [True])
+            return d_pos, None, None, None, None, None, None
         dev = dist.device
         dvec = torch.empty(gi.E, 3, device=dev)
         d_pos = torch.empty(gi.N, 3, device=dev)
@@ -216,13 +221,21 @@ class _Linear(torch.autograd.Function):
         _call("lcao_linear_fwd", ptr(x2), _ld(x2), ptr(w), ptr(bias), ptr(y), Nout, ptr(pre), Nout, M, K, Nout, act,
               _gemm_mode, stream_ptr())
         ctx.act, ctx.shape, ctx.has_bias = act, shape, bias is not None
-        ctx.save_for_backward(x2, w, pre)
+        ctx.save_for_backward(x2, w, pre, x, weight, bias)
         return y.reshape(*shape[:-1], Nout)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
-        x2, w, pre = ctx.saved_tensors
+        x2, w, pre, x_in, w_in, b_in = ctx.saved_tensors
+        if torch.is_grad_enabled():  # create_graph=True (see second_order.py)
+            with torch.enable_grad():
+                ins = second_order.aliases([x_in, w_in, b_in])
+                y = second_order.linear(*ins, ctx.act)
+                wanted = list(ctx.needs_input_grad[:3])
+                if positions_only.active:
+                    wanted[1] = wanted[2] = False
+                gx, gw, gb = second_order.grads_with_graph([y], ins, [dy], wanted)
+            return gx, gw, gb, None
         M, K, Nout = x2.shape[0], x2.shape[1], w.shape[0]
         dy2 = _rows(dy)
         st = stream_ptr()
@@ -563,15 +576,26 @@ class _InteractionLayer(torch.autograd.Function):
         if grad:
             ctx.aux = aux
             ctx.save_for_backward(x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2,
-                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, pre_h, agg, psum)
+                                  B, gram, gate, tbw, g, lw, bw, a1, pre_a, pre_h, agg, psum, b_n, w_1, b_1, b_2)
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, d_out):
         (x, table, rb, unit, w_n, w_c0, w_c2, w_3, w_b, w_1cat, w_2, w_o, nw, t1, pre1, tab, pre2, B, gram, gate, tbw, g,
-         lw, bw, a1, pre_a, pre_h, agg, psum) = ctx.saved_tensors
+         lw, bw, a1, pre_a, pre_h, agg, psum, b_n, w_1, b_1, b_2) = ctx.saved_tensors
         pair, grouping, vmask, lgrp, gi, NL, C, sinks, act = ctx.aux
+        if torch.is_grad_enabled():
+            # create_graph=True: this backward pass is itself being differentiated (training on autograd forces,
+            # lcaonet.py:310-317).  The operator is re-evaluated in its any-order differentiable form (second_order.py) on
+            # the saved INPUTS, and autograd returns their gradients together with the graph behind them.
+            inputs = second_order.aliases([x, table, rb, unit, w_n, b_n, w_c0, w_c2, w_3, w_b, w_1, b_1, w_2, b_2, w_o])
+            wanted = list(ctx.needs_input_grad[:15])
+            if positions_only.active:  # only the path to the positions: x, rb, unit
+                wanted = [wanted[0], False, wanted[2], wanted[3]] + [False] * 11
+            with torch.enable_grad():
+                out = second_order.interaction(*inputs, pair, vmask, lgrp, gi, NL, C, act)
+                grads = second_order.grads_with_graph([out], inputs, [d_out], wanted)
+            return (*grads, None)
         # `positions_only` (autograd forces): no parameter gradient is wanted from this pass, and the sinks are not its to write
         wg = not positions_only.active
         if not wg:
@@ -809,13 +833,18 @@ class _SegmentReduce(torch.autograd.Function):
         _call("lcao_segment_sum", ptr(x2), _ld(x2), None, 0, ptr(seg_ptr), ptr(seg_perm), R, C, 1 if mean else 0,
               ptr(out), C, stream_ptr())
         ctx.mean, ctx.n = mean, x2.shape[0]
-        ctx.save_for_backward(seg_ptr, seg_of_item)
+        ctx.save_for_backward(seg_ptr, seg_of_item, x)
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, d_out):
-        seg_ptr, seg_of_item = ctx.saved_tensors
+        seg_ptr, seg_of_item, x_in = ctx.saved_tensors
+        if torch.is_grad_enabled():  # create_graph=True (see second_order.py)
+            with torch.enable_grad():
+                (x_,) = second_order.aliases([x_in])
+                out = second_order.segment_reduce(x_, seg_of_item, seg_ptr.numel() - 1, ctx.mean)
+                (gx,) = second_order.grads_with_graph([out], [x_], [d_out], [True])
+            return gx, None, None, None, None
         d_out = d_out.contiguous()
         if ctx.mean:
             cnt = (seg_ptr[1:] - seg_ptr[:-1]).clamp(min=1).to(d_out.dtype)

@@ -162,7 +162,9 @@ def test_grad_bucket_with_autograd_forces_equals_plain_path(monkeypatch):
             (energy**2).mean().backward()
         res.append((energy.detach(), forces.detach(), _grads(model)))
     (e0, f0, g0), (e1, f1, g1) = res
-    assert rel_l2(e1, e0) < 1e-6 and rel_l2(f1, f0) < 1e-6 and g0.keys() == g1.keys()
+    # (training mode: the forces come from the re-evaluated differentiable operators, whose CPU scatter-adds are not
+    # run-to-run reproducible to the last bit)
+    assert rel_l2(e1, e0) < 1e-6 and rel_l2(f1, f0) < 1e-5 and g0.keys() == g1.keys()
     for n in g0:
         assert rel_l2(g1[n], g0[n]) < 1e-5, n
     worst = max(rel_l2(g1[n], gold["grads_energy_f64"][n]) for n in g1 if float(gold["grads_energy_f64"][n].norm()) > 0)
@@ -251,3 +253,51 @@ def test_swish_beta_is_trained(monkeypatch):
     x = torch.randn(5, 8)
     want = seq[1](torch.nn.functional.linear(x, seq[0].weight, seq[0].bias))
     assert rel_l2(_mlp(seq, x), want) < 1e-6
+
+
+# ---- double backward: training ON autograd forces ----------------------------------------------------
+@pytest.mark.parametrize("bucket", [False, True])
+def test_force_loss_gradients_match_reference(bucket, monkeypatch):
+    """loss = mean(E^2) + mean(F^2) with F = -dE/dpos (create_graph=True, lcaonet.py:310-317): the gradient w.r.t. every
+    parameter needs the backward pass of each operator on the pos -> E path to be differentiable; golden = the
+    reference's own FP64 gradients of the same loss."""
+    from lcaonet_b200.dist import FlatGradBucket
+    gold, model, g, _ = _run("crystal_autograd_forces", monkeypatch)
+    b = FlatGradBucket(model) if bucket else None
+    for _ in range(2 if bucket else 1):
+        if b is not None:
+            b.zero()
+        energy, forces = model(GraphBatch({k: v.clone() for k, v in gold["graph"].items()}))
+        assert forces.requires_grad
+        assert rel_l2(energy, gold["energy_f64"]) < 1e-5 and rel_l2(forces, gold["forces_f64"]) < 2e-5
+        ((energy**2).mean() + (forces**2).mean()).backward()
+    worst, who = 0.0, None
+    for n, p in model.named_parameters():
+        ref = gold["grads_f64"][n]
+        if ref is None or float(ref.norm()) == 0.0:
+            continue
+        err = rel_l2(p.grad, ref)
+        if err > worst:
+            worst, who = err, n
+    assert worst < 3e-4, (who, worst)
+
+
+def test_training_on_forces_reduces_the_loss(monkeypatch):
+    """the reference's own trainability test (tests/model/test_lcaonet.py:219-233): 0.001 E-loss + 0.999 F-loss, Adam,
+    on the 3-atom periodic fixture; the loss must fall below 2"""
+    from lcaonet_b200.synth import reference_fixture_graph
+    cpu_abi.install(monkeypatch)
+    torch.manual_seed(0)
+    model = LCAONet(emb_size=16, emb_size_coeff=16, emb_size_conv=16, out_size=1, n_interaction=2, cutoff=2.0,
+                    cutoff_net="envelope", max_z=5, regress_forces=True, direct_forces=False)
+    opt = torch.optim.Adam(model.parameters(), lr=0.001)
+    g0 = reference_fixture_graph()
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        energy, forces = model(GraphBatch({k: v.clone() for k, v in g0.items()}))
+        loss = 0.001 * torch.nn.functional.mse_loss(energy, torch.ones(1, 1)) + 0.999 * torch.nn.functional.mse_loss(forces, torch.ones(3, 3))
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert min(losses) < 2 and losses[-1] < losses[0]
