@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "liblcao_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["abi.cu", "graph_index.cu", "neighbor.cu", "geom_basis.cu", "edge_ops.cu", "pair_table.cu", "table_norm.cu", "threebody.cu", "threebody_mma.cu", "gemm_simt.cu", "gemm_tc.cu",
+SOURCES = ["abi.cu", "graph_index.cu", "neighbor.cu", "geom_basis.cu", "edge_ops.cu", "pair_table.cu", "table_norm.cu", "threebody.cu", "threebody_mma.cu", "threebody_staged.cu", "gemm_simt.cu", "gemm_tc.cu",
            "linear.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + HERE]

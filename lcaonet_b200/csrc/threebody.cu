@@ -501,6 +501,11 @@ int tile_in(const char* env, int dflt, int lo, int hi) {
 int lcao_tb_mma_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
                     const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
                     const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, float* tbw, cudaStream_t st);
+// staged backward (threebody_staged.cu): bulk-copy staging + producer warp, the default backward for C <= 128
+int lcao_tb_staged_bwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
+                       const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
+                       const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, const float* d_tbw, const float* dP,
+                       float* dB, float* q, float* du_ks, float* du_st, cudaStream_t st);
 // LCAO_TB_IMPL=simt forces the FP32-pipe forward kernel of this file (A/B measurements); it also serves C > 128 and
 // buffers that are not 16-byte aligned (the bulk copies need that)
 static bool use_mma(int C, const void* B, const void* gate, int64_t ldg) {
@@ -557,6 +562,9 @@ extern "C" int lcao_threebody_bwd(const float* B, int32_t NG, const double* gram
   LCAO_REQUIRE(NG <= NL + 1, "lcao_threebody_bwd: at most one valence group (NG <= NL + 1)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool forces = d_unit_ks != nullptr;
+  if (use_mma(C, B, gate, ldg) && (reinterpret_cast<uintptr_t>(d_tbw) & 15u) == 0)
+    return lcao_tb_staged_bwd(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, N, C, NL, d_tbw, dP, dB,
+                              q, d_unit_ks, d_unit_st, st);
   const int V4 = C <= 128 ? 1 : 2;
   const bool full = C == 128 * V4;
   static const int per_sm_b = tile_in("LCAO_TB_GRID_BWD", 24, 1, 64);

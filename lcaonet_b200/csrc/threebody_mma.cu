@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "tb_common.cuh"
+#include "tb_async.cuh"
 
 namespace {
 
@@ -54,40 +55,6 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
   mma_tf32(d, ah, bh0, bh1);
 }
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-
-// ---------------------------------------------------------------------------------------------
-// per-warp shared-memory staging by bulk asynchronous copies (TMA unit, cp.async.bulk) completed on an mbarrier.
-// The FP32-pipe kernels and the first tensor-core version loaded their rows with per-thread LDGs and were bound by the
-// latency of each warp's dependent chain at ~12 resident warps (long-scoreboard stalls, 25 % of the DRAM bandwidth):
-// a warp here puts ALL rows of its node (tens of KB) in flight with two copy instructions per in-edge and then computes
-// out of shared memory; the resident warps of an SM are out of phase, so their loads overlap the others' MMAs.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();  // (bounded: a lost copy must not hang the GPU)
-  }
-}
-__device__ __forceinline__ float4 lds4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 constexpr int kIB = 8;      // in-edges per forward stage = one K-block of the MMAs
 constexpr int kStages = 3;  // forward ring depth: two items in flight behind the one being multiplied
@@ -126,9 +93,6 @@ enum { kItemFirst = 1, kItemLast = 2, kItemEnd = 4 };
 // sit in the producer's registers.  The 128 coefficients of an item are computed one per consumer thread and exchanged
 // through shared memory in fragment order (one named barrier among the consumers per item).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NL>
