@@ -1,5 +1,6 @@
 // Error reporting and version for the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,11 @@ void lcao_set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_lcao_launches = 0;
+
+bool lcao_pdl_enabled() {
+  static const bool on = [] { const char* s = getenv("LCAO_PDL"); return !(s && s[0] == '0'); }();
+  return on;
+}
 
 extern "C" int lcao_version(void) { return 100; }
 extern "C" int64_t lcao_launch_count(void) { return (int64_t)g_lcao_launches; }

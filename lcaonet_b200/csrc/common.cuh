@@ -32,6 +32,29 @@ extern unsigned long long g_lcao_launches;  // kernels launched by this library 
     LCAO_CUDA(cudaGetLastError()); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may begin — block scheduling, barrier /
+// TMEM set-up, the split of its resident weights — while the kernel before it in the stream is still draining, once every
+// CTA of that kernel has executed pdl_trigger() (or exited).  It must call pdl_wait() before it touches anything the
+// stream's earlier work produces or still reads; pdl_wait() returns when ALL earlier grids have completed and flushed.
+// Kernels without the launch attribute, and predecessors that never trigger (torch's kernels, memsets), behave as usual.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool lcao_pdl_enabled();  // abi.cu: LCAO_PDL=0 switches the launch attribute off
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lcao_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float warp_sum(float v) {

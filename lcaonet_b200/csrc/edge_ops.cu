@@ -120,6 +120,8 @@ template <bool VAL, int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_fwd(const float* __restrict__ B, int NG,
                                                                    const float* __restrict__ g, int64_t E, int C,
                                                                    int NL, float* __restrict__ lw) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_twobody_bwd(const float* 
                                                                    const float* __restrict__ d_lw, int64_t E, int C,
                                                                    int NL, int compact, float* __restrict__ dB,
                                                                    float* __restrict__ d_g) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_edge_pair_fwd(
     const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, const float* __restrict__ bias,
     const int32_t* __restrict__ src32, const int32_t* __restrict__ dst32, int64_t E, int C, int act,
     float* __restrict__ out, float* __restrict__ pre) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
@@ -230,6 +236,8 @@ template <bool VEC, bool GEN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_segment_sum(
     const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ ptr,
     const int32_t* __restrict__ perm, int64_t R, int C, int mean, float* __restrict__ out, int64_t ldo) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t r = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -272,6 +280,7 @@ template <typename IdxT, bool VEC>
 __global__ void k_gather_rows(const float* __restrict__ table, int64_t ldt, const IdxT* __restrict__ idx,
                               const float* __restrict__ mul, int64_t ldm, int64_t n, int W, float* __restrict__ out,
                               int64_t ldo) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   const int WV = VEC ? W / 4 : W;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n * WV) return;
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(256) k_reduce_by_key(const float* __restrict__
 
 // Y = act(X) elementwise (the activations the tcgen05 epilogue does not fuse); X may alias Y
 __global__ void k_act_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t M, int C4, int act) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= M * C4) return;
   const int64_t i = t / C4;
@@ -332,6 +342,8 @@ __global__ void k_act_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, in
 template <bool GEN>
 __global__ void k_act_bwd(const float* __restrict__ dY, int64_t ldy, const float* __restrict__ H, int64_t ldh,
                           float* __restrict__ dH, int64_t ldd, int64_t M, int C4, int act) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= M * C4) return;
   const int64_t i = t / C4;
@@ -348,6 +360,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
     const float* __restrict__ d_agg, int64_t lda, const int32_t* __restrict__ src32, const float* __restrict__ h,
     const float* __restrict__ bw, const float* __restrict__ pre_h, int64_t E, int C, int act, float* __restrict__ d_bw,
     float* __restrict__ d_pre_h) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t e = blockIdx.x * (int64_t)kWarpsPerCta + (threadIdx.x >> 5);
   if (e >= E) return;
   const int lane = threadIdx.x & 31;
@@ -363,6 +377,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_msg_bwd(
 
 __global__ void k_sigmoid_rows(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int64_t M,
                                int C4) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= M * C4) return;
   const int64_t i = t / C4;
@@ -433,11 +449,11 @@ extern "C" int lcao_twobody_fwd(const float* B, int32_t NG, const float* g, int6
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 128) {
-    if (valence) k_twobody_fwd<true, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
-    else k_twobody_fwd<false, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+    if (valence) LCAO_CUDA(launch_pdl(k_twobody_fwd<true, 1>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, E, C, NL, lw));
+    else LCAO_CUDA(launch_pdl(k_twobody_fwd<false, 1>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, E, C, NL, lw));
   } else {
-    if (valence) k_twobody_fwd<true, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
-    else k_twobody_fwd<false, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, E, C, NL, lw);
+    if (valence) LCAO_CUDA(launch_pdl(k_twobody_fwd<true, 2>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, E, C, NL, lw));
+    else LCAO_CUDA(launch_pdl(k_twobody_fwd<false, 2>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, E, C, NL, lw));
   }
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
@@ -452,11 +468,11 @@ extern "C" int lcao_twobody_bwd(const float* B, int32_t NG, const float* g, cons
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 128) {
-    if (valence) k_twobody_bwd<true, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
-    else k_twobody_bwd<false, 1><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+    if (valence) LCAO_CUDA(launch_pdl(k_twobody_bwd<true, 1>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, d_lw, E, C, NL, compact, dB, d_g));
+    else LCAO_CUDA(launch_pdl(k_twobody_bwd<false, 1>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, d_lw, E, C, NL, compact, dB, d_g));
   } else {
-    if (valence) k_twobody_bwd<true, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
-    else k_twobody_bwd<false, 2><<<grid, kWarpsPerCta * 32, 0, st>>>(B, NG, g, d_lw, E, C, NL, compact, dB, d_g);
+    if (valence) LCAO_CUDA(launch_pdl(k_twobody_bwd<true, 2>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, d_lw, E, C, NL, compact, dB, d_g));
+    else LCAO_CUDA(launch_pdl(k_twobody_bwd<false, 2>, grid, kWarpsPerCta * 32, 0, st, B, NG, g, d_lw, E, C, NL, compact, dB, d_g));
   }
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
@@ -470,11 +486,11 @@ extern "C" int lcao_edge_pair_fwd(const float* a, int64_t lda, const float* b, i
   LCAO_REQUIRE(C % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(out),
                "lcao_edge_pair_fwd: need C, lda, ldb multiples of 4 and 16-byte aligned buffers");
   if (act == LCAO_ACT_NONE || act == LCAO_ACT_SILU)
-    k_edge_pair_fwd<false><<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre);
+    LCAO_CUDA(launch_pdl(k_edge_pair_fwd<false>, (unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream, 
+        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre));
   else
-    k_edge_pair_fwd<true><<<(unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre);
+    LCAO_CUDA(launch_pdl(k_edge_pair_fwd<true>, (unsigned)ceil_div64(E, kWarpsPerCta), kWarpsPerCta * 32, 0, (cudaStream_t)stream, 
+        a, lda, b, ldb, bias, src32, dst32, E, C, act, out, pre));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -492,9 +508,9 @@ extern "C" int lcao_segment_sum(const float* x, int64_t ldx, const float* y, int
   const int kind = (mean >> 4) & 15;
   LCAO_REQUIRE(kind <= LCAO_ACT_LAST, "lcao_segment_sum: unsupported activation %d", kind);
   const bool gen = (mean & 6) != 0 && kind > LCAO_ACT_SILU;  // only the non-default activations take the generic kernel
-  if (vec && !gen) k_segment_sum<true, false><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
-  else if (vec) k_segment_sum<true, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
-  else k_segment_sum<false, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo);
+  if (vec && !gen) LCAO_CUDA(launch_pdl(k_segment_sum<true, false>, grid, kWarpsPerCta * 32, 0, st, x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo));
+  else if (vec) LCAO_CUDA(launch_pdl(k_segment_sum<true, true>, grid, kWarpsPerCta * 32, 0, st, x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo));
+  else LCAO_CUDA(launch_pdl(k_segment_sum<false, true>, grid, kWarpsPerCta * 32, 0, st, x, ldx, y, ldy, ptr, perm, R, C, mean, out, ldo));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -536,8 +552,8 @@ extern "C" int lcao_act_bwd(const float* dY, int64_t ldy, const float* H, int64_
   LCAO_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && ldd % 4 == 0 && (act == LCAO_ACT_NONE || ldh % 4 == 0),
                "lcao_act_bwd: need C and strides multiples of 4");
   const unsigned grid = (unsigned)ceil_div64(M * (C / 4), 256);
-  if (act <= LCAO_ACT_SILU) k_act_bwd<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
-  else k_act_bwd<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, ldy, H, ldh, dH, ldd, M, C / 4, act);
+  if (act <= LCAO_ACT_SILU) LCAO_CUDA(launch_pdl(k_act_bwd<false>, grid, 256, 0, (cudaStream_t)stream, dY, ldy, H, ldh, dH, ldd, M, C / 4, act));
+  else LCAO_CUDA(launch_pdl(k_act_bwd<true>, grid, 256, 0, (cudaStream_t)stream, dY, ldy, H, ldh, dH, ldd, M, C / 4, act));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -558,7 +574,7 @@ extern "C" int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_
   LCAO_REQUIRE(x && out, "lcao_sigmoid_rows: null buffer");
   LCAO_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out),
                "lcao_sigmoid_rows: need C and strides multiples of 4, 16-byte aligned buffers");
-  k_sigmoid_rows<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, M, C / 4);
+  LCAO_CUDA(launch_pdl(k_sigmoid_rows, (unsigned)ceil_div64(M * (C / 4), 256), 256, 0, (cudaStream_t)stream, x, ldx, out, ldo, M, C / 4));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -574,9 +590,9 @@ extern "C" int lcao_msg_bwd(const float* d_agg, int64_t lda, const int32_t* src3
   LCAO_REQUIRE(act > LCAO_ACT_NONE && act <= LCAO_ACT_LAST, "lcao_msg_bwd: unsupported activation %d", act);
   const unsigned grid = (unsigned)ceil_div64(E, kWarpsPerCta);
   if (act == LCAO_ACT_SILU)
-    k_msg_bwd<false><<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h);
+    LCAO_CUDA(launch_pdl(k_msg_bwd<false>, grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream, d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h));
   else
-    k_msg_bwd<true><<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h);
+    LCAO_CUDA(launch_pdl(k_msg_bwd<true>, grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream, d_agg, lda, src32, h, bw, pre_h, E, C, act, d_bw, d_pre_h));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -201,6 +201,7 @@ template <bool RP, bool EPI8>
 __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k_tc_rows(const RowsArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (g.debug & 32) return;  // (ablation: launch cost only)
+  pdl_trigger();  // the next kernel of the stream may start its own set-up while this one runs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t blockB = g.Nb * 128;                 // bytes of one 32-k column block of the weight
   const uint32_t halfB = (g.Kc / kChunkK) * blockB;   // bytes of one of {W_hi, W_lo}
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
     }
   };
   if (is_prod) {
+    pdl_wait();
     const int64_t my_tiles = nblocks > (int64_t)blockIdx.x ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     rp_total = (uint32_t)(my_tiles * nchunk);
     issue_load(rbuf[0]);
@@ -281,16 +283,17 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
   }
 
   // ---- resident B operand (the layer's weight), split hi/lo once per CTA by the 9 non-loader warps while the
-  //      loader warps already stream the first A stages; 4 loads in flight per thread (the weights come from L2 /
+  //      loader warps already stream the first A stages; kWB loads in flight per thread (the weights come from L2 /
   //      HBM with ~1 us latency: a dependent loop would cost ~10 us per launch)
   constexpr int kStageThreads = (4 + 4 + 1) * 32;  // 288
+  constexpr int kWB = 8;  // weight loads in flight per thread (64 KB of weights = 14 float4 per thread: two round trips to L2)
   if (warp < 9) {
     const int kq = g.Kc / 4, total = g.Nb * kq;
-    for (int base = 0; base < total; base += 4 * kStageThreads) {
-      float4 w[4];
-      int n[4], kg[4];
+    for (int base = 0; base < total; base += kWB * kStageThreads) {
+      float4 w[kWB];
+      int n[kWB], kg[kWB];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kWB; ++u) {
         const int idx = base + u * kStageThreads + (int)threadIdx.x;
         w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         n[u] = -1;
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kWB; ++u) {
         if (n[u] >= 0) {
           float4 hi, lo;
           split4(w[u], hi, lo);
@@ -320,6 +323,9 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
     asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");  // weights complete (non-loader warps only)
   }
 
+  // Everything above (barriers, TMEM, the split of the resident weight: parameters, never written by a kernel that triggers
+  // early) may overlap the tail of the previous kernel (programmatic dependent launch); the activations may not.
+  pdl_wait();
   if (is_prod) {
     // ============================== producers: registers -> hi / lo stages ==============================
     uint32_t it = 0;
@@ -586,6 +592,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // (set-up above overlaps the previous kernel's tail)
   if (c_beg >= c_end) {  // more CTAs than row chunks: nothing to do but to zero this CTA's partial slot
     for (int i = threadIdx.x; i < g.Kx * 128; i += kRowsThreads) g.part[(size_t)blockIdx.x * g.Kx * 128 + i] = 0.f;
     if (g.db && threadIdx.x < 128) g.part[(size_t)gridDim.x * g.Kx * 128 + (size_t)blockIdx.x * 128 + threadIdx.x] = 0.f;
@@ -771,6 +779,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
 __global__ void __launch_bounds__(1024) k_wgrad_reduce(const float* __restrict__ part, int ncta, int Kx, float* __restrict__ dW,
                                                        int64_t ldw, float* __restrict__ db) {
   __shared__ float s_p[8][128];
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x, n = threadIdx.x & 127, ty = threadIdx.x >> 7;
   const bool bias_row = j >= Kx;
   const float* src = bias_row ? part + (size_t)ncta * Kx * 128 + n : part + (size_t)j * 128 + n;
@@ -852,9 +862,9 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   // path, 20.5 -> 18.4 us); with many tiles per CTA the drain overlaps the next tile's MMAs and they do not (85 -> 88 us)
   static const int epi8_env = getenv("LCAO_TC_EPI8") ? atoi(getenv("LCAO_TC_EPI8")) : -1;
   const bool epi8 = epi8_env >= 0 ? epi8_env != 0 : nblocks <= num_sms();
-  if (rp) k_tc_rows<true, false><<<grid, kRowsThreads, smem, st>>>(g);
-  else if (epi8) k_tc_rows<false, true><<<grid, kRowsThreads + 128, smem, st>>>(g);
-  else k_tc_rows<false, false><<<grid, kRowsThreads, smem, st>>>(g);
+  if (rp) LCAO_CUDA(launch_pdl(k_tc_rows<true, false>, grid, kRowsThreads, smem, st, g));
+  else if (epi8) LCAO_CUDA(launch_pdl(k_tc_rows<false, true>, grid, kRowsThreads + 128, smem, st, g));
+  else LCAO_CUDA(launch_pdl(k_tc_rows<false, false>, grid, kRowsThreads, smem, st, g));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }
@@ -894,9 +904,9 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
     attr_set = true;
   }
   const unsigned grid = wgrad_grid(M);
-  k_tc_wgrad<<<grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st>>>(g);
+  LCAO_CUDA(launch_pdl(k_tc_wgrad, grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st, g));
   LCAO_LAUNCH_CHECK();
-  k_wgrad_reduce<<<Kx + (db ? 1 : 0), 1024, 0, st>>>(part, (int)grid, Kx, dW, ldw, db);
+  LCAO_CUDA(launch_pdl(k_wgrad_reduce, Kx + (db ? 1 : 0), 1024, 0, st, (const float*)part, (int)grid, Kx, dW, ldw, db));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_pair_contract_fwd(
     const float* __restrict__ tab, const int64_t* __restrict__ pair, const float* __restrict__ rb,
     const float* __restrict__ vmask, const int32_t* __restrict__ lgrp, int64_t E, int O, int C, float* __restrict__ B,
     double* __restrict__ gram, float* __restrict__ psum) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   __shared__ int s_l[LCAO_MAX_ORB];
   if (threadIdx.x < O) s_l[threadIdx.x] = lgrp[threadIdx.x];
   __syncthreads();
@@ -299,6 +301,8 @@ __global__ void __launch_bounds__(256) k_pair_reduce_partial(
     const int32_t* __restrict__ kptr, const int32_t* __restrict__ kperm, const int32_t* __restrict__ cptr, int P,
     const float* __restrict__ rb, const float* __restrict__ vmask, const int32_t* __restrict__ lgrp,
     const float* __restrict__ dB, int O, int C, int NL, float* __restrict__ partial) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_e = reinterpret_cast<int32_t*>(smem_raw);            // kChunk
   float* s_r = reinterpret_cast<float*>(s_e + kChunk);            // O x kChunk   rb[e,o]
@@ -363,6 +367,8 @@ __global__ void __launch_bounds__(256) k_pair_reduce_partial(
 __global__ void __launch_bounds__(256) k_pair_reduce_final(const int32_t* __restrict__ cptr, int P, int W4,
                                                            const float* __restrict__ partial,
                                                            float* __restrict__ d_tab) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
+  pdl_wait();     // launched through launch_pdl: nothing of the stream's earlier work is touched before this
   __shared__ float4 s_part[8][32];
   const int key = blockIdx.x, col = blockIdx.y * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
   const int32_t q0 = cptr[key], q1 = cptr[key + 1];
@@ -393,7 +399,7 @@ extern "C" int lcao_pair_contract_fwd(const float* tab, const int64_t* pair, con
   const int64_t want = ceil_div64(E, kWarps);
   const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
-#define PC_CALL(nl, val) k_pair_contract_fwd<nl, val><<<grid, kWarps * 32, 0, st>>>(tab, pair, rb, vmask, lgrp, E, O, C, B, gram, psum)
+#define PC_CALL(nl, val) LCAO_CUDA(launch_pdl(k_pair_contract_fwd<nl, val>, grid, kWarps * 32, 0, st, tab, pair, rb, vmask, lgrp, E, O, C, B, gram, psum))
   if (valence) {
     switch (NL) { case 1: PC_CALL(1, true); break; case 2: PC_CALL(2, true); break; case 3: PC_CALL(3, true); break; default: PC_CALL(4, true); }
   } else {
@@ -449,12 +455,12 @@ extern "C" int lcao_pair_contract_bwd(const float* tab, const int64_t* pair, con
       LCAO_CUDA(cudaFuncSetAttribute(valence ? k_pair_reduce_partial<true> : k_pair_reduce_partial<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (valence) k_pair_reduce_partial<true><<<(unsigned)chunks, 256, smem, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
-    else k_pair_reduce_partial<false><<<(unsigned)chunks, 256, smem, st>>>(kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial);
+    if (valence) LCAO_CUDA(launch_pdl(k_pair_reduce_partial<true>, (unsigned)chunks, 256, smem, st, kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial));
+    else LCAO_CUDA(launch_pdl(k_pair_reduce_partial<false>, (unsigned)chunks, 256, smem, st, kptr, kperm, cptr, (int)P, rb, vmask, lgrp, dB, O, C, NL, partial));
     LCAO_LAUNCH_CHECK();
   }
   const int W4 = O * Cp / 4;
-  k_pair_reduce_final<<<dim3((unsigned)P, (unsigned)((W4 + 31) / 32)), 256, 0, st>>>(cptr, (int)P, W4, partial, d_tab);
+  LCAO_CUDA(launch_pdl(k_pair_reduce_final, dim3((unsigned)P, (unsigned)((W4 + 31) / 32)), 256, 0, st, cptr, (int)P, W4, partial, d_tab));
   LCAO_LAUNCH_CHECK();
   }
   if (d_rb && E > 0) {

@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (!done) {
-      __nanosleep(128);
+      __nanosleep(256);
       if (++spins > (1u << 20)) __trap();
     }
   }

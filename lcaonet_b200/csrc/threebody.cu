@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 8) k_threebody_fwd(
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr,
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
     const int32_t* __restrict__ out_edge, int N, int C, float* __restrict__ tbw) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   __shared__ __align__(16) float s_a[kFwdWarps][32 * 4];  // per-warp coefficient scratch: pair (t, r) at slot t*8 + r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sa = s_a[warp];
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) k_threebody_bwd(
     const int32_t* __restrict__ in_edge, const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr,
     const int32_t* __restrict__ out_edge, int N, int C, const float* __restrict__ d_tbw, const float* __restrict__ dP,
     float* __restrict__ dB, float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   constexpr int NP = NL * (NL + 1) / 2;
   const int NGP = NG - NL + 1;  // rows of the compact two-body gradient dP: [all l < NL | valence slot]
   // per-warp scratch, one slot per out-edge of the current chunk of 32: a_l = w Y_l | norm-path flag | (forces) w Y'_l

@@ -31,29 +31,10 @@
 #include "common.cuh"
 #include "tb_common.cuh"
 #include "tb_async.cuh"
+#include "tb_mma.cuh"
 
 namespace {
 
-// x = hi + lo for the 3xTF32 product: hi = x rounded to TF32 (10 mantissa bits) by an integer add + mask on the FP32
-// bits (round half away from zero; `cvt.rna.tf32.f32` is a 6-instruction sequence on sm_100a and was a third of the first
-// version's instruction count), lo = x - hi exactly.  The tensor core reads the upper 19 bits of an operand register,
-// so lo is handed over as FP32 bits: the part it drops is below 2^-10 |lo| <= 2^-21 |x|.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// d += A B in FP32-equivalent arithmetic: small terms first
-__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                       uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma_tf32(d, al, bh0, bh1);
-  mma_tf32(d, ah, bl0, bl1);
-  mma_tf32(d, ah, bh0, bh1);
-}
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 constexpr int kIB = 8;      // in-edges per forward stage = one K-block of the MMAs
@@ -101,6 +82,7 @@ __global__ void __launch_bounds__(160) k_tb_fwd_mma(
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_edge,
     const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_edge, int N,
     int C, float* __restrict__ tbw) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   constexpr int NP = NL * (NL + 1) / 2;
   extern __shared__ __align__(16) float smem[];
   const FwdPlan pl = fwd_plan(C, NL);
@@ -110,6 +92,7 @@ __global__ void __launch_bounds__(160) k_tb_fwd_mma(
     for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 4); }
   }
   __syncthreads();
+  pdl_wait();  // (launched through launch_pdl: the set-up above may overlap the previous kernel's tail)
   // every CTA walks a CONTIGUOUS range of nodes: CSR pointers and in-edge id lists are read front to back
   const int per_cta = (N + (int)gridDim.x - 1) / (int)gridDim.x;
   const int s_end = min(N, ((int)blockIdx.x + 1) * per_cta);
@@ -318,8 +301,8 @@ int lcao_tb_mma_fwd(const float* B, int32_t NG, const double* gram, const float*
       LCAO_CUDA(cudaFuncSetAttribute(k_tb_fwd_mma<nl>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));      \
       attr_done = true;                                                                                              \
     }                                                                                                                \
-    k_tb_fwd_mma<nl><<<grid, 160, smem, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, \
-                                              (int)N, C, tbw);                                                       \
+    LCAO_CUDA(launch_pdl(k_tb_fwd_mma<nl>, grid, 160, smem, st, B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr, out_edge, \
+                                              (int)N, C, tbw));                                                       \
   }
   switch (NL) {
     case 1: CALL(1) break;

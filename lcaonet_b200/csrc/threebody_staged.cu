@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(160, 3) k_tb_bwd_staged(
     const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_edge, int N,
     int C_rt, int nst, const float* __restrict__ d_tbw, const float* __restrict__ dP, float* __restrict__ dB,
     float* __restrict__ q, float* __restrict__ du_ks, float* __restrict__ du_st) {
+  pdl_trigger();  // (programmatic dependent launch: the next kernel may start its set-up; common.cuh)
   constexpr int NP = NL * (NL + 1) / 2;
   const int C = CT ? CT : C_rt;
   const int NGP = NG - NL + 1;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(160, 3) k_tb_bwd_staged(
   }
   fence_proxy_async();  // the zero fill (generic proxy) is ordered before the bulk copies (async proxy) into the same bytes
   __syncthreads();
+  pdl_wait();  // (launched through launch_pdl: the set-up above may overlap the previous kernel's tail)
   const int per_cta = (N + (int)gridDim.x - 1) / (int)gridDim.x;
   const int s_end = min(N, ((int)blockIdx.x + 1) * per_cta);
 
@@ -493,8 +495,8 @@ int launch_bwd(const float* B, int NG, const double* gram, const float* unit, co
   }
   const int64_t want = (N + 1) / 2;  // at least two nodes per CTA
   const unsigned grid = (unsigned)(want < 148ll * per_sm ? (want > 0 ? want : 1) : 148ll * per_sm);
-  k_tb_bwd_staged<NL, FORCES, CT><<<grid, 160, smem, st>>>(B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr,
-                                                          out_edge, (int)N, C, nst, d_tbw, dP, dB, q, du_ks, du_st);
+  LCAO_CUDA(launch_pdl(k_tb_bwd_staged<NL, FORCES, CT>, grid, 160, smem, st, B, NG, gram, unit, gate, ldg, in_ptr, in_edge, in_src, out_ptr,
+                                                          out_edge, (int)N, C, nst, d_tbw, dP, dB, q, du_ks, du_st));
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

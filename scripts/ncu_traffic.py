@@ -20,7 +20,7 @@ from lcaonet_b200.csrc.build import _digest  # noqa: E402
 
 # kernel-name substring -> C-ABI call, and how many launches of that kernel one call makes
 KERNELS = [("k_tb_fwd_mma", "lcao_threebody_fwd", 1), ("k_threebody_fwd", "lcao_threebody_fwd", 1),
-           ("k_threebody_bwd", "lcao_threebody_bwd", 1), ("k_pair_contract_fwd", "lcao_pair_contract_fwd", 1),
+           ("k_threebody_bwd", "lcao_threebody_bwd", 1), ("k_tb_bwd_staged", "lcao_threebody_bwd", 1), ("k_pair_contract_fwd", "lcao_pair_contract_fwd", 1),
            ("k_pair_reduce_partial", "lcao_pair_contract_bwd", 1), ("k_pair_reduce_final", "lcao_pair_contract_bwd", 1),
            ("k_chunk_ptr", "lcao_pair_contract_bwd", 1), ("k_pair_contract_drb", "lcao_pair_contract_bwd", 1),
            ("k_twobody_fwd", "lcao_twobody_fwd", 1), ("k_twobody_bwd", "lcao_twobody_bwd", 1)]
