@@ -64,10 +64,13 @@ int64_t lcao_launch_count(void);
 const char* lcao_last_error(void);
 
 /* ---- index construction -------------------------------------------------------------------- */
-/* Bucket sort: perm lists item ids grouped by key; ptr has nb+1 entries; scratch: (nb + n) int32.
+/* Bucket sort: perm lists item ids grouped by key; ptr has nb+1 entries; scratch: (nb + n) int32
+ * (stable=2: nb + n + nb * ceil(n / 1024)).
  * stable=1: inside a bucket items are ordered by (sec asc, id asc) (sec may be NULL) — deterministic,
  *           cost sum_b |b|^2, meant for small buckets (edges per node, atoms per graph).
- * stable=0: grouping only (order inside a bucket unspecified) — for few huge buckets (species / pair keys).  Replaces the argsort + CSR
+ * stable=0: grouping only (order inside a bucket unspecified: it depends on the order atomics land in).
+ * stable=2: ORDERED grouping for few huge buckets (species / species-pair keys, nb <= 50000): items of a bucket in
+ *           ascending id, no dependence on atomic ordering — every keyed reduction that walks perm is reproducible.  Replaces the argsort + CSR
  * machinery of torch_sparse.SparseTensor (reference call site lcaonet.py:462) and the implicit
  * sort inside torch_scatter-by-batch (lcaonet.py:293).  Bit-exact, deterministic. */
 int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr,

@@ -248,10 +248,67 @@ __global__ void k_validate(const int64_t* __restrict__ z, int64_t N, int64_t max
   if (bad && (threadIdx.x & 31) == 0) atomicOr(status, bad);
 }
 
+// ---- ORDERED grouping (stable = 2): few huge buckets (species / species-pair keys), items of a bucket in ascending id.
+// Three passes over blocks of kOrdBlock consecutive items: per-block key histograms (shared-memory integer atomics:
+// order independent), an exclusive scan of every key's column over the blocks (starting at the bucket's offset), and a
+// fill in which one warp per block takes its 32-item groups in order and ranks equal keys inside a group with
+// match_any — no position depends on the order in which atomics land, so the permutation (and every keyed reduction
+// that walks it) is reproducible from run to run.
+constexpr int kOrdBlock = 1024;
+
+__global__ void __launch_bounds__(256) k_ord_hist(const int64_t* __restrict__ keys, int64_t n, int nb, int32_t* __restrict__ hist) {
+  extern __shared__ int32_t s_cnt[];
+  for (int k = threadIdx.x; k < nb; k += 256) s_cnt[k] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kOrdBlock;
+  for (int j = threadIdx.x; j < kOrdBlock; j += 256) {
+    const int64_t i = base + j;
+    if (i < n) atomicAdd(&s_cnt[keys[i]], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nb; k += 256) hist[(int64_t)blockIdx.x * nb + k] = s_cnt[k];
+}
+
+__global__ void k_ord_scan(int32_t* __restrict__ hist, int nblk, int nb, const int32_t* __restrict__ ptr) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  int32_t run = ptr[k];
+  for (int b = 0; b < nblk; ++b) {
+    const int32_t t = hist[(int64_t)b * nb + k];
+    hist[(int64_t)b * nb + k] = run;
+    run += t;
+  }
+}
+
+// one warp per block of kOrdBlock items: its 32-item groups in ascending order, keys preloaded
+__global__ void __launch_bounds__(32) k_ord_fill(const int64_t* __restrict__ keys, int64_t n, int nb, const int32_t* __restrict__ hist,
+                                                 int32_t* __restrict__ perm) {
+  extern __shared__ int32_t s_off[];
+  const int lane = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * kOrdBlock;
+  int32_t key[kOrdBlock / 32];
+#pragma unroll
+  for (int g = 0; g < kOrdBlock / 32; ++g) {
+    const int64_t i = base + g * 32 + lane;
+    key[g] = i < n ? (int32_t)keys[i] : -1 - lane;  // (distinct negative keys: no peers)
+  }
+  for (int k = lane; k < nb; k += 32) s_off[k] = hist[(int64_t)blockIdx.x * nb + k];
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < kOrdBlock / 32; ++g) {
+    const int32_t k = key[g];
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    if (k >= 0) perm[s_off[k] + __popc(peers & ((1u << lane) - 1u))] = (int32_t)(base + g * 32 + lane);
+    __syncwarp();
+    if (k >= 0 && lane == __ffs(peers) - 1) s_off[k] += __popc(peers);
+    __syncwarp();
+  }
+}
+
 int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t nb, int32_t* ptr, int32_t* perm,
-                     int32_t* aux, int32_t* scratch, bool stable, cudaStream_t st) {
+                     int32_t* aux, int32_t* scratch, int stable, cudaStream_t st) {
   int32_t* cursor = scratch;     // nb
-  int32_t* tmp = scratch + nb;   // n
+  int32_t* tmp = scratch + nb;   // n  (stable = 2: per-block histograms, nb * ceil(n / kOrdBlock), follow)
   LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
   if (n > 0) {
     k_hist64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, cursor);
@@ -261,6 +318,22 @@ int bucket_sort_impl(const int64_t* keys, const int64_t* sec, int64_t n, int64_t
   LCAO_LAUNCH_CHECK();
   if (n > 0) {
     LCAO_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nb, st));
+    if (stable == 2) {
+      const int nblk = (int)ceil_div64(n, kOrdBlock);
+      int32_t* hist = scratch + nb + n;
+      const size_t smem = sizeof(int32_t) * (size_t)nb;
+      if (smem > 48 * 1024) {
+        LCAO_CUDA(cudaFuncSetAttribute(k_ord_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LCAO_CUDA(cudaFuncSetAttribute(k_ord_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      }
+      k_ord_hist<<<nblk, 256, smem, st>>>(keys, n, (int)nb, hist);
+      LCAO_LAUNCH_CHECK();
+      k_ord_scan<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(hist, nblk, (int)nb, ptr);
+      LCAO_LAUNCH_CHECK();
+      k_ord_fill<<<nblk, 32, smem, st>>>(keys, n, (int)nb, hist, perm);
+      LCAO_LAUNCH_CHECK();
+      return LCAO_OK;
+    }
     k_fill64<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(keys, n, ptr, cursor, stable ? tmp : perm);
     LCAO_LAUNCH_CHECK();
     if (stable) {
@@ -277,7 +350,8 @@ extern "C" int lcao_bucket_sort(const int64_t* keys, const int64_t* sec, int64_t
                                 int32_t* perm, int32_t* scratch, int32_t stable, void* stream) {
   LCAO_REQUIRE(n >= 0 && nb >= 0 && ptr && scratch && (n == 0 || (keys && perm)), "lcao_bucket_sort: bad arguments");
   LCAO_REQUIRE(n < (1ll << 31) && nb < (1ll << 31), "lcao_bucket_sort: sizes must fit int32");
-  return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, stable != 0, (cudaStream_t)stream);
+  LCAO_REQUIRE(stable >= 0 && stable <= 2 && (stable != 2 || nb <= 50000), "lcao_bucket_sort: stable must be 0, 1 or 2 (2: at most 50000 buckets)");
+  return bucket_sort_impl(keys, sec, n, nb, ptr, perm, nullptr, scratch, stable, (cudaStream_t)stream);
 }
 
 extern "C" int lcao_validate_graph(const int64_t* z, int64_t N, int64_t max_z, const int64_t* batch, int64_t n_graph,

@@ -188,7 +188,7 @@ class PairCoeffs:
         whichever of the embedding / interaction parameters or the positions is being differentiated."""
         if self.kptr is None:
             with torch.no_grad():
-                self.kptr, self.kperm = ops.bucket_sort(self.pair, self.table.shape[0], stable=False)
+                self.kptr, self.kperm = ops.bucket_sort(self.pair, self.table.shape[0], stable="ordered")
         return self.kptr, self.kperm
 
     def materialize(self) -> Tensor:
@@ -298,7 +298,7 @@ class LCAOEmbedding(nn.Module):
             xtab, ctab = self._tables(cnt_z, cnt_pair)
         need_bwd = torch.is_grad_enabled() and xtab.requires_grad
         if H % 4 == 0:
-            x = ops.gather_rows(xtab, z, *(ops.bucket_sort(z, Zd, stable=False) if need_bwd else (None, None)))
+            x = ops.gather_rows(xtab, z, *(ops.bucket_sort(z, Zd, stable="ordered") if need_bwd else (None, None)))
         else:
             x = xtab[z]
         O = ctab.shape[1] // self.emb_size_coeff

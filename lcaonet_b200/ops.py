@@ -136,17 +136,19 @@ class GraphIndex:
         return (k, e_ks, e_st) if unit is None else (k, e_ks, e_st, cos)
 
 
-def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None, stable: bool = True):
+def bucket_sort(keys: Tensor, n_buckets: int, sec: Tensor | None = None, stable: bool | str = True):
     """(ptr int32 (nb+1), perm int32 (n)): items grouped by key; stable=True orders each bucket by
-    (sec, id) (small buckets only), stable=False just groups (few huge buckets)."""
+    (sec, id) (small buckets only), stable="ordered" lists the items of a bucket in ascending id (few huge buckets:
+    species / species-pair keys; reproducible), stable=False just groups (order inside a bucket unspecified)."""
     require_cuda(keys)
     keys = keys.contiguous()
     n, dev = keys.numel(), keys.device
     p = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
     perm = torch.empty(n, dtype=torch.int32, device=dev)
-    scratch = torch.empty(n_buckets + n + 1, dtype=torch.int32, device=dev)
+    mode = 2 if stable == "ordered" else (1 if stable else 0)
+    scratch = torch.empty(n_buckets + n + 1 + (n_buckets * ((n + 1023) // 1024) if mode == 2 else 0), dtype=torch.int32, device=dev)
     _call("lcao_bucket_sort", ptr(keys), ptr(sec.contiguous() if sec is not None else None), n, n_buckets, ptr(p),
-          ptr(perm), ptr(scratch), 1 if stable else 0, stream_ptr())
+          ptr(perm), ptr(scratch), mode, stream_ptr())
     return p, perm
 
 
@@ -356,7 +358,7 @@ def _grouping(grouping, pair, P):
     if grouping is not None and grouping[0] is not None:
         return grouping
     with torch.no_grad():
-        return bucket_sort(pair, P, stable=False)
+        return bucket_sort(pair, P, stable="ordered")
 
 
 def pair_contract(tab, pair, grouping, rb, vmask, lgrp, NL, C):
