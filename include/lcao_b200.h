@@ -188,6 +188,14 @@ int lcao_table_norm_bwd(const float* dy, const float* x, const float* counts, co
                         const float* save_rstd, int64_t R, int32_t F, int32_t training, float* dx, float* dgamma,
                         float* dbeta, void* stream);
 
+/* Species-pair coefficient table before its BatchNorm (embed.py:234-249 evaluated on the (Zd x Zd) pair table):
+ * pre[s,t,o,k] = fe[t,o,k] * (1 + za[s,k] + zb[t,k]);  fe (Zd,O,K), za / zb (Zd,K), pre (Zd,Zd,O,K); K % 4 == 0. */
+int lcao_pair_outer_fwd(const float* fe, const float* za, const float* zb, int32_t Zd, int32_t O, int32_t K, float* pre,
+                        void* stream);
+/* gradients of the above (fixed-order sums: deterministic): d_fe (Zd,O,K), d_za (Zd,K), d_zb (Zd,K) */
+int lcao_pair_outer_bwd(const float* dpre, const float* fe, const float* za, const float* zb, int32_t Zd, int32_t O,
+                        int32_t K, float* d_fe, float* d_za, float* d_zb, void* stream);
+
 /* ---- three-body message passing (lcaonet.py:173-189, shbf.py:75-87) --------------------------- */
 /* gate[n,:] = sigmoid(xk[n,:]) per node (lcaonet.py:186-188), computed once per layer */
 int lcao_sigmoid_rows(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t M, int32_t C, void* stream);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "lcao_coeff_gram": [_p, _i32, _i64, _i32, _i32, _p, _p],
     "lcao_table_norm_fwd": [_p, _p, _p, _p, _i64, _i32, C.c_float, C.c_float, _i32, _p, _p, _p, _p, _p, _p, _p],
     "lcao_table_norm_bwd": [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p],
+    "lcao_pair_outer_fwd": [_p, _p, _p, _i32, _i32, _i32, _p, _p],
+    "lcao_pair_outer_bwd": [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p],
     "lcao_sigmoid_rows": [_p, _i64, _p, _i64, _i64, _i32, _p],
     "lcao_threebody_fwd": [_p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p],
     "lcao_threebody_bwd": [_p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p,

@@ -119,6 +119,58 @@ __global__ void __launch_bounds__(kCols * kLanes) k_wbn_bwd(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Species-pair coefficient table before its BatchNorm (embed.py:234-249 on the (Zd x Zd) pair table):
+//   pre[s, t, o, k] = fe[t, o, k] * (1 + za[s, k] + zb[t, k])
+// with fe (Zd, O, K) the per-orbital electron embedding of the TARGET element after f_e, za / zb (Zd, K) the two
+// halves of f_z applied to the source / target element embedding.  One kernel forward, one backward (three fixed-order
+// sums over the 5.6 MB tensor, L2 resident) instead of ~25 broadcast / reduce launches of the eager expression.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_outer_fwd(const float* __restrict__ fe, const float* __restrict__ za,
+                                                        const float* __restrict__ zb, int Zd, int O, int K, float* __restrict__ pre) {
+  const int64_t n4 = (int64_t)Zd * Zd * O * (K / 4);
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const int k = (int)(i % (K / 4)) * 4;
+    const int64_t r = i / (K / 4);
+    const int o = (int)(r % O);
+    const int t = (int)((r / O) % Zd), s = (int)(r / ((int64_t)O * Zd));
+    const float4 f = ldg4(fe + ((int64_t)t * O + o) * K + k), a = ldg4(za + (int64_t)s * K + k), b = ldg4(zb + (int64_t)t * K + k);
+    st4(pre + i * 4, make_float4(f.x * (1.f + a.x + b.x), f.y * (1.f + a.y + b.y), f.z * (1.f + a.z + b.z), f.w * (1.f + a.w + b.w)));
+  }
+}
+
+// thread = one output element (k fastest: coalesced), sequential fixed-order sums: deterministic.
+//   d_fe[t,o,k] = sum_s dpre[s,t,o,k] (1 + za[s,k] + zb[t,k]);  d_za[s,k] = sum_{t,o} dpre fe[t,o,k];  d_zb[t,k] = sum_{s,o} dpre fe[t,o,k]
+__global__ void __launch_bounds__(128) k_pair_outer_bwd(const float* __restrict__ dpre, const float* __restrict__ fe,
+                                                        const float* __restrict__ za, const float* __restrict__ zb, int Zd, int O,
+                                                        int K, float* __restrict__ d_fe, float* __restrict__ d_za,
+                                                        float* __restrict__ d_zb) {
+  const int64_t n_fe = (int64_t)Zd * O * K, n_z = (int64_t)Zd * K;
+  const int64_t i = blockIdx.x * 128ll + threadIdx.x;
+  const int64_t OK = (int64_t)O * K, row = (int64_t)Zd * OK;  // strides of t and s in dpre
+  if (i < n_fe) {
+    const int k = (int)(i % K), t = (int)(i / OK);
+    const float b1 = 1.f + zb[(int64_t)t * K + k];
+    float acc = 0.f;
+    for (int s = 0; s < Zd; ++s) acc = fmaf(dpre[s * row + i], b1 + za[(int64_t)s * K + k], acc);
+    d_fe[i] = acc;
+  } else if (i < n_fe + n_z) {
+    const int64_t j = i - n_fe;
+    const int k = (int)(j % K), s = (int)(j / K);
+    float acc = 0.f;
+    for (int64_t to = 0; to < (int64_t)Zd * O; ++to) acc = fmaf(dpre[s * row + to * K + k], fe[to * K + k], acc);
+    d_za[j] = acc;
+  } else if (i < n_fe + 2 * n_z) {
+    const int64_t j = i - n_fe - n_z;
+    const int k = (int)(j % K), t = (int)(j / K);
+    float acc = 0.f;
+    for (int s = 0; s < Zd; ++s)
+      for (int o = 0; o < O; ++o) acc = fmaf(dpre[s * row + ((int64_t)t * O + o) * K + k], fe[((int64_t)t * O + o) * K + k], acc);
+    d_zb[j] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" int lcao_table_norm_fwd(const float* x, const float* counts, const float* gamma, const float* beta, int64_t R,
@@ -145,6 +197,27 @@ extern "C" int lcao_table_norm_bwd(const float* dy, const float* x, const float*
                "lcao_table_norm_bwd: null buffer");
   k_wbn_bwd<<<(unsigned)((F + kCols - 1) / kCols), dim3(kCols, kLanes), 0, (cudaStream_t)stream>>>(
       dy, x, counts, gamma, save_mean, save_rstd, (int)R, F, training, dx, dgamma, dbeta);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_pair_outer_fwd(const float* fe, const float* za, const float* zb, int32_t Zd, int32_t O, int32_t K, float* pre,
+                                   void* stream) {
+  LCAO_REQUIRE(fe && za && zb && pre && Zd > 0 && O > 0 && K > 0 && K % 4 == 0, "lcao_pair_outer_fwd: need K %% 4 == 0 and non-null buffers");
+  LCAO_REQUIRE(((reinterpret_cast<uintptr_t>(fe) | reinterpret_cast<uintptr_t>(za) | reinterpret_cast<uintptr_t>(zb) |
+                 reinterpret_cast<uintptr_t>(pre)) & 15u) == 0, "lcao_pair_outer_fwd: buffers must be 16-byte aligned");
+  const int64_t n4 = (int64_t)Zd * Zd * O * (K / 4);
+  const int64_t want = ceil_div64(n4, 256);
+  k_pair_outer_fwd<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, (cudaStream_t)stream>>>(fe, za, zb, Zd, O, K, pre);
+  LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+extern "C" int lcao_pair_outer_bwd(const float* dpre, const float* fe, const float* za, const float* zb, int32_t Zd, int32_t O,
+                                   int32_t K, float* d_fe, float* d_za, float* d_zb, void* stream) {
+  LCAO_REQUIRE(dpre && fe && za && zb && d_fe && d_za && d_zb && Zd > 0 && O > 0 && K > 0, "lcao_pair_outer_bwd: null buffer");
+  const int64_t n = (int64_t)Zd * O * K + 2ll * Zd * K;
+  k_pair_outer_bwd<<<(unsigned)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(dpre, fe, za, zb, Zd, O, K, d_fe, d_za, d_zb);
   LCAO_LAUNCH_CHECK();
   return LCAO_OK;
 }

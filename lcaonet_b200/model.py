@@ -238,7 +238,10 @@ class LCAOEmbedding(nn.Module):
         za = ops.linear(coeff_z.contiguous(), wz[:, :K].contiguous())
         zb = ops.linear(coeff_z.contiguous(), wz[:, K:].contiguous())
         fe = _mlp(self.coeff_embed.f_e, coeff_e.contiguous())  # (Zd, O, K), orbitals of the TARGET element
-        pre = fe.unsqueeze(0) * (1.0 + za[:, None, None, :] + zb[None, :, None, :])  # (Zd_s, Zd_t, O, K)
+        if fe.dtype == torch.float32 and K % 4 == 0:
+            pre = ops.pair_outer(fe, za, zb)  # (Zd_s, Zd_t, O, K): one kernel forward, one backward
+        else:
+            pre = fe.unsqueeze(0) * (1.0 + za[:, None, None, :] + zb[None, :, None, :])
         ctab = _weighted_batch_norm(self.coeff_embed.bn, pre.reshape(Zd * Zd, O * K), cnt_pair, self.training)
         return xtab.contiguous(), ctab
 

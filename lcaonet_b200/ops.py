@@ -746,6 +746,35 @@ def table_norm(x, counts, weight, bias, running_mean, running_var, tracked, trai
     return _TableNorm.apply(x, counts, weight, bias, running_mean, running_var, tracked, training, momentum, eps)
 
 
+class _PairOuter(torch.autograd.Function):
+    """pre[s,t,o,k] = fe[t,o,k] * (1 + za[s,k] + zb[t,k]): the species-pair coefficient table before its BatchNorm
+    (embed.py:234-249 on the pair table) as one kernel forward and one backward."""
+
+    @staticmethod
+    def forward(ctx, fe, za, zb):
+        require_cuda(fe, za, zb)
+        fe, za, zb = fe.contiguous(), za.contiguous(), zb.contiguous()
+        Zd, O, K = fe.shape
+        pre = torch.empty(Zd, Zd, O, K, device=fe.device)
+        _call("lcao_pair_outer_fwd", ptr(fe), ptr(za), ptr(zb), Zd, O, K, ptr(pre), stream_ptr())
+        ctx.save_for_backward(fe, za, zb)
+        return pre
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dpre):
+        fe, za, zb = ctx.saved_tensors
+        Zd, O, K = fe.shape
+        dpre = dpre.contiguous()
+        d_fe, d_za, d_zb = torch.empty_like(fe), torch.empty_like(za), torch.empty_like(zb)
+        _call("lcao_pair_outer_bwd", ptr(dpre), ptr(fe), ptr(za), ptr(zb), Zd, O, K, ptr(d_fe), ptr(d_za), ptr(d_zb), stream_ptr())
+        return d_fe, d_za, d_zb
+
+
+def pair_outer(fe, za, zb):
+    return _PairOuter.apply(fe, za, zb)
+
+
 # ------------------------------------------------------------------------------------------------
 # gathers / segment sums
 # ------------------------------------------------------------------------------------------------

@@ -616,6 +616,20 @@ def lcao_table_norm_bwd(dy, x, counts, gamma, smean, srstd, R, Fd, training, dx,
         view(dbeta, Fd).copy_(db)
 
 
+def lcao_pair_outer_fwd(fe, za, zb, Zd, O, K, pre, stream):
+    f, a, b = view(fe, Zd * O, K).reshape(Zd, O, K), view(za, Zd, K), view(zb, Zd, K)
+    view(pre, Zd * Zd * O, K).copy_((f.unsqueeze(0) * (1.0 + a[:, None, None, :] + b[None, :, None, :])).reshape(-1, K))
+
+
+def lcao_pair_outer_bwd(dpre, fe, za, zb, Zd, O, K, d_fe, d_za, d_zb, stream):
+    g = view(dpre, Zd * Zd * O, K).reshape(Zd, Zd, O, K)
+    f, a, b = view(fe, Zd * O, K).reshape(Zd, O, K), view(za, Zd, K), view(zb, Zd, K)
+    view(d_fe, Zd * O, K).copy_((g * (1.0 + a[:, None, None, :] + b[None, :, None, :])).sum(0).reshape(-1, K))
+    gf = g * f.unsqueeze(0)
+    view(d_za, Zd, K).copy_(gf.sum((1, 2)))
+    view(d_zb, Zd, K).copy_(gf.sum((0, 2)))
+
+
 def lcao_act_fwd(X, ldx, Y, ldy, M, Cc, act, stream):
     view(Y, M, Cc, ld=ldy).copy_(_act(view(X, M, Cc, ld=ldx).clone(), act))
 
