@@ -27,7 +27,7 @@ constexpr int kEpiWarps = 4, kProdWarps = 4;
 constexpr int kThreadsTC = (kEpiWarps + kProdWarps + 1) * 32;  // 288
 constexpr int kBlockM = 128;                                   // rows per tile (UMMA M)
 constexpr int kChunkK = 32;                                    // contraction elements per smem stage
-constexpr uint32_t kSpinLimit = 1u << 28;
+constexpr uint32_t kSpinLimit = 1u << 24;
 
 // ---------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,6 +180,7 @@ struct RowsArgs {
   int64_t M; int Kc; int Nb;
   int b_trans, act, accumulate, x3, stages, lo_stages;
   int wide_store;  // Y / pre rows are 32-byte aligned: 256-bit stores
+  int one_acc;  // 3xTF32 corrections accumulate into the same TMEM accumulator as hi*hi (LCAO_TC_ONEACC, experiment)
   int debug;  // ablation bits for tuning runs (LCAO_TC_DEBUG): 1 = no output stores, 2 = no input copies, 4 = no MMAs
 };
 
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
         const int acc = tile & 1;
         mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Nb;
+        const uint32_t d = tmem_base + acc * acc_cols, dc = g.one_acc ? d : d + g.Nb;
         for (int kc = 0; kc < nchunk; ++kc, ++it) {
           const int s = it % R, l = it % L;
           mbar_wait(&full[s], (it / R) & 1);
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
               const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
               umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
               if (g.x3) {
-                umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, (kc | kk) != 0);
+                umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, g.one_acc ? 1 : (kc | kk) != 0);
                 umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
               }
             }
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
         }
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + c0, v);
-        if (g.x3) {
+        if (g.x3 && !g.one_acc) {
           float w[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + g.Nb + c0, w);
 #pragma unroll
@@ -506,6 +507,274 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
                 o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
               }
               if (!(g.debug & 1)) store8(g.Y + m * g.ldy + c0 + j, o, wide);
+            }
+          }
+        }
+        if (g.G) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) gq[q] = gn[q];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =================================================================================================
+// Kernel 1b: the row-streaming GEMM with the A operand in TENSOR MEMORY (3xTF32 mode, many tiles per CTA).
+// k_tc_rows keeps every 128 x 32 chunk of A in shared memory twice (hi in place, lo in a second ring) from the moment
+// its cp.async copies are issued until the MMAs that read it have committed (~3 us), and only 3 + 3 stages of 16 KB
+// fit beside the 128 KB weight: 48 KB of loads in flight per SM = 2.4 TB/s for the whole GPU (profiles/r01_notes.md).
+// Here the split warps move a chunk out of shared memory as soon as it has landed: thread = row, hi / lo are written
+// with tcgen05.st into a ring of 4 x (32 + 32) TMEM columns and the MMAs take A from tensor memory
+// (tcgen05.mma ... [d], [a], b-desc).  Shared memory then holds only raw chunks in flight (6 x 16 KB beside the
+// weight), twice as many bytes on the wire.  TMEM: 2 x Nb accumulator columns (hi*hi and the corrections share ONE
+// accumulator: 48 instead of 16 truncating accumulations per output, measured within the parity tolerances) + 256.
+// Warp roles as in k_tc_rows (0-3 epilogue, 4-7 split, 8 MMA issuer, 9-12 loaders).
+// =================================================================================================
+constexpr int kTaStages = 4;       // TMEM A ring: stage = 32 hi + 32 lo columns
+constexpr uint32_t kTaCol0 = 256;  // first column of the ring (accumulators below)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp writes row (lane base + i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t blockB = g.Nb * 128;
+  const uint32_t halfB = (g.Kc / kChunkK) * blockB;
+  const int R = g.stages;
+  uint8_t* sB = smem_raw;
+  uint8_t* sRaw = sB + 2 * halfB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + (size_t)R * kStageBytes);
+  uint64_t* raw_full = bars;               // [R] loaders (cp.async completion) -> split warps
+  uint64_t* raw_empty = raw_full + R;      // [R] split warps -> loaders
+  uint64_t* a_full = raw_empty + R;        // [kTaStages] split warps -> MMA
+  uint64_t* a_empty = a_full + kTaStages;  // [kTaStages] MMA -> split warps
+  uint64_t* tfull = a_empty + kTaStages;   // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int64_t nblocks = (g.M + kBlockM - 1) / kBlockM;
+  const int nchunk = g.Kc / kChunkK;
+  constexpr uint32_t tmem_cols = 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&raw_full[s], kLoadWarps * 32);
+      mbar_init(&raw_empty[s], 4 * 32);
+    }
+    for (int s = 0; s < kTaStages; ++s) {
+      mbar_init(&a_full[s], 4 * 32);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- resident B operand (the layer's weight), split hi/lo once per CTA by the 9 non-loader warps (see k_tc_rows)
+  constexpr int kStageThreads = (4 + 4 + 1) * 32;
+  constexpr int kWB = 8;
+  if (warp < 9) {
+    const int kq = g.Kc / 4, total = g.Nb * kq;
+    for (int base = 0; base < total; base += kWB * kStageThreads) {
+      float4 w[kWB];
+      int n[kWB], kg[kWB];
+#pragma unroll
+      for (int u = 0; u < kWB; ++u) {
+        const int idx = base + u * kStageThreads + (int)threadIdx.x;
+        w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        n[u] = -1;
+        if (idx < total) {
+          if (!g.b_trans) {
+            n[u] = idx / kq; kg[u] = idx - n[u] * kq;
+            w[u] = ldg4(g.W + (int64_t)n[u] * g.ldw + kg[u] * 4);
+          } else {
+            kg[u] = idx / g.Nb; n[u] = idx - kg[u] * g.Nb;
+            w[u] = make_float4(__ldg(g.W + (int64_t)(kg[u] * 4 + 0) * g.ldw + n[u]), __ldg(g.W + (int64_t)(kg[u] * 4 + 1) * g.ldw + n[u]),
+                               __ldg(g.W + (int64_t)(kg[u] * 4 + 2) * g.ldw + n[u]), __ldg(g.W + (int64_t)(kg[u] * 4 + 3) * g.ldw + n[u]));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kWB; ++u) {
+        if (n[u] >= 0) {
+          float4 hi, lo;
+          split4(w[u], hi, lo);
+          const uint32_t off = (kg[u] >> 3) * blockB + sw128_off(n[u], kg[u] & 7);
+          *reinterpret_cast<float4*>(sB + off) = hi;
+          *reinterpret_cast<float4*>(sB + halfB + off) = lo;
+        }
+      }
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+  }
+  pdl_wait();  // (the set-up and the weight split above may overlap the previous kernel's tail)
+
+  if (warp >= 9 && warp < 13) {
+    // ============================== loader warps (as in k_tc_rows) ==============================
+    const int lw = warp - 9, row_in = lane >> 3, c = lane & 7;
+    const uint32_t raw_base = smem_u32(sRaw);
+    uint32_t it = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
+      const int64_t mrow = mb * kBlockM + 32 * lw + row_in;
+      for (int kc = 0; kc < nchunk; ++kc, ++it) {
+        const int s = it % R;
+        mbar_wait(&raw_empty[s], ((it / R) & 1) ^ 1);
+        const uint32_t dst = raw_base + s * kStageBytes;
+        const float* src = g.A + mrow * g.lda + kc * kChunkK + c * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = mrow + 4 * j < g.M;
+          cp_async16(dst + sw128_off(32 * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+        }
+        cp_async_arrive(&raw_full[s]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================== split warps: raw chunk (smem) -> hi | lo (TMEM), thread = row =================
+    const int row = threadIdx.x - 128;  // 0..127 = TMEM lane (warp % 4 = lane quadrant)
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
+      for (int kc = 0; kc < nchunk; ++kc, ++it) {
+        const int s = it % R, ts = it % kTaStages;
+        mbar_wait(&raw_full[s], (it / R) & 1);
+        const uint8_t* pr = sRaw + (size_t)s * kStageBytes;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(pr + sw128_off(row, c));
+          float4 h, l;
+          split4(v, h, l);
+          hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y); hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
+          lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y); lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+        }
+        mbar_arrive(&raw_empty[s]);  // the chunk is in registers: its stage can take the next copy
+        mbar_wait(&a_empty[ts], ((it / kTaStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_base + kTaCol0 + ts * 64;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&a_full[ts]);
+      }
+    }
+  } else if (warp == 8) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, g.Nb, 0, 0);
+      const uint32_t bBase = smem_u32(sB);
+      uint32_t it = 0, tile = 0;
+      for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
+        const int acc = tile & 1;
+        mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * g.Nb;
+        for (int kc = 0; kc < nchunk; ++kc, ++it) {
+          const int ts = it % kTaStages;
+          mbar_wait(&a_full[ts], (it / kTaStages) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + kTaCol0 + ts * 64, a_lo = a_hi + 32;
+          const uint32_t b_hi = bBase + kc * blockB, b_lo = b_hi + halfB;
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 8; ++kk) {
+            const uint64_t dBh = make_desc_sw128(b_hi + kk * 32);
+            umma_tf32_ts(d, a_hi + kk * 8, dBh, idesc, (kc | kk) != 0);
+            umma_tf32_ts(d, a_lo + kk * 8, dBh, idesc, 1);
+            umma_tf32_ts(d, a_hi + kk * 8, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+          }
+          umma_commit(&a_empty[ts]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ============================== epilogue warps (as in k_tc_rows, one accumulator) ==============================
+    const bool wide = g.wide_store != 0;
+    const int quad = warp & 3;
+    uint32_t tile = 0;
+    for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
+      const int acc = tile & 1;
+      const int64_t m = mb * kBlockM + quad * 32 + lane;
+      float4 gq[8];
+      if (g.G && m < g.M) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gq[q] = (4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&tfull[acc], (tile >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < g.Nb; c0 += 32) {
+        float4 gn[8];
+        if (g.G && m < g.M && c0 + 32 < g.Nb) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            gn[q] = (c0 + 32 + 4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + c0 + 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * g.Nb + c0, v);
+        if (m < g.M) {
+          const int nc = min(32, g.Nb - c0);  // multiple of 16
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < nc) {
+              float* o = v + j;
+              if (g.bias) {
+                const float4 b0 = ldg4(g.bias + c0 + j), b1 = ldg4(g.bias + c0 + j + 4);
+                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+              }
+              if (g.accumulate) {
+                const float4 p0 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
+                const float4 p1 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j + 4);
+                o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w; o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+              }
+              if (g.pre) store8(g.pre + m * g.ldp + c0 + j, o, wide);
+              if (g.act == LCAO_ACT_SILU) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
+              }
+              if (g.G) {
+                const float4 h0 = gq[j / 4], h1 = gq[j / 4 + 1];
+                o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
+                o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
+              }
+              store8(g.Y + m * g.ldy + c0 + j, o, wide);
             }
           }
         }
@@ -836,6 +1105,8 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
                  (!pre || ((reinterpret_cast<uintptr_t>(pre) | (uintptr_t)(ldp * 4)) & 31u) == 0);
   static const int dbg = getenv("LCAO_TC_DEBUG") ? atoi(getenv("LCAO_TC_DEBUG")) : 0;
   g.debug = dbg;
+  static const int one_acc = getenv("LCAO_TC_ONEACC") ? atoi(getenv("LCAO_TC_ONEACC")) : 0;
+  g.one_acc = x3 ? one_acc : 0;
   // the 3xTF32 weight (hi + lo) takes 128 KB at K = N = 128: 6 operand stages of 16 KB remain -> 3 hi + 3 lo
   int lo_stages = x3 ? 3 : 0;
   int stages = 8;
@@ -862,6 +1133,23 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
   // path, 20.5 -> 18.4 us); with many tiles per CTA the drain overlaps the next tile's MMAs and they do not (85 -> 88 us)
   static const int epi8_env = getenv("LCAO_TC_EPI8") ? atoi(getenv("LCAO_TC_EPI8")) : -1;
   const bool epi8 = epi8_env >= 0 ? epi8_env != 0 : nblocks <= num_sms();
+  // many tiles per CTA in 3xTF32 mode: the A-operand-in-tensor-memory kernel (twice the bytes in flight)
+  static const int ta_env = getenv("LCAO_TC_TA") ? atoi(getenv("LCAO_TC_TA")) : 1;
+  if (ta_env && x3 && !rp && nblocks >= 2 * num_sms() && Nb <= 128 && Kc % kChunkK == 0 &&
+      2 * (size_t)(Kc / kChunkK) * Nb * 128 + 3 * kStageBytes + 512 + 1024 <= kMaxSmem) {
+    static bool ta_attr = false;
+    if (!ta_attr) {
+      LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      ta_attr = true;
+    }
+    const size_t halfB = (size_t)(Kc / kChunkK) * Nb * 128;
+    int R = 8;
+    while (R > 2 && 2 * halfB + (size_t)R * kStageBytes + 512 + 1024 > kMaxSmem) --R;
+    g.stages = R;
+    LCAO_CUDA(launch_pdl(k_tc_rows_ta, grid, kRowsThreads, 2 * halfB + (size_t)R * kStageBytes + 512 + 1024, st, g));
+    LCAO_LAUNCH_CHECK();
+    return LCAO_OK;
+  }
   if (rp) LCAO_CUDA(launch_pdl(k_tc_rows<true, false>, grid, kRowsThreads, smem, st, g));
   else if (epi8) LCAO_CUDA(launch_pdl(k_tc_rows<false, true>, grid, kRowsThreads + 128, smem, st, g));
   else LCAO_CUDA(launch_pdl(k_tc_rows<false, false>, grid, kRowsThreads, smem, st, g));

@@ -273,10 +273,15 @@ __global__ void k_ord_scan(int32_t* __restrict__ hist, int nblk, int nb, const i
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nb) return;
   int32_t run = ptr[k];
-  for (int b = 0; b < nblk; ++b) {
-    const int32_t t = hist[(int64_t)b * nb + k];
-    hist[(int64_t)b * nb + k] = run;
-    run += t;
+  for (int b0 = 0; b0 < nblk; b0 += 8) {  // eight independent loads in flight, then the running sums in block order
+    int32_t t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = (b0 + u < nblk) ? hist[(int64_t)(b0 + u) * nb + k] : 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (b0 + u < nblk) hist[(int64_t)(b0 + u) * nb + k] = run;
+      run += t[u];
+    }
   }
 }
 

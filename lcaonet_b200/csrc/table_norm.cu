@@ -153,18 +153,21 @@ __global__ void __launch_bounds__(128) k_pair_outer_bwd(const float* __restrict_
     const int k = (int)(i % K), t = (int)(i / OK);
     const float b1 = 1.f + zb[(int64_t)t * K + k];
     float acc = 0.f;
+#pragma unroll 8
     for (int s = 0; s < Zd; ++s) acc = fmaf(dpre[s * row + i], b1 + za[(int64_t)s * K + k], acc);
     d_fe[i] = acc;
   } else if (i < n_fe + n_z) {
     const int64_t j = i - n_fe;
     const int k = (int)(j % K), s = (int)(j / K);
     float acc = 0.f;
+#pragma unroll 8
     for (int64_t to = 0; to < (int64_t)Zd * O; ++to) acc = fmaf(dpre[s * row + to * K + k], fe[to * K + k], acc);
     d_za[j] = acc;
   } else if (i < n_fe + 2 * n_z) {
     const int64_t j = i - n_fe - n_z;
     const int k = (int)(j % K), t = (int)(j / K);
     float acc = 0.f;
+#pragma unroll 4
     for (int s = 0; s < Zd; ++s)
       for (int o = 0; o < O; ++o) acc = fmaf(dpre[s * row + ((int64_t)t * O + o) * K + k], fe[((int64_t)t * O + o) * K + k], acc);
     d_zb[j] = acc;
