@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
 // accumulator: 48 instead of 16 truncating accumulations per output, measured within the parity tolerances) + 256.
 // Warp roles as in k_tc_rows (0-3 epilogue, 4-7 split, 8 MMA issuer, 9-12 loaders).
 // =================================================================================================
+constexpr int kTaThreads = 15 * 32;  // 8 epilogue + 4 split + 1 MMA + 2 loader warps
 constexpr int kTaStages = 4;       // TMEM A ring: stage = 32 hi + 32 lo columns
 constexpr uint32_t kTaCol0 = 256;  // first column of the ring (accumulators below)
 
@@ -561,9 +562,32 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// the same load as tmem_ld32 without the wait: several loads in flight, then tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g) {
+// CPS = 32-column chunks per pipeline stage (1 or 2).  Every stage costs one round of mbarrier hand-shakes between the
+// loaders, the split warps and the MMA issuer (~0.35 us: with nothing but the hand-shakes left the kernel takes 29 us
+// at M = 252 798 with one chunk per stage, 20 us with two), but the hand-shakes are not the critical path: the full
+// kernel does not get faster with CPS = 2, nor with a second group of split warps taking the odd chunks.  What set
+// the pace after the operand moved to tensor memory was the epilogue (see below); profiles/r02_notes.md.
+template <int CPS>
+__global__ void __launch_bounds__(kTaThreads, 1) k_tc_rows_ta(const RowsArgs g) {
+  // warps: 0-3 epilogue (columns 0-63), 4-7 split, 8 MMA issuer, 9-10 loaders (64 rows each), 11-14 epilogue (columns 64-127)
+  constexpr int kLd = 2;
+  constexpr uint32_t kStB = CPS * kStageBytes;         // bytes of one raw stage
+  constexpr int kTaSt = kTaStages / CPS;               // TMEM ring depth (stage = CPS x (32 hi + 32 lo) columns)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -572,7 +596,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g
   const int R = g.stages;
   uint8_t* sB = smem_raw;
   uint8_t* sRaw = sB + 2 * halfB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + (size_t)R * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + (size_t)R * kStB);
   uint64_t* raw_full = bars;               // [R] loaders (cp.async completion) -> split warps
   uint64_t* raw_empty = raw_full + R;      // [R] split warps -> loaders
   uint64_t* a_full = raw_empty + R;        // [kTaStages] split warps -> MMA
@@ -581,21 +605,21 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g
   uint64_t* tempty = tfull + 2;            // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int64_t nblocks = (g.M + kBlockM - 1) / kBlockM;
-  const int nchunk = g.Kc / kChunkK;
+  const int nchunk = g.Kc / (kChunkK * CPS);  // pipeline stages per tile
   constexpr uint32_t tmem_cols = 512;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < R; ++s) {
-      mbar_init(&raw_full[s], kLoadWarps * 32);
+      mbar_init(&raw_full[s], kLd * 32);
       mbar_init(&raw_empty[s], 4 * 32);
     }
-    for (int s = 0; s < kTaStages; ++s) {
+    for (int s = 0; s < kTaSt; ++s) {
       mbar_init(&a_full[s], 4 * 32);
       mbar_init(&a_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], kEpiWarps * 32);
+      mbar_init(&tempty[a], 2 * kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -645,51 +669,65 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g
   }
   pdl_wait();  // (the set-up and the weight split above may overlap the previous kernel's tail)
 
-  if (warp >= 9 && warp < 13) {
-    // ============================== loader warps (as in k_tc_rows) ==============================
+  if (warp >= 9 && warp < 9 + kLd) {
+    // ============================== loader warps (as in k_tc_rows; 128 / kLd rows each) ==============================
+    constexpr int kRowsPerLd = kBlockM / kLd;
     const int lw = warp - 9, row_in = lane >> 3, c = lane & 7;
     const uint32_t raw_base = smem_u32(sRaw);
     uint32_t it = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
-      const int64_t mrow = mb * kBlockM + 32 * lw + row_in;
+      const int64_t mrow = mb * kBlockM + kRowsPerLd * lw + row_in;
       for (int kc = 0; kc < nchunk; ++kc, ++it) {
         const int s = it % R;
         mbar_wait(&raw_empty[s], ((it / R) & 1) ^ 1);
-        const uint32_t dst = raw_base + s * kStageBytes;
-        const float* src = g.A + mrow * g.lda + kc * kChunkK + c * 4;
+        if (!(g.debug & 2))
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool ok = mrow + 4 * j < g.M;
-          cp_async16(dst + sw128_off(32 * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+        for (int sub = 0; sub < CPS; ++sub) {
+          const uint32_t dst = raw_base + s * kStB + sub * kStageBytes;
+          const float* src = g.A + mrow * g.lda + (kc * CPS + sub) * kChunkK + c * 4;
+#pragma unroll
+          for (int j = 0; j < kRowsPerLd / 4; ++j) {
+            const bool ok = mrow + 4 * j < g.M;
+            cp_async16(dst + sw128_off(kRowsPerLd * lw + 4 * j + row_in, c), ok ? src + (int64_t)4 * j * g.lda : g.A, ok ? 16u : 0u);
+          }
         }
         cp_async_arrive(&raw_full[s]);
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ============================== split warps: raw chunk (smem) -> hi | lo (TMEM), thread = row =================
-    const int row = threadIdx.x - 128;  // 0..127 = TMEM lane (warp % 4 = lane quadrant)
+    const int row = (warp & 3) * 32 + lane;  // 0..127 = TMEM lane (a warp reaches the lane quadrant warp % 4)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x) {
       for (int kc = 0; kc < nchunk; ++kc, ++it) {
-        const int s = it % R, ts = it % kTaStages;
+        const int s = it % R, ts = it % kTaSt;
         mbar_wait(&raw_full[s], (it / R) & 1);
-        const uint8_t* pr = sRaw + (size_t)s * kStageBytes;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(pr + sw128_off(row, c));
-          float4 h, l;
-          split4(v, h, l);
-          hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y); hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
-          lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y); lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+        if (g.debug & 16) {  // (ablation: no split work, no TMEM stores)
+          mbar_arrive(&raw_empty[s]);
+          mbar_wait(&a_empty[ts], ((it / kTaSt) & 1) ^ 1);
+          mbar_arrive(&a_full[ts]);
+          continue;
         }
-        mbar_arrive(&raw_empty[s]);  // the chunk is in registers: its stage can take the next copy
-        mbar_wait(&a_empty[ts], ((it / kTaStages) & 1) ^ 1);
+        mbar_wait(&a_empty[ts], ((it / kTaSt) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t ta = tmem_base + lane_base + kTaCol0 + ts * 64;
-        tmem_st32(ta, hi);
-        tmem_st32(ta + 32, lo);
+#pragma unroll
+        for (int sub = 0; sub < CPS; ++sub) {
+          const uint8_t* pr = sRaw + (size_t)s * kStB + sub * kStageBytes;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(pr + sw128_off(row, c));
+            float4 h, l;
+            split4(v, h, l);
+            hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y); hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
+            lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y); lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+          }
+          const uint32_t ta = tmem_base + lane_base + kTaCol0 + (ts * CPS + sub) * 64;
+          tmem_st32(ta, hi);
+          tmem_st32(ta + 32, lo);
+        }
+        mbar_arrive(&raw_empty[s]);  // the stage is in registers / tensor memory: it can take the next copies
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&a_full[ts]);
@@ -707,17 +745,20 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g
         tc_fence_after();
         const uint32_t d = tmem_base + acc * g.Nb;
         for (int kc = 0; kc < nchunk; ++kc, ++it) {
-          const int ts = it % kTaStages;
-          mbar_wait(&a_full[ts], (it / kTaStages) & 1);
+          const int ts = it % kTaSt;
+          mbar_wait(&a_full[ts], (it / kTaSt) & 1);
           tc_fence_after();
-          const uint32_t a_hi = tmem_base + kTaCol0 + ts * 64, a_lo = a_hi + 32;
-          const uint32_t b_hi = bBase + kc * blockB, b_lo = b_hi + halfB;
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / 8; ++kk) {
-            const uint64_t dBh = make_desc_sw128(b_hi + kk * 32);
-            umma_tf32_ts(d, a_hi + kk * 8, dBh, idesc, (kc | kk) != 0);
-            umma_tf32_ts(d, a_lo + kk * 8, dBh, idesc, 1);
-            umma_tf32_ts(d, a_hi + kk * 8, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+          for (int sub = 0; sub < CPS; ++sub) {
+            const uint32_t a_hi = tmem_base + kTaCol0 + (ts * CPS + sub) * 64, a_lo = a_hi + 32;
+            const uint32_t b_hi = bBase + (kc * CPS + sub) * blockB, b_lo = b_hi + halfB;
+#pragma unroll
+            for (int kk = 0; kk < ((g.debug & 4) ? 0 : kChunkK / 8); ++kk) {
+              const uint64_t dBh = make_desc_sw128(b_hi + kk * 32);
+              umma_tf32_ts(d, a_hi + kk * 8, dBh, idesc, (kc | sub | kk) != 0);
+              umma_tf32_ts(d, a_lo + kk * 8, dBh, idesc, 1);
+              umma_tf32_ts(d, a_hi + kk * 8, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+            }
           }
           umma_commit(&a_empty[ts]);
         }
@@ -725,66 +766,73 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_rows_ta(const RowsArgs g
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ============================== epilogue warps (as in k_tc_rows, one accumulator) ==============================
+  } else if (warp < 4 || warp >= 9 + kLd) {
+    // ============================== epilogue warps ==============================
+    // Eight warps, two per TMEM lane quadrant (warp % 4), 64 columns each.  A warp issues both of its 32-column TMEM
+    // loads at once, waits once, RELEASES the accumulator (the tile is in registers: the MMAs of the tile after next
+    // can start) and only then finishes the rows (bias, accumulate, pre-activation, SiLU, SiLU' factor) and stores
+    // them with 256-bit stores.  (Four warps draining 32 columns at a time with a wait per load took 7.3 k cycles per
+    // tile against 4.9 k for the whole main loop: the epilogue, not the operand pipeline, set the pace.)
     const bool wide = g.wide_store != 0;
     const int quad = warp & 3;
+    const int c_begin = warp >= 9 + kLd ? 64 : 0, c_end = min(g.Nb, c_begin + 64);
     uint32_t tile = 0;
+    long long t_wait = 0, t_work = 0;  // (LCAO_TC_DEBUG & 64: cycles spent waiting for a finished tile / draining it)
     for (int64_t mb = blockIdx.x; mb < nblocks; mb += gridDim.x, ++tile) {
       const int acc = tile & 1;
+      const long long tq0 = clock64();
       const int64_t m = mb * kBlockM + quad * 32 + lane;
-      float4 gq[8];
-      if (g.G && m < g.M) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) gq[q] = (4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < g.Nb; c0 += 32) {
-        float4 gn[8];
-        if (g.G && m < g.M && c0 + 32 < g.Nb) {
+      const long long tq1 = clock64();
+      float v[2][32];
+      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * g.Nb;
+      if (c_begin < c_end) tmem_ld32_nw(t0 + c_begin, v[0]);
+      if (c_begin + 32 < c_end) tmem_ld32_nw(t0 + c_begin + 32, v[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (m < g.M && !(g.debug & 8)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            gn[q] = (c0 + 32 + 4 * q < g.Nb) ? ldg4(g.G + m * g.ldg + c0 + 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * g.Nb + c0, v);
-        if (m < g.M) {
-          const int nc = min(32, g.Nb - c0);  // multiple of 16
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = c_begin + 32 * h;
+          if (c0 < c_end) {
+            const int nc = min(32, c_end - c0);  // multiple of 16
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < nc) {
-              float* o = v + j;
-              if (g.bias) {
-                const float4 b0 = ldg4(g.bias + c0 + j), b1 = ldg4(g.bias + c0 + j + 4);
-                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-              }
-              if (g.accumulate) {
-                const float4 p0 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
-                const float4 p1 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j + 4);
-                o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w; o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
-              }
-              if (g.pre) store8(g.pre + m * g.ldp + c0 + j, o, wide);
-              if (g.act == LCAO_ACT_SILU) {
+            for (int j = 0; j < 32; j += 8) {
+              if (j < nc) {
+                float* o = v[h] + j;
+                if (g.bias) {
+                  const float4 b0 = ldg4(g.bias + c0 + j), b1 = ldg4(g.bias + c0 + j + 4);
+                  o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+                }
+                if (g.accumulate) {
+                  const float4 p0 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j);
+                  const float4 p1 = *reinterpret_cast<const float4*>(g.Y + m * g.ldy + c0 + j + 4);
+                  o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w; o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+                }
+                if (g.pre) store8(g.pre + m * g.ldp + c0 + j, o, wide);
+                if (g.act == LCAO_ACT_SILU) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
+                  for (int q = 0; q < 8; ++q) o[q] = silu_fast(o[q]);
+                }
+                if (g.G) {
+                  const float4 h0 = ldg4(g.G + m * g.ldg + c0 + j), h1 = ldg4(g.G + m * g.ldg + c0 + j + 4);
+                  o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
+                  o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
+                }
+                if (!(g.debug & 1)) store8(g.Y + m * g.ldy + c0 + j, o, wide);
               }
-              if (g.G) {
-                const float4 h0 = gq[j / 4], h1 = gq[j / 4 + 1];
-                o[0] *= silu_grad_fast(h0.x); o[1] *= silu_grad_fast(h0.y); o[2] *= silu_grad_fast(h0.z); o[3] *= silu_grad_fast(h0.w);
-                o[4] *= silu_grad_fast(h1.x); o[5] *= silu_grad_fast(h1.y); o[6] *= silu_grad_fast(h1.z); o[7] *= silu_grad_fast(h1.w);
-              }
-              store8(g.Y + m * g.ldy + c0 + j, o, wide);
             }
           }
         }
-        if (g.G) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) gq[q] = gn[q];
-        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      t_wait += tq1 - tq0;
+      t_work += clock64() - tq1;
+    }
+    if ((g.debug & 64) && threadIdx.x == 0) {
+      g.Y[2 * blockIdx.x] = (float)t_wait / (float)max(1u, tile);
+      g.Y[2 * blockIdx.x + 1] = (float)t_work / (float)max(1u, tile);
     }
   }
   tc_fence_before();
@@ -1139,14 +1187,19 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
       2 * (size_t)(Kc / kChunkK) * Nb * 128 + 3 * kStageBytes + 512 + 1024 <= kMaxSmem) {
     static bool ta_attr = false;
     if (!ta_attr) {
-      LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows_ta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      LCAO_CUDA(cudaFuncSetAttribute(k_tc_rows_ta<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
       ta_attr = true;
     }
     const size_t halfB = (size_t)(Kc / kChunkK) * Nb * 128;
+    static const int cps_env = getenv("LCAO_TC_TA_CPS") ? atoi(getenv("LCAO_TC_TA_CPS")) : 1;  // (2 measured slower in the step: 9.47 vs 9.34 ms)
+    const int cps = (cps_env == 2 && Kc % (2 * kChunkK) == 0) ? 2 : 1;
     int R = 8;
-    while (R > 2 && 2 * halfB + (size_t)R * kStageBytes + 512 + 1024 > kMaxSmem) --R;
+    while (R > 2 && 2 * halfB + (size_t)R * cps * kStageBytes + 512 + 1024 > kMaxSmem) --R;
     g.stages = R;
-    LCAO_CUDA(launch_pdl(k_tc_rows_ta, grid, kRowsThreads, 2 * halfB + (size_t)R * kStageBytes + 512 + 1024, st, g));
+    const size_t smem_ta = 2 * halfB + (size_t)R * cps * kStageBytes + 512 + 1024;
+    if (cps == 2) LCAO_CUDA(launch_pdl(k_tc_rows_ta<2>, grid, kTaThreads, smem_ta, st, g));
+    else LCAO_CUDA(launch_pdl(k_tc_rows_ta<1>, grid, kTaThreads, smem_ta, st, g));
     LCAO_LAUNCH_CHECK();
     return LCAO_OK;
   }
