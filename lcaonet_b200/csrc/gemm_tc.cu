@@ -860,6 +860,7 @@ struct WgradArgs {
   float* db;
   float* part;     // per-CTA partial sums: [grid][Kx][128] then [grid][128] column sums (deterministic two-stage reduction)
   int64_t M; int Kx; int x3, raw_stages, op_stages;
+  int one_acc;  // 3xTF32 corrections accumulate into the same TMEM chain as hi*hi (LCAO_TC_ONEACC, experiment)
 };
 
 __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g) {
@@ -1025,7 +1026,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
         const int acc = fl & 1;
         mbar_wait(&tempty[acc], ((fl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Kx;
+        const uint32_t d = tmem_base + acc * acc_cols, dc = g.one_acc ? d : d + g.Kx;
         const int64_t c_stop = min(c_end, c + kFlush);
         for (int first = 1; c < c_stop; ++c, ++it) {
           const int s = it % S;
@@ -1037,7 +1038,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
             const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
             umma_tf32(d, dAh, dBh, idesc, !first);
             if (g.x3) {
-              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, !first);
+              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, g.one_acc ? 1 : !first);
               umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
             }
             first = 0;
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
           tmem_ld32(t0 + c0, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
-          if (g.x3) {
+          if (g.x3 && !g.one_acc) {
             tmem_ld32(t0 + g.Kx + c0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
@@ -1079,6 +1080,242 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
     }
     const int n = warp * 32 + lane;
     float* pp = g.part + (size_t)blockIdx.x * g.Kx * 128 + n;   // [cta][j][n]: coalesced over the 128 rows n
+#pragma unroll
+    for (int j = 0; j < kMaxCols; ++j)
+      if (j < g.Kx) pp[(size_t)j * 128] = sum[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =================================================================================================
+// Kernel 2b: the weight gradient with MN-MAJOR operands (3xTF32 mode).
+// tcgen05 accepts MN-major shared-memory operands for TF32 (instruction descriptor bits 15 / 16), and both operands of
+// dW = dY^T X are MN-major as they lie in HBM: A[n, m] = dY[m, n] has n contiguous, B[k, m] = X[m, k] has k contiguous.
+// So the loaders write every 32-row chunk straight into the canonical MN-major SWIZZLE_128B layout
+//   [32-column block][4-row group][row in group: 128 B, 32-byte chunks XOR-swizzled by the row]   (LBO = 4096, SBO = 512)
+// and the MMAs read that raw tile as the `hi` operand (the tensor core ignores the 13 low mantissa bits: exactly the
+// hi = trunc(x) of the split).  The transform warps only compute lo = trunc(x - trunc(x)) — an elementwise pass into a
+// second ring — and the column sums of dY: no register transposes, no `hi` stores, and the per-chunk latency of the
+// transform stage (the bottleneck of k_tc_wgrad: ~1.5 us x 53 chunks per CTA at E rows) drops accordingly.
+// Shared memory: Rr raw stages (dY + X chunk, in flight / being multiplied) + S lo stages.
+// =================================================================================================
+// MN-major 32-bit operands take the 32-byte-base 128 B swizzle (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1,
+// Layout_MN_SW128_32B_Atom): atom = 4 K-rows of 128 B (32 elements along M / N), the 32-byte chunk q of row r stored at
+// chunk q ^ (r & 3); 4-row groups SBO = 512 B apart, 32-element blocks LBO apart.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: next 32-element block along M / N
+  d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: next 4-row group along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// byte offset of the 16-byte piece `pc` (4 columns) of row m (0..31) inside a 32-row MN-major chunk tile
+__device__ __forceinline__ uint32_t mn_off(int m, int pc) {
+  const int p = pc & 7;
+  return (uint32_t)(pc >> 3) * 4096u + (uint32_t)(m >> 2) * 512u + (uint32_t)(m & 3) * 128u + (uint32_t)(((p >> 1) ^ (m & 3)) << 5) +
+         (uint32_t)(p & 1) * 16u;
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad_mn(const WgradArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rawA = kChunkK * 512, rawB = kChunkK * g.Kx * 4;  // chunk tile bytes (dY: 128 cols, X: Kx cols)
+  const uint32_t raw_stage = rawA + rawB;
+  const int Rr = g.raw_stages, S = g.op_stages;
+  uint8_t* sRaw = smem_raw;
+  uint8_t* sLo = sRaw + (size_t)Rr * raw_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + (size_t)S * raw_stage);
+  uint64_t* raw_full = bars;             // [Rr] loaders -> transform
+  uint64_t* raw_empty = raw_full + Rr;   // [Rr] MMA (commit) -> loaders
+  uint64_t* op_full = raw_empty + Rr;    // [S]  transform -> MMA  (lo written; implies the raw stage has landed)
+  uint64_t* op_empty = op_full + S;      // [S]  MMA (commit) -> transform
+  uint64_t* tfull = op_empty + S;        // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_cs = reinterpret_cast<float*>(tmem_slot + 4);  // [4][128] column-sum partials of the transform warps
+  constexpr int kFlush = 8;
+  const uint32_t acc_cols = 2 * g.Kx;
+  const uint32_t need_cols = 2 * acc_cols;
+  const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
+  const int64_t nchunks = (g.M + kChunkK - 1) / kChunkK;
+  const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c_beg = min(nchunks, (int64_t)blockIdx.x * per), c_end = min(nchunks, c_beg + per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Rr; ++s) {
+      mbar_init(&raw_full[s], kLoadWarps * 32);
+      mbar_init(&raw_empty[s], 1);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&op_full[s], 4 * 32);
+      mbar_init(&op_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // (set-up above overlaps the previous kernel's tail)
+  if (c_beg >= c_end) {  // more CTAs than row chunks: nothing to do but to zero this CTA's partial slot
+    for (int i = threadIdx.x; i < g.Kx * 128; i += kRowsThreads) g.part[(size_t)blockIdx.x * g.Kx * 128 + i] = 0.f;
+    if (g.db && threadIdx.x < 128) g.part[(size_t)gridDim.x * g.Kx * 128 + (size_t)blockIdx.x * 128 + threadIdx.x] = 0.f;
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
+
+  if (warp >= 9) {
+    // ============================== loader warps ==============================
+    // lanes 0-7 of an instruction copy 8 consecutive 16-byte pieces of one row (one 128-byte line of HBM) into the 128-byte
+    // row (m & 7) of one 32-column block: conflict free on both sides
+    const int lw = warp - 9, r_in = lane >> 3, pl = lane & 7;
+    const uint32_t raw_base = smem_u32(sRaw);
+    const int pgB = g.Kx / 32;  // 32-column blocks per X row
+    uint32_t it = 0;
+    for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+      const int s = it % Rr;
+      mbar_wait(&raw_empty[s], ((it / Rr) & 1) ^ 1);
+      const uint32_t dA = raw_base + s * raw_stage, dB = dA + rawA;
+      const int64_t m0 = c * kChunkK;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // dY: 32 rows x 4 blocks; this warp: rows 8 lw .. 8 lw + 7
+        const int r = 8 * lw + (j & 1) * 4 + r_in, pg = j >> 1;
+        const bool ok = m0 + r < g.M;
+        cp_async16(dA + mn_off(r, pg * 8 + pl), ok ? g.dY + (m0 + r) * g.ldy + (pg * 8 + pl) * 4 : g.dY, ok ? 16u : 0u);
+      }
+      for (int j = 0; j < 2 * pgB; ++j) {
+        const int r = 8 * lw + (j & 1) * 4 + r_in, pg = j >> 1;
+        const bool ok = m0 + r < g.M;
+        cp_async16(dB + mn_off(r, pg * 8 + pl), ok ? g.X + (m0 + r) * g.ldx + (pg * 8 + pl) * 4 : g.X, ok ? 16u : 0u);
+      }
+      cp_async_arrive(&raw_full[s]);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================== transform warps: lo = trunc(x - trunc(x)), column sums of dY ==============
+    // thread t: 4-column piece pc = t % 32 (+ 32 j for X), rows m = t / 32 + 4 i  ->  every thread sums the same four
+    // dY columns over its rows; the four warps' partials meet once at the end
+    const int t = threadIdx.x - 128;
+    const int pc0 = t & 31, mrow = t >> 5;
+    const int pgB = g.Kx / 32;
+    float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t it = 0;
+    for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+      const int r = it % Rr, s = it % S;
+      mbar_wait(&raw_full[r], (it / Rr) & 1);
+      mbar_wait(&op_empty[s], ((it / S) & 1) ^ 1);
+      const uint8_t* rA = sRaw + (size_t)r * raw_stage;
+      const uint8_t* rB = rA + rawA;
+      uint8_t* lA = sLo + (size_t)s * raw_stage;
+      uint8_t* lB = lA + rawA;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = mn_off(mrow + 4 * i, pc0);
+        const float4 v = *reinterpret_cast<const float4*>(rA + off);
+        colsum = make_float4(colsum.x + v.x, colsum.y + v.y, colsum.z + v.z, colsum.w + v.w);
+        float4 hi, lo;
+        split4(v, hi, lo);
+        *reinterpret_cast<float4*>(lA + off) = lo;
+      }
+      for (int jb = 0; jb < pgB / 4 + (pgB % 4 != 0); ++jb) {  // X: Kx / 4 pieces per row, 32 per pass
+        const int pc = pc0 + 32 * jb;
+        if (pc < g.Kx / 4) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t off = mn_off(mrow + 4 * i, pc);
+            float4 hi, lo;
+            split4(*reinterpret_cast<const float4*>(rB + off), hi, lo);
+            *reinterpret_cast<float4*>(lB + off) = lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&op_full[s]);
+    }
+    if (g.db) {
+      *reinterpret_cast<float4*>(s_cs + mrow * 128 + pc0 * 4) = colsum;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (t < 32) {
+        const float4 a = *reinterpret_cast<const float4*>(s_cs + t * 4), b = *reinterpret_cast<const float4*>(s_cs + 128 + t * 4);
+        const float4 c2 = *reinterpret_cast<const float4*>(s_cs + 256 + t * 4), d2 = *reinterpret_cast<const float4*>(s_cs + 384 + t * 4);
+        *reinterpret_cast<float4*>(g.part + (size_t)gridDim.x * g.Kx * 128 + (size_t)blockIdx.x * 128 + t * 4) =
+            make_float4((a.x + b.x) + (c2.x + d2.x), (a.y + b.y) + (c2.y + d2.y), (a.z + b.z) + (c2.z + d2.z), (a.w + b.w) + (c2.w + d2.w));
+      }
+    }
+  } else if (warp == 8) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBlockM, g.Kx, 1, 1);  // both operands MN-major
+      const uint32_t rbase = smem_u32(sRaw), lbase = smem_u32(sLo);
+      uint32_t it = 0, fl = 0;
+      for (int64_t c = c_beg; c < c_end; ++fl) {
+        const int acc = fl & 1;
+        mbar_wait(&tempty[acc], ((fl >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * acc_cols, dc = d + g.Kx;
+        const int64_t c_stop = min(c_end, c + kFlush);
+        for (int first = 1; c < c_stop; ++c, ++it) {
+          const int r = it % Rr, s = it % S;
+          mbar_wait(&op_full[s], (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = rbase + r * raw_stage, b_hi = a_hi + rawA, a_lo = lbase + s * raw_stage, b_lo = a_lo + rawA;
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 8; ++kk) {  // two 4-row groups per MMA
+            const uint64_t dAh = make_desc_mn_sw128(a_hi + kk * 1024), dBh = make_desc_mn_sw128(b_hi + kk * 1024);
+            umma_tf32(d, dAh, dBh, idesc, !first);
+            umma_tf32(dc, make_desc_mn_sw128(a_lo + kk * 1024), dBh, idesc, !first);
+            umma_tf32(dc, dAh, make_desc_mn_sw128(b_lo + kk * 1024), idesc, 1);
+            first = 0;
+          }
+          umma_commit(&raw_empty[r]);
+          umma_commit(&op_empty[s]);
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps (as in k_tc_wgrad) ==============================
+    constexpr int kMaxCols = 128;
+    float sum[kMaxCols];
+#pragma unroll
+    for (int j = 0; j < kMaxCols; ++j) sum[j] = 0.f;
+    const int64_t n_flush = (c_end - c_beg + kFlush - 1) / kFlush;
+    for (int64_t fl = 0; fl < n_flush; ++fl) {
+      const int acc = fl & 1;
+      mbar_wait(&tfull[acc], (fl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols;
+#pragma unroll
+      for (int c0 = 0; c0 < kMaxCols; c0 += 32) {
+        if (c0 < g.Kx) {
+          float v[32];
+          tmem_ld32(t0 + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
+          tmem_ld32(t0 + g.Kx + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c0 + j] += v[j];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+    const int n = warp * 32 + lane;
+    float* pp = g.part + (size_t)blockIdx.x * g.Kx * 128 + n;
 #pragma unroll
     for (int j = 0; j < kMaxCols; ++j)
       if (j < g.Kx) pp[(size_t)j * 128] = sum[j];
@@ -1235,6 +1472,8 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
   WgradArgs g{};
   g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db; g.part = part;
   g.M = M; g.Kx = Kx; g.x3 = x3;
+  static const int one_acc_w = getenv("LCAO_TC_ONEACC") ? atoi(getenv("LCAO_TC_ONEACC")) : 0;
+  g.one_acc = x3 ? one_acc_w : 0;
   g.op_stages = 2;
   int raw_stages = 6;
   while (raw_stages > 2 && wgrad_smem(Kx, x3, raw_stages, g.op_stages) > kMaxSmem) --raw_stages;
@@ -1245,6 +1484,23 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
     attr_set = true;
   }
   const unsigned grid = wgrad_grid(M);
+  static const int mn_env = getenv("LCAO_TC_WGRAD_MN") ? atoi(getenv("LCAO_TC_WGRAD_MN")) : 0;  // (experiment: correct, 91-95 us vs 85 us at E rows)
+  if (mn_env && x3 && Kx % 32 == 0) {
+    // MN-major operands: raw stages (dY + X chunk) are the `hi` operands, lo stages beside them
+    static bool mn_attr = false;
+    if (!mn_attr) {
+      LCAO_CUDA(cudaFuncSetAttribute(k_tc_wgrad_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      mn_attr = true;
+    }
+    const size_t stage = (size_t)kChunkK * (512 + Kx * 4);
+    static const int s_env = getenv("LCAO_TC_WGRAD_S") ? atoi(getenv("LCAO_TC_WGRAD_S")) : 3;
+    int S = s_env >= 2 && s_env <= 4 ? s_env : 3, Rr = 8;
+    while (Rr > 2 && (size_t)(Rr + S) * stage + 2048 + 1024 + 1024 > kMaxSmem) --Rr;
+    if (Rr < 3) { S = 2; Rr = 8; while (Rr > 2 && (size_t)(Rr + S) * stage + 2048 + 1024 + 1024 > kMaxSmem) --Rr; }
+    g.raw_stages = Rr;
+    g.op_stages = S;
+    LCAO_CUDA(launch_pdl(k_tc_wgrad_mn, grid, kRowsThreads, (size_t)(Rr + S) * stage + 2048 + 1024 + 1024, st, g));
+  } else
   LCAO_CUDA(launch_pdl(k_tc_wgrad, grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st, g));
   LCAO_LAUNCH_CHECK();
   LCAO_CUDA(launch_pdl(k_wgrad_reduce, Kx + (db ? 1 : 0), 1024, 0, st, (const float*)part, (int)grid, Kx, dW, ldw, db));
