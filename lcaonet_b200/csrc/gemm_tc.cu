@@ -861,6 +861,7 @@ struct WgradArgs {
   float* part;     // per-CTA partial sums: [grid][Kx][128] then [grid][128] column sums (deterministic two-stage reduction)
   int64_t M; int Kx; int x3, raw_stages, op_stages;
   int one_acc;  // 3xTF32 corrections accumulate into the same TMEM chain as hi*hi (LCAO_TC_ONEACC, experiment)
+  int debug_timing;  // LCAO_TC_DEBUG & 64: CTA 0 prints where its transform warps / MMA issuer wait
 };
 
 __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g) {
@@ -955,10 +956,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
     const int ngB = g.Kx / 4;
     float4 colsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     uint32_t it = 0;
+    long long tw_raw = 0, tw_op = 0, tw_work = 0;  // (LCAO_TC_DEBUG & 64: where the transform stage spends its cycles)
     for (int64_t c = c_beg; c < c_end; ++c, ++it) {
       const int r = it % Rr, s = it % S;
+      const long long q0 = clock64();
       mbar_wait(&raw_full[r], (it / Rr) & 1);
+      const long long q1 = clock64();
       mbar_wait(&op_empty[s], ((it / S) & 1) ^ 1);
+      const long long q2 = clock64();
+      tw_raw += q1 - q0; tw_op += q2 - q1;
       const uint8_t* rA = sRaw + (size_t)r * (rawA + rawB);
       const uint8_t* rB = rA + rawA;
       uint8_t* oA = sOp + (size_t)s * op_stage;
@@ -1002,7 +1008,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
       fence_proxy_async();
       mbar_arrive(&op_full[s]);
       mbar_arrive(&raw_empty[r]);
+      tw_work += clock64() - q2;
     }
+    if (g.debug_timing && blockIdx.x == 0 && t == 0)
+      printf("wgrad transform (CTA 0, %d chunks): per chunk waits raw %lld, waits op stage %lld, works %lld cycles\n", (int)it,
+             tw_raw / max(1u, it), tw_op / max(1u, it), tw_work / max(1u, it));
     if (g.db) {  // the 8 row-group threads (kg = lane & 7) of a column group are adjacent lanes
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -1022,15 +1032,21 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
       const uint32_t idesc = make_idesc(kBlockM, g.Kx, 0, 0);
       const uint32_t base = smem_u32(sOp);
       uint32_t it = 0, fl = 0;
+      long long tm_wait = 0, tm_acc = 0;
+      const long long tm0 = clock64();
       for (int64_t c = c_beg; c < c_end; ++fl) {
         const int acc = fl & 1;
+        const long long qa = clock64();
         mbar_wait(&tempty[acc], ((fl >> 1) & 1) ^ 1);
+        tm_acc += clock64() - qa;
         tc_fence_after();
         const uint32_t d = tmem_base + acc * acc_cols, dc = g.one_acc ? d : d + g.Kx;
         const int64_t c_stop = min(c_end, c + kFlush);
         for (int first = 1; c < c_stop; ++c, ++it) {
           const int s = it % S;
+          const long long qb = clock64();
           mbar_wait(&op_full[s], (it / S) & 1);
+          tm_wait += clock64() - qb;
           tc_fence_after();
           const uint32_t a_hi = base + s * op_stage, a_lo = a_hi + opA, b_hi = a_hi + (g.x3 ? 2 : 1) * opA, b_lo = b_hi + opB;
 #pragma unroll
@@ -1047,6 +1063,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
         }
         umma_commit(&tfull[acc]);
       }
+      if (g.debug_timing && blockIdx.x == 0)
+        printf("wgrad MMA issuer (CTA 0): %lld cycles in all, waits for operands %lld, for a free accumulator %lld\n", clock64() - tm0, tm_wait, tm_acc);
     }
     __syncwarp();
   } else {
@@ -1474,6 +1492,8 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
   g.M = M; g.Kx = Kx; g.x3 = x3;
   static const int one_acc_w = getenv("LCAO_TC_ONEACC") ? atoi(getenv("LCAO_TC_ONEACC")) : 0;
   g.one_acc = x3 ? one_acc_w : 0;
+  static const int dbg_w = getenv("LCAO_TC_DEBUG") ? atoi(getenv("LCAO_TC_DEBUG")) : 0;
+  g.debug_timing = (dbg_w & 64) != 0;
   g.op_stages = 2;
   int raw_stages = 6;
   while (raw_stages > 2 && wgrad_smem(Kx, x3, raw_stages, g.op_stages) > kMaxSmem) --raw_stages;
