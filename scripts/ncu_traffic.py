@@ -23,7 +23,11 @@ KERNELS = [("k_tb_fwd_mma", "lcao_threebody_fwd", 1), ("k_threebody_fwd", "lcao_
            ("k_threebody_bwd", "lcao_threebody_bwd", 1), ("k_tb_bwd_staged", "lcao_threebody_bwd", 1), ("k_pair_contract_fwd", "lcao_pair_contract_fwd", 1),
            ("k_pair_reduce_partial", "lcao_pair_contract_bwd", 1), ("k_pair_reduce_final", "lcao_pair_contract_bwd", 1),
            ("k_chunk_ptr", "lcao_pair_contract_bwd", 1), ("k_pair_contract_drb", "lcao_pair_contract_bwd", 1),
-           ("k_twobody_fwd", "lcao_twobody_fwd", 1), ("k_twobody_bwd", "lcao_twobody_bwd", 1)]
+           ("k_twobody_fwd", "lcao_twobody_fwd", 1), ("k_twobody_bwd", "lcao_twobody_bwd", 1),
+           # dense layers: one C-ABI call = one (or, for 256 outputs, two) launches of the kernels below; the per-launch
+           # figure of these calls is the step total divided by the calls per step (LINEAR_CALLS)
+           ("k_tc_wgrad", "lcao_linear_wgrad", 1), ("k_wgrad_reduce", "lcao_linear_wgrad", 1), ("k_tiny_wgrad", "lcao_linear_wgrad", 1)]
+LINEAR_CALLS = {"lcao_linear_wgrad": 27}  # calls per training step of the default model (bench.py `kernels`)
 
 
 def main():
@@ -48,8 +52,11 @@ def main():
                 break
     out = {"_source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of `{' '.join(sys.argv[1:])}` (bench.py step, config 2)",
            "csrc_digest": _digest()}
+    steps = max(agg["lcao_threebody_bwd"]["launches"].values()) / 3.0 if "lcao_threebody_bwd" in agg else 1.0  # 3 layers per step
     for call, a in sorted(agg.items()):
         n_calls = max(a["launches"].values())  # every kernel of a call is launched once per call
+        if call in LINEAR_CALLS:
+            n_calls = int(round(steps * LINEAR_CALLS[call]))
         out[call] = {"dram_bytes_per_launch": int(a["bytes"] / n_calls), "ncu_us_per_launch": round(a["us"] / n_calls, 1),
                      "calls_profiled": n_calls, "kernels": dict(a["launches"])}
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
