@@ -78,7 +78,7 @@ __device__ __forceinline__ int bfly4_index(int lane) { return ((lane >> 4) & 1) 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NL, bool FORCES, int CT>
-__global__ void __launch_bounds__(160, 3) k_tb_bwd_staged(
+__global__ void __launch_bounds__(160, FORCES ? 3 : 4) k_tb_bwd_staged(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_edge,
     const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_edge, int N,
@@ -481,11 +481,13 @@ int launch_bwd(const float* B, int NG, const double* gram, const float* unit, co
                const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
                const int32_t* out_edge, int64_t N, int C, const float* d_tbw, const float* dP, float* dB, float* q,
                float* du_ks, float* du_st, cudaStream_t st) {
-  static const int per_sm = knob("LCAO_TBS_GRID", 12, 1, 128);
+  static const int per_sm = knob("LCAO_TBS_GRID", 16, 1, 128);
   static const int nst_env = knob("LCAO_TBS_STAGES", 0, 2, 4);
-  // ring depth: as many stages (<= 4) as keep three CTAs resident per SM (227 KB of shared memory, 1 KB reserved per CTA)
+  // ring depth: as many stages (<= 4) as keep four CTAs (energy path: 96 registers) or three (forces: 128) resident per
+  // SM (227 KB of shared memory, 1 KB reserved per CTA).  Four CTAs with a two-stage ring measured 0.402 ms against
+  // 0.428 ms for three with four stages; the forces variant spills at 96 registers and stays at three.
   int nst = 4;
-  while (nst > 2 && sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total > 74 * 1024) --nst;
+  while (nst > 2 && sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total > (FORCES ? 74 : 55) * 1024) --nst;
   if (nst_env) nst = nst_env;
   const size_t smem = sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total;
   static bool attr_done = false;
