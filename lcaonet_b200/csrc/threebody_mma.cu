@@ -38,7 +38,7 @@ namespace {
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 constexpr int kIB = 8;      // in-edges per forward stage = one K-block of the MMAs
-constexpr int kStages = 3;  // forward ring depth: two items in flight behind the one being multiplied
+constexpr int kStages = 2;  // forward ring depth: one item in flight behind the one being multiplied (41 KB per CTA: five CTAs per SM; three stages / three CTAs: 0.248 ms, two / five: 0.190 ms, one: 0.203 ms)
 
 // Shared-memory plan of one forward CTA: two stages of
 //   [B rows | gate rows | unit + edge id of the in-edges | their Gram rows | unit + edge id of the 16 out-edge rows | item]
@@ -290,7 +290,7 @@ int grid_knob(const char* env, int dflt, int lo, int hi) {
 int lcao_tb_mma_fwd(const float* B, int32_t NG, const double* gram, const float* unit, const float* gate, int64_t ldg,
                     const int32_t* in_ptr, const int32_t* in_edge, const int32_t* in_src, const int32_t* out_ptr,
                     const int32_t* out_edge, int64_t N, int32_t C, int32_t NL, float* tbw, cudaStream_t st) {
-  static const int per_sm = grid_knob("LCAO_TBM_GRID_FWD", 24, 1, 128);
+  static const int per_sm = grid_knob("LCAO_TBM_GRID_FWD", 40, 1, 128);
   const int64_t want = (N + 1) / 2;  // at least two nodes per CTA
   const unsigned grid = (unsigned)(want < 148ll * per_sm ? (want > 0 ? want : 1) : 148ll * per_sm);
   const size_t smem = sizeof(float) * (size_t)fwd_plan(C, NL).total;
