@@ -30,6 +30,7 @@ namespace {
 constexpr int kSlots = 4;   // in-edges per item = consumer warps
 constexpr int kJC = 32;     // out-edges per chunk (lane <-> out-edge in the coefficient phase)
 constexpr int kGtBufs = 2;  // resident d_tbw chunks
+constexpr bool kForces4 = false;  // forces variant with pair groups of 4 only (96 registers): measured 0.64 vs 0.575 ms, the CTA count stays at three (shared memory)
 enum { kFirst = 1, kLast = 2, kEnd = 4, kNodeFirst = 8, kNodeLast = 16 };
 
 // Shared-memory plan (floats).  [0, 128 B): mbarriers full_in[4] | empty_in[4] | full_gt[2].
@@ -78,7 +79,7 @@ __device__ __forceinline__ int bfly4_index(int lane) { return ((lane >> 4) & 1) 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NL, bool FORCES, int CT>
-__global__ void __launch_bounds__(160, FORCES ? 3 : 4) k_tb_bwd_staged(
+__global__ void __launch_bounds__(160, (FORCES && !kForces4) ? 3 : 4) k_tb_bwd_staged(
     const float* __restrict__ B, int NG, const double* __restrict__ gram, const float* __restrict__ unit,
     const float* __restrict__ gate, int64_t ldg, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_edge,
     const int32_t* __restrict__ in_src, const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_edge, int N,
@@ -401,8 +402,12 @@ __global__ void __launch_bounds__(160, FORCES ? 3 : 4) k_tb_bwd_staged(
           }
         };
         int j0 = 0;
-        for (; j0 + 4 < nO; j0 += 8) group(std::integral_constant<int, 8>{}, j0);
-        if (j0 < nO) group(std::integral_constant<int, 4>{}, j0);
+        if constexpr (FORCES && kForces4) {  // (groups of 4 only: 32 fewer registers, see launch_bwd)
+          for (; j0 < nO; j0 += 4) group(std::integral_constant<int, 4>{}, j0);
+        } else {
+          for (; j0 + 4 < nO; j0 += 8) group(std::integral_constant<int, 8>{}, j0);
+          if (j0 < nO) group(std::integral_constant<int, 4>{}, j0);
+        }
       }
       if (flags & kLast) {
         // ---- finish this in-edge
@@ -487,7 +492,7 @@ int launch_bwd(const float* B, int NG, const double* gram, const float* unit, co
   // SM (227 KB of shared memory, 1 KB reserved per CTA).  Four CTAs with a two-stage ring measured 0.402 ms against
   // 0.428 ms for three with four stages; the forces variant spills at 96 registers and stays at three.
   int nst = 4;
-  while (nst > 2 && sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total > (FORCES ? 74 : 55) * 1024) --nst;
+  while (nst > 2 && sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total > ((FORCES && !kForces4) ? 74 : 55) * 1024) --nst;
   if (nst_env) nst = nst_env;
   const size_t smem = sizeof(float) * (size_t)bwd_plan(C, NL, FORCES, nst).total;
   static bool attr_done = false;
