@@ -517,8 +517,13 @@ def profile_step(ops, fn, reps=3):
         elif name == "lcao_linear_wgrad":
             M, K, Nout = a[9], a[10], a[11]
             meta = (4 * M * (K + Nout), 2 * M * K * Nout)
-        if meta and os.environ.get("LCAO_BENCH_SHAPES"):
-            name = f"{name}[M={a[8] if name != 'lcao_linear_wgrad' else a[9]},K={a[9] if name != 'lcao_linear_wgrad' else a[10]},N={a[10] if name != 'lcao_linear_wgrad' else a[11]}]"
+        elif name == "lcao_linear_wgrad_deferred":  # stage 1 of a weight gradient whose reduction is batched at the end
+            M, K, Nout = a[6], a[7], a[8]
+            name, meta = "lcao_linear_wgrad", (4 * M * (K + Nout), 2 * M * K * Nout)
+        elif name == "lcao_wgrad_reduce_batch":  # ... and that batched second stage: time of the family, not a call of its own
+            name, meta = "lcao_linear_wgrad", "extra"
+        if meta and meta != "extra" and os.environ.get("LCAO_BENCH_SHAPES"):
+            name = f"{name}[M={M},K={K},N={Nout}]"
         records.append((name, e0, e1, meta))
 
     ops._call = timed_call
@@ -532,6 +537,8 @@ def profile_step(ops, fn, reps=3):
     for name, e0, e1, meta in records:
         d = out.setdefault(name, {"ms": 0.0, "calls": 0, "bytes": 0, "flops": 0})
         d["ms"] += e0.elapsed_time(e1) / reps
+        if meta == "extra":
+            continue
         d["calls"] += 1
         if meta:
             d["bytes"] += meta[0] / reps

@@ -275,6 +275,16 @@ int lcao_linear_dgrad_act(const float* dY, int64_t ldy, const float* W, const fl
 /* dW (Nout,K) += (dY * act'(H))^T X ; db (Nout) += its column sums (db nullable).  dW/db zeroed by the caller. */
 int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* X, int64_t ldx,
                       float* dW, float* db, int64_t M, int32_t K, int32_t Nout, int32_t mode, float* scratch, void* stream);
+/* lcao_linear_wgrad (act = none) with its second stage — the deterministic sum of the per-CTA partial tiles into dW / db
+ * — DEFERRED to lcao_wgrad_reduce_batch: a training step needs its weight gradients only at the optimizer, so the ~30
+ * small reduction launches of a backward pass become one.  desc: HOST buffer of 6 int64 per 128-column pass
+ * (ceil(Nout / 128) passes); *n_desc: descriptors written (0: the shape took the CUDA-core kernel and dW is final).
+ * scratch: lcao_linear_bwd_scratch(...) floats PER PASS; it must stay untouched until the batch reduction has run. */
+int lcao_linear_wgrad_deferred(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int64_t M,
+                               int32_t K, int32_t Nout, int32_t mode, float* scratch, int64_t* desc, int32_t* n_desc,
+                               void* stream);
+/* dW / db += the partial tiles of n deferred weight gradients (descriptors from lcao_linear_wgrad_deferred, HOST memory) */
+int lcao_wgrad_reduce_batch(const int64_t* desc, int32_t n, void* stream);
 /* number of floats of `scratch` the two calls above need for these arguments (0 when the act' factor is fused
  * into the tcgen05 prologue).  Pass X = NULL / dX = NULL for the call that will not be made. */
 int64_t lcao_linear_bwd_scratch(const float* dY, int64_t ldy, const float* H, int64_t ldh, int32_t act, const float* W,

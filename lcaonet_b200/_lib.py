@@ -70,6 +70,8 @@ SIGNATURES = {
     "lcao_linear_dgrad": [_p, _i64, _p, _i64, _i32, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "lcao_linear_dgrad_act": [_p, _i64, _p, _p, _i64, _i32, _p, _i64, _i64, _i32, _i32, _i32, _p],
     "lcao_linear_wgrad": [_p, _i64, _p, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _p],
+    "lcao_linear_wgrad_deferred": [_p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p],
+    "lcao_wgrad_reduce_batch": [_p, _i32, _p],
     "lcao_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p],
     "lcao_act_fwd": [_p, _i64, _p, _i64, _i64, _i32, _i32, _p],
 }

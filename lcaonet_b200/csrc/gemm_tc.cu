@@ -1368,6 +1368,32 @@ __global__ void __launch_bounds__(1024) k_wgrad_reduce(const float* __restrict__
   }
 }
 
+// stage 2 for SEVERAL weight gradients in one launch (blockIdx.y = gradient): a training step's weight gradients are only
+// needed by the optimizer, so their stage-1 partials can wait and be summed together (31 launches of ~7 us -> one).
+struct WgradDesc { const float* part; float* dW; float* db; int64_t ldw; int ncta, Kx; };
+constexpr int kMaxWgradBatch = 32;
+struct WgradBatch { WgradDesc d[kMaxWgradBatch]; };
+__global__ void __launch_bounds__(1024) k_wgrad_reduce_batch(const WgradBatch b) {
+  __shared__ float s_p[8][128];
+  pdl_trigger();
+  pdl_wait();
+  const WgradDesc& g = b.d[blockIdx.y];
+  const int j = blockIdx.x, n = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  if (j > g.Kx || (j == g.Kx && !g.db)) return;
+  const bool bias_row = j >= g.Kx;
+  const float* src = bias_row ? g.part + (size_t)g.ncta * g.Kx * 128 + n : g.part + (size_t)j * 128 + n;
+  const size_t stride = bias_row ? 128 : (size_t)g.Kx * 128;
+  float acc = 0.f;
+  for (int c = ty; c < g.ncta; c += 8) acc += src[(size_t)c * stride];
+  s_p[ty][n] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    const float t = ((s_p[0][n] + s_p[1][n]) + (s_p[2][n] + s_p[3][n])) + ((s_p[4][n] + s_p[5][n]) + (s_p[6][n] + s_p[7][n]));
+    if (bias_row) g.db[n] += t;
+    else g.dW[(int64_t)n * g.ldw + j] += t;
+  }
+}
+
 constexpr size_t kMaxSmem = 227 * 1024;
 
 int num_sms() {
@@ -1486,7 +1512,7 @@ int64_t lcao_tc_wgrad_scratch(int64_t M, int Kx) { return (int64_t)wgrad_grid(M)
 
 // dW (128 rows of the weight gradient, row stride ldw) += dY[:, 0:128]^T X[:, 0:Kx]
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
-                  int Kx, int x3, float* part, cudaStream_t st) {
+                  int Kx, int x3, float* part, cudaStream_t st, int64_t* defer_desc) {
   WgradArgs g{};
   g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.dW = dW; g.ldw = ldw; g.db = db; g.part = part;
   g.M = M; g.Kx = Kx; g.x3 = x3;
@@ -1523,7 +1549,32 @@ int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, flo
   } else
   LCAO_CUDA(launch_pdl(k_tc_wgrad, grid, kRowsThreads, wgrad_smem(Kx, x3, raw_stages, g.op_stages), st, g));
   LCAO_LAUNCH_CHECK();
+  if (defer_desc) {  // stage 2 is left to lcao_wgrad_reduce_batch: {part, dW, db, ldw, ncta, Kx}
+    defer_desc[0] = (int64_t)(uintptr_t)part; defer_desc[1] = (int64_t)(uintptr_t)dW; defer_desc[2] = (int64_t)(uintptr_t)db;
+    defer_desc[3] = ldw; defer_desc[4] = (int64_t)grid; defer_desc[5] = Kx;
+    return LCAO_OK;
+  }
   LCAO_CUDA(launch_pdl(k_wgrad_reduce, Kx + (db ? 1 : 0), 1024, 0, st, (const float*)part, (int)grid, Kx, dW, ldw, db));
   LCAO_LAUNCH_CHECK();
+  return LCAO_OK;
+}
+
+// sums the partial tiles of n deferred weight gradients (descriptors of 6 int64 written by lcao_tc_wgrad) into their dW / db
+int lcao_tc_wgrad_reduce_batch(const int64_t* desc, int n, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += kMaxWgradBatch) {
+    WgradBatch b{};
+    const int m = n - i0 < kMaxWgradBatch ? n - i0 : kMaxWgradBatch;
+    int kmax = 0;
+    for (int i = 0; i < m; ++i) {
+      const int64_t* d = desc + 6 * (int64_t)(i0 + i);
+      b.d[i].part = reinterpret_cast<const float*>((uintptr_t)d[0]);
+      b.d[i].dW = reinterpret_cast<float*>((uintptr_t)d[1]);
+      b.d[i].db = reinterpret_cast<float*>((uintptr_t)d[2]);
+      b.d[i].ldw = d[3]; b.d[i].ncta = (int)d[4]; b.d[i].Kx = (int)d[5];
+      kmax = b.d[i].Kx > kmax ? b.d[i].Kx : kmax;
+    }
+    LCAO_CUDA(launch_pdl(k_wgrad_reduce_batch, dim3((unsigned)(kmax + 1), (unsigned)m), 1024, 0, st, b));
+    LCAO_LAUNCH_CHECK();
+  }
   return LCAO_OK;
 }

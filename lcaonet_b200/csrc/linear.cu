@@ -14,8 +14,9 @@ int lcao_tc_rows(const float* A, int64_t lda, const float* W, int64_t ldw, int b
                  int64_t ldg, float* Y, int64_t ldy, float* pre, int64_t ldp, int64_t M, int Kc, int Nb, int act,
                  int accumulate, int x3, cudaStream_t st);
 bool lcao_tc_wgrad_ok(int64_t M, int Kx, int64_t ldy, int64_t ldx, const void* dY, const void* X);
+int lcao_tc_wgrad_reduce_batch(const int64_t* desc, int n, cudaStream_t st);
 int lcao_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int64_t ldw, float* db, int64_t M,
-                  int Kx, int x3, float* part, cudaStream_t st);
+                  int Kx, int x3, float* part, cudaStream_t st, int64_t* defer_desc);
 int64_t lcao_tc_wgrad_scratch(int64_t M, int Kx);
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -156,8 +157,39 @@ extern "C" int lcao_linear_wgrad(const float* dY, int64_t ldy, const float* H, i
   LCAO_REQUIRE(scratch, "lcao_linear_wgrad: scratch of lcao_linear_bwd_scratch() floats is needed (per-CTA partial tiles)");
   for (int n0 = 0; n0 < Nout; n0 += 128) {
     int rc = lcao_tc_wgrad(dY + n0, ldy, X, ldx, dW + (int64_t)n0 * K, K, db ? db + n0 : nullptr, M, K,
-                           mode == LCAO_GEMM_TF32X3, part, st);
+                           mode == LCAO_GEMM_TF32X3, part, st, nullptr);
     if (rc) return rc;
   }
   return LCAO_OK;
+}
+
+// The same with the second stage (the sum of the per-CTA partial tiles into dW / db) DEFERRED: a training step needs its
+// weight gradients only at the optimizer, so the ~30 small reduction launches of a backward pass can be one
+// (lcao_wgrad_reduce_batch).  desc (HOST memory, 6 int64 per 128-column pass, Nout / 128 passes) receives the
+// descriptors, *n_desc their number — 0 when the shape took the CUDA-core kernel, which finishes dW at once.  scratch:
+// lcao_linear_bwd_scratch() floats PER PASS, and it must stay untouched until lcao_wgrad_reduce_batch has run.
+extern "C" int lcao_linear_wgrad_deferred(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db,
+                                          int64_t M, int32_t K, int32_t Nout, int32_t mode, float* scratch, int64_t* desc,
+                                          int32_t* n_desc, void* stream) {
+  LCAO_REQUIRE(desc && n_desc, "lcao_linear_wgrad_deferred: null descriptor buffer");
+  *n_desc = 0;
+  if (M == 0 || K == 0 || Nout == 0) return LCAO_OK;
+  LCAO_REQUIRE(dY && X && dW, "lcao_linear_wgrad_deferred: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!wgrad_tc(dY, ldy, X, ldx, M, K, Nout, mode)) return lcao_simt_linear_wgrad(dY, ldy, X, ldx, dW, db, M, K, Nout, st);
+  LCAO_REQUIRE(scratch, "lcao_linear_wgrad_deferred: scratch is needed (per-CTA partial tiles of every pass)");
+  const int64_t per_pass = lcao_tc_wgrad_scratch(M, K);
+  for (int n0 = 0; n0 < Nout; n0 += 128) {
+    int rc = lcao_tc_wgrad(dY + n0, ldy, X, ldx, dW + (int64_t)n0 * K, K, db ? db + n0 : nullptr, M, K,
+                           mode == LCAO_GEMM_TF32X3, scratch + (n0 / 128) * per_pass, st, desc + 6 * (int64_t)*n_desc);
+    if (rc) return rc;
+    *n_desc += 1;
+  }
+  return LCAO_OK;
+}
+
+extern "C" int lcao_wgrad_reduce_batch(const int64_t* desc, int32_t n, void* stream) {
+  if (n <= 0) return LCAO_OK;
+  LCAO_REQUIRE(desc, "lcao_wgrad_reduce_batch: null descriptors");
+  return lcao_tc_wgrad_reduce_batch(desc, n, (cudaStream_t)stream);
 }

@@ -497,6 +497,25 @@ def _lin_dgrad_act(dy, ldy, M, w, pre_in, dx, ldx, st, act=ACT_SILU):
     _call("lcao_linear_dgrad_act", ptr(dy), ldy, ptr(w), ptr(pre_in), K, act, ptr(dx), ldx, M, K, Nout, _gemm_mode, st)
 
 
+# Weight gradients that go straight into the parameters' .grad buffers (gradient sinks) are only read by the optimizer /
+# the all-reduce, so the second stage of the tcgen05 weight-gradient kernel (the sum of its per-CTA partial tiles) is
+# deferred: the descriptors pile up here and ONE batched launch at the end of the backward pass (an autograd engine
+# callback) finishes them all.  `defer_wgrad = False` restores one reduction launch per layer.
+defer_wgrad = True
+_pending_wgrad = {"desc": [], "keep": [], "queued": False, "stream": None}
+
+
+def flush_wgrad():
+    """Finish the deferred weight gradients (runs by itself at the end of every backward pass that deferred any)."""
+    p = _pending_wgrad
+    p["queued"] = False
+    if p["desc"]:
+        import ctypes as C
+        arr = (C.c_int64 * len(p["desc"]))(*p["desc"])
+        _call("lcao_wgrad_reduce_batch", arr, len(p["desc"]) // 6, p["stream"])
+    p["desc"], p["keep"], p["stream"] = [], [], None
+
+
 def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
     """dW (+ db) of one layer.  With sinks (the parameters' .grad buffers) the kernels accumulate straight into them
     — the C ABI's `dW +=` contract — and (None, None) is returned: no zero-fill, no separate accumulation pass."""
@@ -505,6 +524,22 @@ def _lin_wgrad(dy, ldy, x, ldx, M, w, has_bias, st, dw_sink=None, db_sink=None):
     db = (db_sink if db_sink is not None else torch.zeros(Nout, device=w.device)) if has_bias else None
     n_scr = int(_lib.load().lcao_linear_bwd_scratch(ptr(dy), ldy, None, 0, ACT_NONE, None, ptr(x), ldx, None, 0, M, K, Nout,
                                                     _gemm_mode))
+    if defer_wgrad and dw_sink is not None and (db_sink is not None or not has_bias) and n_scr:
+        import ctypes as C
+        passes = (Nout + 127) // 128
+        scr = torch.empty(n_scr * passes, device=w.device)
+        desc, nd = (C.c_int64 * (6 * passes))(), C.c_int32(0)
+        _call("lcao_linear_wgrad_deferred", ptr(dy), ldy, ptr(x), ldx, ptr(dw), ptr(db), M, K, Nout, _gemm_mode, ptr(scr), desc,
+              C.byref(nd), st)
+        if nd.value:
+            p = _pending_wgrad
+            p["desc"].extend(desc[: 6 * nd.value])
+            p["keep"].append((scr, dw, db))  # the partial tiles and their targets stay alive until the flush
+            p["stream"] = st
+            if not p["queued"]:
+                torch.autograd.Variable._execution_engine.queue_callback(flush_wgrad)
+                p["queued"] = True
+        return None, None
     scr = torch.empty(n_scr, device=w.device) if n_scr else None
     _call("lcao_linear_wgrad", ptr(dy), ldy, None, 0, ACT_NONE, ptr(x), ldx, ptr(dw), ptr(db), M, K, Nout, _gemm_mode,
           ptr(scr), st)

@@ -26,7 +26,7 @@ KERNELS = [("k_tb_fwd_mma", "lcao_threebody_fwd", 1), ("k_threebody_fwd", "lcao_
            ("k_twobody_fwd", "lcao_twobody_fwd", 1), ("k_twobody_bwd", "lcao_twobody_bwd", 1),
            # dense layers: one C-ABI call = one (or, for 256 outputs, two) launches of the kernels below; the per-launch
            # figure of these calls is the step total divided by the calls per step (LINEAR_CALLS)
-           ("k_tc_wgrad", "lcao_linear_wgrad", 1), ("k_wgrad_reduce", "lcao_linear_wgrad", 1), ("k_tiny_wgrad", "lcao_linear_wgrad", 1)]
+           ("k_tc_wgrad", "lcao_linear_wgrad", 1), ("k_wgrad_reduce", "lcao_linear_wgrad", 1), ("k_tiny_wgrad", "lcao_linear_wgrad", 1)]  # (k_wgrad_reduce matches k_wgrad_reduce_batch too)
 LINEAR_CALLS = {"lcao_linear_wgrad": 27}  # calls per training step of the default model (bench.py `kernels`)
 
 

@@ -574,6 +574,14 @@ def lcao_linear_wgrad(dY, ldy, H, ldh, act, X, ldx, dW, db, M, K, Nout, mode, sc
         view(db, Nout).add_(d.sum(0))
 
 
+def lcao_linear_wgrad_deferred(dY, ldy, X, ldx, dW, db, M, K, Nout, mode, scratch, desc, n_desc, stream):
+    lcao_linear_wgrad(dY, ldy, None, 0, 0, X, ldx, dW, db, M, K, Nout, mode, scratch, stream)  # finished at once: no descriptors
+
+
+def lcao_wgrad_reduce_batch(desc, n, stream):
+    pass
+
+
 def lcao_table_norm_fwd(x, counts, gamma, beta, R, Fd, eps, momentum, training, rmean, rvar, tracked, y, smean, srstd, stream):
     X = view(x, R, Fd)
     if training:
