@@ -43,10 +43,14 @@ class FlatGradBucket:
 
     def zero(self) -> None:
         """Replaces `zero_grad()`: clears the flat buffer and keeps every `.grad` attached to it."""
+        from . import ops
+        ops._pending_wgrad.update(desc=[], keep=[], queued=False, stream=None)  # (a backward pass that raised may have left entries)
         self.flat.zero_()
         self.attach()
 
     def all_reduce_mean(self) -> None:
+        from . import ops
+        ops.flush_wgrad()  # (no-op unless something is pending: the backward pass flushes its deferred weight gradients itself)
         self.attach()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)

@@ -163,3 +163,28 @@ def test_device_collated_stream_feeds_fresh_batches():
         for (n, p), q in zip(m_plain.named_parameters(), m_fast.parameters()):
             if p.grad is not None and float(p.grad.norm()) > 0:
                 assert rel_l2(q.grad, p.grad) < 2e-5, (step, n)
+
+
+def test_deferred_weight_gradient_reduction_is_bitwise_the_same(monkeypatch):
+    """With gradient sinks the second stage of the tcgen05 weight gradients is deferred to one batched launch at the end
+    of the backward pass (ops.defer_wgrad); same partial tiles, same summation order: the flat gradient bucket must be
+    bitwise equal to the one-reduction-per-layer path (interaction blocks), and nothing may be left pending."""
+    g = qm9_like_batch(96, seed=3).to(DEV)
+    flats = []
+    for defer in (True, False):
+        monkeypatch.setattr(ops, "defer_wgrad", defer)
+        torch.manual_seed(5)
+        model = LCAONet(cutoff=5.0, cutoff_net="polynomial").to(DEV).train()
+        model.side_effect_keys = False
+        bucket = FlatGradBucket(model)
+        for _ in range(2):
+            bucket.zero()
+            out = model(g)
+            ((out - g["y"].reshape(out.shape)) ** 2).mean().backward()
+            assert not ops._pending_wgrad["desc"] and not ops._pending_wgrad["queued"]
+        flats.append({n: t.clone() for n, t in _bucket_grads(model, bucket).items()})
+    for n in flats[0]:
+        if n.startswith("int_layers."):
+            assert torch.equal(flats[0][n], flats[1][n]), n
+        else:
+            assert rel_l2(flats[0][n], flats[1][n]) < 1e-4, n
