@@ -27,7 +27,7 @@ constexpr int kEpiWarps = 4, kProdWarps = 4;
 constexpr int kThreadsTC = (kEpiWarps + kProdWarps + 1) * 32;  // 288
 constexpr int kBlockM = 128;                                   // rows per tile (UMMA M)
 constexpr int kChunkK = 32;                                    // contraction elements per smem stage
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr uint32_t kSpinLimit = 1u << 28;  // (several seconds: under programmatic dependent launch a CTA may poll while the previous kernel drains)
 
 // ---------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

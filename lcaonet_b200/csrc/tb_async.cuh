@@ -22,8 +22,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// Bounded waits: a lost copy / protocol bug must trap instead of hanging the GPU, but a legitimate wait can be long —
+// under programmatic dependent launch the producer warp sits in griddepcontrol.wait until the WHOLE previous kernel has
+// finished while the consumers already poll their `full` barriers.  The bound is therefore wall-clock time (20 s).
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
+  unsigned long long t0 = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -32,13 +41,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1u << 22)) __trap();  // (bounded: a lost copy must not hang the GPU)
+    if (!done && (++spins & 0xfffu) == 0) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20000000000ull) __trap();
+    }
   }
 }
 // the same with a back-off between polls: for a producer warp that is ahead of its consumers and must not take issue
 // slots from them while it waits
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
+  unsigned long long t0 = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -49,7 +63,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "memory");
     if (!done) {
       __nanosleep(256);
-      if (++spins > (1u << 20)) __trap();
+      if ((++spins & 0xffu) == 0) {
+        const unsigned long long t = global_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 20000000000ull) __trap();
+      }
     }
   }
 }
