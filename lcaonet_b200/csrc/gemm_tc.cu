@@ -65,6 +65,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One lane of a converged warp.  The MMA-issuer warps run their loops with all 32 lanes (uniform control flow, so the
+// descriptors / addresses stay in uniform registers) and elect a lane only around the tcgen05 instruction itself: issued
+// from inside an `if (lane == 0)` region the compiler had to broadcast every operand through R2UR waterfall loops,
+// ~18 instructions per MMA, and the single issuing thread (128 cycles per MMA) was slower than the tensor core (~69).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -409,8 +418,8 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
       }
     }
   } else if (warp == 8) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (all lanes run the loop; one is elected per instruction) ==============
+    {
       const uint32_t idesc = make_idesc(kBlockM, g.Nb, 0, 0);
       const uint32_t hiBase = smem_u32(sHi), loBase = smem_u32(sLo), bBase = smem_u32(sB);
       uint32_t it = 0, tile = 0;
@@ -426,20 +435,25 @@ __global__ void __launch_bounds__(EPI8 ? kRowsThreads + 128 : kRowsThreads, 1) k
           const uint32_t a_hi = hiBase + s * kStageBytes, a_lo = loBase + l * kStageBytes;
           const uint32_t b_hi = bBase + kc * blockB, b_lo = b_hi + halfB;
           if (!(g.debug & 4)) {
+            const uint64_t dAh0 = make_desc_sw128(a_hi), dBh0 = make_desc_sw128(b_hi), dAl0 = make_desc_sw128(a_lo), dBl0 = make_desc_sw128(b_lo);
 #pragma unroll
             for (int kk = 0; kk < kChunkK / 8; ++kk) {
-              const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
-              umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
-              if (g.x3) {
-                umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, g.one_acc ? 1 : (kc | kk) != 0);
-                umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+              const uint64_t dAh = dAh0 + 2 * kk, dBh = dBh0 + 2 * kk, dAl = dAl0 + 2 * kk, dBl = dBl0 + 2 * kk;
+              if (elect_one()) {
+                umma_tf32(d, dAh, dBh, idesc, (kc | kk) != 0);
+                if (g.x3) {
+                  umma_tf32(dc, dAl, dBh, idesc, g.one_acc ? 1 : (kc | kk) != 0);
+                  umma_tf32(dc, dAh, dBl, idesc, 1);
+                }
               }
             }
           }
-          umma_commit(&hi_empty[s]);
-          if (g.x3) umma_commit(&lo_empty[l]);
+          if (elect_one()) {
+            umma_commit(&hi_empty[s]);
+            if (g.x3) umma_commit(&lo_empty[l]);
+          }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -734,8 +748,8 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tc_rows_ta(const RowsArgs g) 
       }
     }
   } else if (warp == 8) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (all lanes run the loop; one is elected per instruction) ==============
+    {
       const uint32_t idesc = make_idesc(kBlockM, g.Nb, 0, 0);
       const uint32_t bBase = smem_u32(sB);
       uint32_t it = 0, tile = 0;
@@ -752,17 +766,20 @@ __global__ void __launch_bounds__(kTaThreads, 1) k_tc_rows_ta(const RowsArgs g) 
           for (int sub = 0; sub < CPS; ++sub) {
             const uint32_t a_hi = tmem_base + kTaCol0 + (ts * CPS + sub) * 64, a_lo = a_hi + 32;
             const uint32_t b_hi = bBase + (kc * CPS + sub) * blockB, b_lo = b_hi + halfB;
+            const uint64_t dBh0 = make_desc_sw128(b_hi), dBl0 = make_desc_sw128(b_lo);
 #pragma unroll
             for (int kk = 0; kk < ((g.debug & 4) ? 0 : kChunkK / 8); ++kk) {
-              const uint64_t dBh = make_desc_sw128(b_hi + kk * 32);
-              umma_tf32_ts(d, a_hi + kk * 8, dBh, idesc, (kc | sub | kk) != 0);
-              umma_tf32_ts(d, a_lo + kk * 8, dBh, idesc, 1);
-              umma_tf32_ts(d, a_hi + kk * 8, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+              const uint64_t dBh = dBh0 + 2 * kk, dBl = dBl0 + 2 * kk;  // (+ 32 B per K step: + 2 in the address field)
+              if (elect_one()) {
+                umma_tf32_ts(d, a_hi + kk * 8, dBh, idesc, (kc | sub | kk) != 0);
+                umma_tf32_ts(d, a_lo + kk * 8, dBh, idesc, 1);
+                umma_tf32_ts(d, a_hi + kk * 8, dBl, idesc, 1);
+              }
             }
           }
-          umma_commit(&a_empty[ts]);
+          if (elect_one()) umma_commit(&a_empty[ts]);
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -1027,8 +1044,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
       }
     }
   } else if (warp == 8) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (all lanes run the loop; one is elected per instruction) ==============
+    {
       const uint32_t idesc = make_idesc(kBlockM, g.Kx, 0, 0);
       const uint32_t base = smem_u32(sOp);
       uint32_t it = 0, fl = 0;
@@ -1049,21 +1066,25 @@ __global__ void __launch_bounds__(kRowsThreads, 1) k_tc_wgrad(const WgradArgs g)
           tm_wait += clock64() - qb;
           tc_fence_after();
           const uint32_t a_hi = base + s * op_stage, a_lo = a_hi + opA, b_hi = a_hi + (g.x3 ? 2 : 1) * opA, b_lo = b_hi + opB;
+          // (a K step of 8 tf32 = 32 B inside the swizzled row: + 2 in the descriptor's 16-byte address field)
+          const uint64_t dAh0 = make_desc_sw128(a_hi), dBh0 = make_desc_sw128(b_hi), dAl0 = make_desc_sw128(a_lo), dBl0 = make_desc_sw128(b_lo);
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 8; ++kk) {
-            const uint64_t dAh = make_desc_sw128(a_hi + kk * 32), dBh = make_desc_sw128(b_hi + kk * 32);
-            umma_tf32(d, dAh, dBh, idesc, !first);
-            if (g.x3) {
-              umma_tf32(dc, make_desc_sw128(a_lo + kk * 32), dBh, idesc, g.one_acc ? 1 : !first);
-              umma_tf32(dc, dAh, make_desc_sw128(b_lo + kk * 32), idesc, 1);
+            const uint64_t dAh = dAh0 + 2 * kk, dBh = dBh0 + 2 * kk, dAl = dAl0 + 2 * kk, dBl = dBl0 + 2 * kk;
+            if (elect_one()) {
+              umma_tf32(d, dAh, dBh, idesc, !first);
+              if (g.x3) {
+                umma_tf32(dc, dAl, dBh, idesc, g.one_acc ? 1 : !first);
+                umma_tf32(dc, dAh, dBl, idesc, 1);
+              }
             }
             first = 0;
           }
-          umma_commit(&op_empty[s]);
+          if (elect_one()) umma_commit(&op_empty[s]);
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
       }
-      if (g.debug_timing && blockIdx.x == 0)
+      if (g.debug_timing && blockIdx.x == 0 && lane == 0)
         printf("wgrad MMA issuer (CTA 0): %lld cycles in all, waits for operands %lld, for a free accumulator %lld\n", clock64() - tm0, tm_wait, tm_acc);
     }
     __syncwarp();
