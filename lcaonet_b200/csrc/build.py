@@ -36,7 +36,9 @@ def _digest() -> str:
     for f in names:
         with open(os.path.join(HERE, f), "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # (the include paths are absolute and differ between checkouts of the same tree — e.g. the GPU box's scratch copy —
+    #  so they stay out of the digest: it identifies the SOURCES and the code-generation flags)
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith("-I")).encode())
     return h.hexdigest()
 
 
