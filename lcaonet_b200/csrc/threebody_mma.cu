@@ -69,9 +69,10 @@ enum { kItemFirst = 1, kItemLast = 2, kItemEnd = 4 };
 // forward: CTA = 4 consumer warps (the four 32-channel quarters of C <= 128) + 1 producer warp.
 // Work items = (node, M-tile of <= 16 out-edges, block of <= 8 in-edges), walked in order by the producer, which
 // keeps the copy engine ahead through a ring of kStages stages (full / empty mbarriers): while item n is multiplied,
-// the bulk copies of items n+1 and n+2 are in flight (measured: a B200 SM needs ~100 KB of row gathers in flight to
-// reach the HBM rate, scripts/micro/bulk_copy.cu), and the unit vectors / Gram rows / edge ids of the items after those
-// sit in the producer's registers.  The 128 coefficients of an item are computed one per consumer thread and exchanged
+// the bulk copies of item n+1 are in flight, and the unit vectors / Gram rows / edge ids of the items after it sit in
+// the producer's registers.  The ring is kept SHALLOW (two stages, 41 KB per CTA) so that five CTAs are resident per SM:
+// the bytes in flight (a B200 SM needs ~100 KB of row gathers in flight to reach the HBM rate,
+// scripts/micro/bulk_copy.cu) come from the number of CTAs, and so do the warps that hide each other's latencies.  The 128 coefficients of an item are computed one per consumer thread and exchanged
 // through shared memory in fragment order (one named barrier among the consumers per item).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
